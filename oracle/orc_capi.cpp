@@ -1,0 +1,257 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. C entry points over orc_model (see orc_capi.h).
+#include "orc_capi.h"
+#include "orc_model.hpp"
+#include <thread>
+#include <memory>
+#include <cstring>
+
+using namespace orc;
+
+namespace {
+
+struct Sim {
+    OrcConfig cfg;
+    Robot nao;
+    Kinematics ik;
+    ZMP zmp;
+    std::unique_ptr<Mpc3dLip> mpc;
+    FootCoeff rF, lF;
+    std::unique_ptr<Controller> ctrl;
+    Vec<60> state;
+    double t = 0;
+    int ik_iters = 0;
+    Vec<60> state0;
+
+    explicit Sim(const OrcConfig& c) : cfg(c) {
+        // apps/offline/main.cpp:16-58, same order
+        zmp = ZMP(cfg.sim_time, cfg.dt, SupportFoot::Double);
+        Vec<6> Rf, Lf;
+        for (int k = 0; k < 6; ++k) { Rf[k] = cfg.rf[k]; Lf[k] = cfg.lf[k]; }
+        Vec<30> desOp = ik.desiredOperationalState(nao, Rf, Lf, v3(cfg.com[0], cfg.com[1], cfg.com[2]));
+        ik_iters = ik.compute(nao, desOp);
+        mpc.reset(new Mpc3dLip(cfg.dt, cfg.time_horizon, nao.CoM[2]));
+        mpc->rebuild_hessian_each_call = cfg.mpc_rebuild_hessian != 0;
+        rF = footCoeffTrajectory(v3(cfg.rf[0], cfg.rf[1], cfg.rf[2]), v3(cfg.rf[0], cfg.rf[1], cfg.rf[2]), 0.0, cfg.sim_time);
+        lF = footCoeffTrajectory(v3(cfg.lf[0], cfg.lf[1], cfg.lf[2]), v3(cfg.lf[0], cfg.lf[1], cfg.lf[2]), 0.0, cfg.sim_time);
+        ctrl.reset(new Controller(nao, *mpc, zmp, rF, lF));
+        ctrl->qp_long_double = cfg.qp_long_double != 0;
+        state.set(0, 0, nao.q);   // stand(): main.cpp:68-72
+        state.set(30, 0, nao.v);
+        state0 = state;
+    }
+    void reset(const double* x0) {
+        if (x0) std::memcpy(state.d, x0, sizeof(double) * 60);
+        else state = state0;
+        t = 0;
+        nao.v = Vec<30>();  // a freshly constructed Robot holds zero velocity
+        ctrl->qp_solves = ctrl->qp_iterations = ctrl->qp_failures = 0;
+    }
+    void fill_dump(const Vec<60>& xdot, OrcStageDump* o) {
+        Controller& c = *ctrl;
+        std::memcpy(o->M, c.dyn.M.d, sizeof(o->M));
+        std::memcpy(o->C, c.dyn.C.d, sizeof(o->C));
+        std::memcpy(o->Cg, c.dyn.Cg.d, sizeof(o->Cg));
+        std::memcpy(o->AG, c.dyn.AG.d, sizeof(o->AG));
+        std::memcpy(o->AGpqp, c.dyn.AGpqp.d, sizeof(o->AGpqp));
+        std::memcpy(o->Jpqp, c.dyn.Jpqp.d, sizeof(o->Jpqp));
+        std::memcpy(o->JFeet, c.kin.JFeet.d, sizeof(o->JFeet));
+        std::memcpy(o->CoM, nao.CoM.d, sizeof(o->CoM));
+        std::memcpy(o->comVel, nao.comVel.d, sizeof(o->comVel));
+        std::memcpy(o->comAngMom, nao.comAngMom.d, sizeof(o->comAngMom));
+        std::memcpy(o->xRef, mpc->xRef.d, sizeof(o->xRef));
+        std::memcpy(o->yRef, mpc->yRef.d, sizeof(o->yRef));
+        std::memcpy(o->qppRef, c.qppRef.d, sizeof(o->qppRef));
+        std::memcpy(o->hGpRef, c.hGpRef.d, sizeof(o->hGpRef));
+        std::memcpy(o->footAccRef, c.footAccRef.d, sizeof(o->footAccRef));
+        std::memcpy(o->H, c.Hqp.d, sizeof(o->H));
+        std::memcpy(o->g, c.gqp.d, sizeof(o->g));
+        std::memcpy(o->x, c.xqp.d, sizeof(o->x));
+        std::memcpy(o->y, c.yqp.d, sizeof(o->y));
+        std::memcpy(o->T7, nao.T[7].d, sizeof(o->T7));
+        std::memcpy(o->T14, nao.T[14].d, sizeof(o->T14));
+        std::memcpy(o->xdot, xdot.d, sizeof(o->xdot));
+        qp_kkt_residuals(74, c.Hqp.d, c.gqp.d, 50, c.Aqp.d, c.lbA.d, c.ubA.d, c.xqp.d, c.yqp.d, o->kkt);
+        o->k_index = mpc->last_k;
+        o->qp_status = c.qpInfo.status;
+        o->qp_iters = c.qpInfo.iterations;
+        o->pad = 0;
+    }
+    // one RK4 step with the bookkeeping the logs need (rk4.hpp:12-17 inlined)
+    void step(OrcStepLog* log) {
+        const double dt = cfg.dt;
+        const bool two = cfg.second_wbc != 0;
+        long it0 = ctrl->qp_iterations, f0 = ctrl->qp_failures;
+        WBCOutput o1;
+        Vec<60> k1 = dynamics(state, t, nao, *ctrl, two, &o1);
+        int kk0 = mpc->last_k;
+        Vec<60> k2 = dynamics(state + (0.5 * dt) * k1, t + 0.5 * dt, nao, *ctrl, two);
+        int kk1 = mpc->last_k;
+        Vec<60> k3 = dynamics(state + (0.5 * dt) * k2, t + 0.5 * dt, nao, *ctrl, two);
+        int kk2 = mpc->last_k;
+        Vec<60> k4 = dynamics(state + dt * k3, t + dt, nao, *ctrl, two);
+        int kk3 = mpc->last_k;
+        state = state + (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4);
+        t += dt;  // Clock::step
+        if (log) {
+            std::memcpy(log->x, state.d, sizeof(log->x));
+            for (int k = 0; k < 3; ++k) {
+                log->com_k4[k] = nao.CoM[k];
+                log->rfoot[k] = nao.T[7](k, 3);
+                log->lfoot[k] = nao.T[14](k, 3);
+            }
+            std::memcpy(log->tau_k1, o1.tau.d, sizeof(log->tau_k1));
+            log->k_index[0] = kk0; log->k_index[1] = kk1; log->k_index[2] = kk2; log->k_index[3] = kk3;
+            log->qp_iters = (int)(ctrl->qp_iterations - it0);
+            log->qp_fail = (int)(ctrl->qp_failures - f0);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void orc_default_config(OrcConfig* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->dt = 0.01; c->sim_time = 5.0; c->time_horizon = 0.5;
+    c->com[0] = -0.02; c->com[1] = 0.0; c->com[2] = 0.26;
+    c->rf[1] = -0.05; c->lf[1] = 0.05;
+    c->second_wbc = 0;
+}
+
+void* orc_sim_create(const OrcConfig* cfg) { return new Sim(*cfg); }
+void orc_sim_destroy(void* s) { delete static_cast<Sim*>(s); }
+int32_t orc_sim_ik_iterations(void* s) { return static_cast<Sim*>(s)->ik_iters; }
+double orc_sim_mass(void* s) { return static_cast<Sim*>(s)->nao.mass; }
+double orc_sim_zcom(void* s) { return static_cast<Sim*>(s)->mpc->zCom; }
+
+void orc_sim_get_state(void* sp, double* x, double* t, double* vh) {
+    Sim* s = static_cast<Sim*>(sp);
+    if (x) std::memcpy(x, s->state.d, sizeof(double) * 60);
+    if (t) *t = s->t;
+    if (vh) std::memcpy(vh, s->nao.v.d, sizeof(double) * 30);
+}
+void orc_sim_set_state(void* sp, const double* x, double t, const double* vh) {
+    Sim* s = static_cast<Sim*>(sp);
+    if (x) std::memcpy(s->state.d, x, sizeof(double) * 60);
+    s->t = t;
+    if (vh) std::memcpy(s->nao.v.d, vh, sizeof(double) * 30);
+}
+
+void orc_sim_stage(void* sp, const double* x60, double t, OrcStageDump* out) {
+    Sim* s = static_cast<Sim*>(sp);
+    Vec<60> x;
+    std::memcpy(x.d, x60, sizeof(double) * 60);
+    WBCOutput o;
+    Vec<60> xd = dynamics(x, t, s->nao, *s->ctrl, s->cfg.second_wbc != 0, &o);
+    s->fill_dump(xd, out);
+    std::memcpy(out->qpp, o.qpp.d, sizeof(out->qpp));
+    std::memcpy(out->tau, o.tau.d, sizeof(out->tau));
+    std::memcpy(out->f, o.f.d, sizeof(out->f));
+}
+
+void orc_sim_step(void* sp, int32_t n, OrcStepLog* log) {
+    Sim* s = static_cast<Sim*>(sp);
+    for (int i = 0; i < n; ++i) s->step(log ? log + i : nullptr);
+}
+
+int32_t orc_sim_run_stand(void* sp, double* comx, int32_t max_steps) {
+    Sim* s = static_cast<Sim*>(sp);
+    int n = 0;
+    while (std::fabs(s->t - s->cfg.sim_time) > 0.01 && n < max_steps) {
+        s->step(nullptr);
+        if (comx) comx[n] = s->nao.CoM[0];
+        ++n;
+    }
+    return n;
+}
+
+void orc_sim_mpc_tables(void* sp, double* Px, double* Pu, int32_t* horizon) {
+    Sim* s = static_cast<Sim*>(sp);
+    int n = s->mpc->horizon + 1;
+    if (horizon) *horizon = s->mpc->horizon;
+    if (Px) std::memcpy(Px, s->mpc->Px.data(), sizeof(double) * n * 2);
+    if (Pu) std::memcpy(Pu, s->mpc->Pu.data(), sizeof(double) * n * n);
+}
+
+void orc_sim_foot_coeffs(void* sp, double* rx, double* ry, double* rz, double* lx, double* ly, double* lz) {
+    Sim* s = static_cast<Sim*>(sp);
+    std::memcpy(rx, s->rF.x.data(), 6 * sizeof(double));
+    std::memcpy(ry, s->rF.y.data(), 6 * sizeof(double));
+    std::memcpy(rz, s->rF.z.data(), 8 * sizeof(double));
+    std::memcpy(lx, s->lF.x.data(), 6 * sizeof(double));
+    std::memcpy(ly, s->lF.y.data(), 6 * sizeof(double));
+    std::memcpy(lz, s->lF.z.data(), 8 * sizeof(double));
+}
+
+int32_t orc_sim_zmp(void* sp, double* zx, double* zy, int32_t cap) {
+    Sim* s = static_cast<Sim*>(sp);
+    int n = (int)s->zmp.zmpXRef.size();
+    for (int i = 0; i < n && i < cap; ++i) { zx[i] = s->zmp.zmpXRef[i]; zy[i] = s->zmp.zmpYRef[i]; }
+    return n;
+}
+
+void orc_sim_link_table(void* sp, double* mass, double* com, double* inertia) {
+    Sim* s = static_cast<Sim*>(sp);
+    for (int i = 0; i < NUM_FRAMES; ++i) {
+        mass[i] = s->nao.links[i].mass;
+        for (int k = 0; k < 3; ++k) com[3 * i + k] = s->nao.links[i].com[k];
+        for (int k = 0; k < 9; ++k) inertia[9 * i + k] = s->nao.links[i].inertia.d[k];
+    }
+}
+
+int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t E, const double* x0, const int32_t* push_step,
+                          const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
+                          double* com_out, double* stats) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > E) n_threads = E > 0 ? E : 1;
+    std::vector<std::thread> pool;
+    std::vector<int> fails(n_threads, 0);
+    for (int th = 0; th < n_threads; ++th) {
+        pool.emplace_back([&, th]() {
+            int lo = (int)((long long)E * th / n_threads), hi = (int)((long long)E * (th + 1) / n_threads);
+            if (lo >= hi) return;
+            Sim sim(*cfg);
+            for (int e = lo; e < hi; ++e) {
+                sim.reset(x0 ? x0 + 60 * (size_t)e : nullptr);
+                double max_tau = 0, max_err = 0;
+                for (int s = 0; s < n_steps; ++s) {
+                    if (push_step && push_step[e] == s && push_dv)
+                        for (int k = 0; k < 6; ++k) sim.state[30 + k] += push_dv[6 * (size_t)e + k];
+                    OrcStepLog lg;
+                    sim.step(&lg);
+                    for (int k = 0; k < 24; ++k) max_tau = std::fmax(max_tau, std::fabs(lg.tau_k1[k]));
+                    double ex = lg.com_k4[0] - 0.0, ey = lg.com_k4[1] - 0.0;
+                    max_err = std::fmax(max_err, std::sqrt(ex * ex + ey * ey));
+                }
+                if (x_out) std::memcpy(x_out + 60 * (size_t)e, sim.state.d, sizeof(double) * 60);
+                if (com_out)
+                    for (int k = 0; k < 3; ++k) com_out[3 * (size_t)e + k] = sim.nao.CoM[k];
+                if (stats) {
+                    stats[4 * (size_t)e + 0] = max_tau;
+                    stats[4 * (size_t)e + 1] = max_err;
+                    stats[4 * (size_t)e + 2] = (double)sim.ctrl->qp_iterations;
+                    stats[4 * (size_t)e + 3] = (double)sim.ctrl->qp_failures;
+                }
+                fails[th] += (int)sim.ctrl->qp_failures;
+            }
+        });
+    }
+    for (auto& t : pool) t.join();
+    int total = 0;
+    for (int f : fails) total += f;
+    return total;
+}
+
+int32_t orc_qp_solve(int32_t n, const double* H, const double* g, int32_t m, const double* A, const double* lbA,
+                     const double* ubA, double* x, double* y, int32_t ld, int32_t* iters, double* kkt4) {
+    std::vector<double> yy(m > 0 ? m : 1);
+    QpInfo info = ld ? qp_solve_gi<long double>(n, H, g, m, A, lbA, ubA, x, yy.data(), 2000)
+                     : qp_solve_gi<double>(n, H, g, m, A, lbA, ubA, x, yy.data(), 2000);
+    if (y) std::memcpy(y, yy.data(), sizeof(double) * m);
+    if (iters) *iters = info.iterations;
+    if (kkt4) qp_kkt_residuals(n, H, g, m, A, lbA, ubA, x, yy.data(), kkt4);
+    return info.status;
+}
+
+}  // extern "C"
