@@ -1,0 +1,146 @@
+/* lmh_capi.h -- C ABI of the B200-native batched NAO controller-and-simulator (liblmh_b200.so).
+ *
+ * The reference (Ema158/linearMpcHumanoid) has no FFI layer: its boundary is the C++ class surface
+ * that apps/offline/main.cpp consumes.  This header is the thin C layer underneath our C++ facade
+ * classes (include/linearMpcHumanoid_b200/facade.hpp) and the Python binding
+ * (linearmpchumanoid_b200/api.py).  Each entry point names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes; every array is FP64 unless its name says otherwise;
+ * per-environment arrays are environment-major ([env][field], one env's record contiguous: a warp
+ * loads its environment with coalesced 128-byte lines); all pointers are HOST pointers unless the
+ * function name ends in _dev; every call returns 0 on success or a negative LMH_E* code, and
+ * lmh_last_error() holds the message.  A handle owns one CUDA device, one stream and all device
+ * buffers; there are no hidden globals.  There is no CPU fallback: without a usable CUDA device
+ * lmh_create fails with LMH_ENODEVICE.
+ */
+#ifndef LMH_CAPI_H
+#define LMH_CAPI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMH_OK 0
+#define LMH_EINVAL (-1)
+#define LMH_ENODEVICE (-2)
+#define LMH_ECUDA (-3)
+#define LMH_ESTATE (-4)
+
+#define LMH_NQ 30      /* Robot.hpp:11  NUM_JOINTS        */
+#define LMH_NJ 24      /* Robot.hpp:12  NUM_ACTUAL_JOINTS */
+#define LMH_NX 60      /* state = [q; v], controller.hpp:20-31 */
+
+typedef struct LmhBatch LmhBatch;
+
+/* Scenario literals of apps/offline/main.cpp:13-56 plus launch geometry. */
+typedef struct {
+    double dt;             /* main.cpp:14 */
+    double sim_time;       /* main.cpp:13 */
+    double time_horizon;   /* main.cpp:38 */
+    double com[3];         /* main.cpp:31 */
+    double rf[6], lf[6];   /* main.cpp:24-27 */
+    double mu;             /* controller.hpp:81 */
+    double mpc_alpha, mpc_beta;   /* mpcLinearPendulum.hpp:47-48 */
+    int32_t qp_max_iter;   /* controller.cpp:438 (nWSR) */
+    int32_t threads_per_env;      /* 32, 64 or 128; 0 = default */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t log_steps;     /* capacity of the per-step log (0 = no log) */
+} LmhConfig;
+
+/* Everything one dynamics() evaluation (apps/offline/main.cpp:91-122) produces, row-major. */
+typedef struct {
+    double M[900], C[30], Cg[30], AG[180], AGpqp[6], Jpqp[12], JFeet[360];      /* Dynamics.hpp:13-20, invKinematics.hpp:31-33 */
+    double CoM[3], comVel[3], comAngMom[3], xRef[3], yRef[3];                    /* Robot.hpp:39-43, mpcLinearPendulum.hpp:22-23 */
+    double qppRef[30], hGpRef[6], footAccRef[12];                                /* controller.cpp:296-386 */
+    double Ha[900], ga[30];                                                      /* controller.cpp:94-132, joint block */
+    double a[30], f[12], c[32], lam[6];                                          /* QP solution (controller.cpp:477) */
+    double qpp[30], tau[24];                                                     /* WBCOutput, controller.hpp:42-48 */
+    double T7[12], T14[12];                                                      /* sole poses: R row-major (9), p (3) */
+    double xdot[60];
+    int32_t k_index;       /* (int)(t/dt), mpcLinearPendulum.cpp:92 */
+    int32_t qp_status;     /* 0 ok, 1 iteration limit */
+    int32_t qp_iters, pad;
+} LmhStageDump;
+
+/* One record per environment and step when logging is on. */
+typedef struct {
+    double com_k4[3];          /* robot.getCoM() as printed by main.cpp:86 (k4 stage state) */
+    double rfoot[3], lfoot[3]; /* sole positions at the same stage */
+    double tau_k1[24];         /* torques of the k1 stage */
+    int32_t k_index[4];
+    int32_t qp_iters, qp_fail;
+} LmhStepLog;
+
+/* Per-environment rollout statistics (lmh_get_stats): */
+typedef struct {
+    double max_abs_tau;        /* over k1 stages */
+    double max_com_err;        /* max |CoM_xy(k4) - zmp_ref_xy| */
+    double max_abs_qpp;
+    int32_t qp_iters, qp_fail; /* totals over all stages */
+    int32_t steps, alive;      /* steps run; alive = state still finite and torso above 0.15 m */
+} LmhStats;
+
+const char* lmh_last_error(void);
+void lmh_default_config(LmhConfig* cfg);
+
+/* main.cpp:16-58: Robot, Kinematics::compute (IK), Mpc3dLip, ZMP, footCoeffTrajectory, Controller.
+ * All n_env environments start at the IK posture with zero velocity at t = 0. */
+int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out);
+void lmh_destroy(LmhBatch* h);
+int32_t lmh_n_env(const LmhBatch* h);
+
+/* Setup results: Robot::getJoints after IK, Mpc3dLip::getZCom, Robot::getMass. */
+int32_t lmh_get_nominal(const LmhBatch* h, double* q0_30, double* zcom, double* mass, int32_t* ik_iterations);
+/* u0 = -(rPx . [pos,vel]) + sum_i r[i] zmp[k+i]  (condensed form of mpcLinearPendulum.cpp:89-101) */
+int32_t lmh_get_mpc_gain(const LmhBatch* h, double* r, int32_t r_cap, int32_t* n1, double* rPx2);
+/* Robot::getLinks after the constructor: mass[28], com[28][3], spatial inertia[28][36]. */
+int32_t lmh_get_link_tables(const LmhBatch* h, double* mass28, double* com28x3, double* isp28x36);
+
+/* Plans replace the ZMP object and the two coefficient vectors handed to the Controller
+ * (controller.hpp:52-57).  zmp_x/zmp_y: [n_plans][zmp_len]; foot_coef: [n_plans][2][20] =
+ * x(6) y(6) z(8) per foot, ascending powers.  plan_ids (or NULL = 0) selects one per env. */
+int32_t lmh_set_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zmp_x, const double* zmp_y,
+                      const double* foot_coef, const int32_t* plan_ids);
+int32_t lmh_get_plan(const LmhBatch* h, int32_t plan, double* zmp_x, double* zmp_y, int32_t cap, int32_t* zmp_len, double* foot_coef40);
+
+/* State: x [n_env][60] = [q; v]; v_held [n_env][30] = velocity the Robot object still holds from the
+ * previous stage evaluation (Robot::v_, refreshed late in Controller::standStep, controller.cpp:48-79);
+ * t [n_env].  NULL leaves a field unchanged (set) or unread (get). */
+int32_t lmh_set_state(LmhBatch* h, const double* x, const double* v_held, const double* t);
+int32_t lmh_get_state(LmhBatch* h, double* x, double* v_held, double* t);
+int32_t lmh_reset(LmhBatch* h);
+/* Velocity impulse added to v[0:6] of env e at the START of step push_step[e] (counted from the last
+ * reset / lmh_set_step_counter); push_step < 0 = none.  Extension: the reference has no pushes. */
+int32_t lmh_set_pushes(LmhBatch* h, const int32_t* push_step, const double* push_dv6);
+int32_t lmh_set_step_counter(LmhBatch* h, int32_t step);
+
+/* One dynamics(x,t) evaluation of every env at its current state, advancing only v_held (as the
+ * reference's call does).  dumps: [n_env] or NULL. */
+int32_t lmh_stage(LmhBatch* h, LmhStageDump* dumps);
+/* n RK4 steps (rk4.hpp:5-18 + Clock::step) of every env, fused on the device; asynchronous. */
+int32_t lmh_step(LmhBatch* h, int32_t n_steps);
+/* same, bracketed by CUDA events on the handle's stream; returns device milliseconds */
+int32_t lmh_step_timed(LmhBatch* h, int32_t n_steps, double* elapsed_ms);
+int32_t lmh_sync(LmhBatch* h);
+
+int32_t lmh_get_stats(LmhBatch* h, LmhStats* stats);
+int32_t lmh_get_log(LmhBatch* h, int32_t first_step, int32_t n_steps, LmhStepLog* out); /* [n_steps][n_env] */
+/* CoM of every env at the last evaluated stage: [n_env][3] */
+int32_t lmh_get_com(LmhBatch* h, double* com);
+
+/* Device-resident access for callers that keep data in HBM (torch tensors): raw device pointers to
+ * x [n_env][60], v_held [n_env][30], t [n_env], and the stream (cudaStream_t) the handle launches on. */
+int32_t lmh_state_dev(LmhBatch* h, double** x_dev, double** v_held_dev, double** t_dev, void** stream);
+int32_t lmh_stats_dev(LmhBatch* h, LmhStats** stats_dev);
+
+/* Launch geometry actually used. */
+int32_t lmh_launch_info(const LmhBatch* h, int32_t* threads_per_env, int32_t* envs_per_block, int32_t* smem_bytes,
+                        int32_t* blocks, int32_t* kernel_launches_total);
+
+/* Measured FP64 FMA throughput of the device (TFLOP/s): the roofline denominator of this path. */
+int32_t lmh_measure_fp64_peak(int32_t device, double* tflops, double* sm_clock_mhz, int32_t* sm_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,267 @@
+"""ctypes binding of liblmh_b200.so (include/lmh_capi.h).  No compute happens in Python and there is
+no CPU fallback: if the shared library or a CUDA device is missing, construction raises."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "liblmh_b200.so")
+_f64, _i32 = C.c_double, C.c_int32
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+
+class LmhError(RuntimeError):
+    pass
+
+
+class LmhConfig(C.Structure):
+    _fields_ = [("dt", _f64), ("sim_time", _f64), ("time_horizon", _f64), ("com", _f64 * 3), ("rf", _f64 * 6),
+                ("lf", _f64 * 6), ("mu", _f64), ("mpc_alpha", _f64), ("mpc_beta", _f64), ("qp_max_iter", _i32),
+                ("threads_per_env", _i32), ("device", _i32), ("log_steps", _i32)]
+
+
+STAGE_DTYPE = np.dtype([("M", "f8", (30, 30)), ("C", "f8", 30), ("Cg", "f8", 30), ("AG", "f8", (6, 30)),
+                        ("AGpqp", "f8", 6), ("Jpqp", "f8", 12), ("JFeet", "f8", (12, 30)), ("CoM", "f8", 3),
+                        ("comVel", "f8", 3), ("comAngMom", "f8", 3), ("xRef", "f8", 3), ("yRef", "f8", 3),
+                        ("qppRef", "f8", 30), ("hGpRef", "f8", 6), ("footAccRef", "f8", 12), ("Ha", "f8", (30, 30)),
+                        ("ga", "f8", 30), ("a", "f8", 30), ("f", "f8", 12), ("c", "f8", 32), ("lam", "f8", 6),
+                        ("qpp", "f8", 30), ("tau", "f8", 24), ("T7", "f8", 12), ("T14", "f8", 12), ("xdot", "f8", 60),
+                        ("k_index", "i4"), ("qp_status", "i4"), ("qp_iters", "i4"), ("pad", "i4")])
+STEPLOG_DTYPE = np.dtype([("com_k4", "f8", 3), ("rfoot", "f8", 3), ("lfoot", "f8", 3), ("tau_k1", "f8", 24),
+                          ("k_index", "i4", 4), ("qp_iters", "i4"), ("qp_fail", "i4")])
+STATS_DTYPE = np.dtype([("max_abs_tau", "f8"), ("max_com_err", "f8"), ("max_abs_qpp", "f8"), ("qp_iters", "i4"),
+                        ("qp_fail", "i4"), ("steps", "i4"), ("alive", "i4")])
+
+# every symbol include/lmh_capi.h declares (checked by the CPU test-suite against the built library)
+SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", "lmh_n_env", "lmh_get_nominal",
+           "lmh_get_mpc_gain", "lmh_get_link_tables", "lmh_set_plans", "lmh_get_plan", "lmh_set_state",
+           "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
+           "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
+           "lmh_stats_dev", "lmh_launch_info", "lmh_measure_fp64_peak"]
+
+
+def build_library(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... in-tree (cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc", "lmh_capi.cu")
+    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("lmh_model.cuh", "lmh_setup.hpp", "lmh_nao_table.inc")]
+    deps.append(os.path.join(_ROOT, "include", "lmh_capi.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, src]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise LmhError("nvcc failed:\n" + r.stdout + r.stderr)
+    return r.stderr if verbose else LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Loads liblmh_b200.so; raises if it was never built (there is nothing to fall back to)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LmhError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.lmh_last_error.restype = C.c_char_p
+    L.lmh_default_config.argtypes = [C.POINTER(LmhConfig)]
+    L.lmh_create.argtypes = [C.POINTER(LmhConfig), _i32, C.POINTER(vp)]
+    L.lmh_destroy.argtypes = [vp]
+    L.lmh_n_env.argtypes = [vp]
+    L.lmh_get_nominal.argtypes = [vp, vp, vp, vp, vp]
+    L.lmh_get_mpc_gain.argtypes = [vp, vp, _i32, vp, vp]
+    L.lmh_get_link_tables.argtypes = [vp, vp, vp, vp]
+    L.lmh_set_plans.argtypes = [vp, _i32, _i32, vp, vp, vp, vp]
+    L.lmh_get_plan.argtypes = [vp, _i32, vp, vp, _i32, vp, vp]
+    L.lmh_set_state.argtypes = [vp, vp, vp, vp]
+    L.lmh_get_state.argtypes = [vp, vp, vp, vp]
+    L.lmh_reset.argtypes = [vp]
+    L.lmh_set_pushes.argtypes = [vp, vp, vp]
+    L.lmh_set_step_counter.argtypes = [vp, _i32]
+    L.lmh_stage.argtypes = [vp, vp]
+    L.lmh_step.argtypes = [vp, _i32]
+    L.lmh_step_timed.argtypes = [vp, _i32, vp]
+    L.lmh_sync.argtypes = [vp]
+    L.lmh_get_stats.argtypes = [vp, vp]
+    L.lmh_get_log.argtypes = [vp, _i32, _i32, vp]
+    L.lmh_get_com.argtypes = [vp, vp]
+    L.lmh_state_dev.argtypes = [vp, vp, vp, vp, vp]
+    L.lmh_stats_dev.argtypes = [vp, vp]
+    L.lmh_launch_info.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.lmh_measure_fp64_peak.argtypes = [_i32, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _chk(L, rc):
+    if rc != 0:
+        raise LmhError(f"lmh error {rc}: {L.lmh_last_error().decode()}")
+
+
+def measure_fp64_peak(device=0):
+    L = load_library()
+    tf, mhz, sms = np.zeros(1), np.zeros(1), np.zeros(1, np.int32)
+    _chk(L, L.lmh_measure_fp64_peak(device, _p(tf), _p(mhz), _p(sms)))
+    return float(tf[0]), float(mhz[0]), int(sms[0])
+
+
+class Batch:
+    """n_env independent NAO environments stepped in lockstep on one GPU.
+
+    Mirrors what apps/offline/main.cpp builds (Robot + IK + Mpc3dLip + ZMP + foot polynomials +
+    Controller) and what its stand() loop does (rk4Step + Clock::step), for a whole batch."""
+
+    def __init__(self, n_env, device=0, threads_per_env=0, log_steps=0, **scenario):
+        self.L = L = load_library()
+        cfg = LmhConfig()
+        L.lmh_default_config(C.byref(cfg))
+        cfg.device, cfg.threads_per_env, cfg.log_steps = device, threads_per_env, log_steps
+        for k, v in scenario.items():
+            if not hasattr(cfg, k):
+                raise LmhError(f"unknown scenario field {k}")
+            if isinstance(v, (list, tuple, np.ndarray)):
+                arr = getattr(cfg, k)
+                for i, x in enumerate(v):
+                    arr[i] = x
+            else:
+                setattr(cfg, k, v)
+        self.cfg = cfg
+        self.n_env = int(n_env)
+        self.h = C.c_void_p()
+        _chk(L, L.lmh_create(C.byref(cfg), self.n_env, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lmh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup results
+    def nominal(self):
+        q0, z, m, it = np.zeros(30), np.zeros(1), np.zeros(1), np.zeros(1, np.int32)
+        _chk(self.L, self.L.lmh_get_nominal(self.h, _p(q0), _p(z), _p(m), _p(it)))
+        return q0, float(z[0]), float(m[0]), int(it[0])
+
+    def mpc_gain(self):
+        r, n1, rpx = np.zeros(512), np.zeros(1, np.int32), np.zeros(2)
+        _chk(self.L, self.L.lmh_get_mpc_gain(self.h, _p(r), 512, _p(n1), _p(rpx)))
+        return r[:int(n1[0])].copy(), rpx
+
+    def link_tables(self):
+        m, c, i = np.zeros(28), np.zeros((28, 3)), np.zeros((28, 6, 6))
+        _chk(self.L, self.L.lmh_get_link_tables(self.h, _p(m), _p(c), _p(i)))
+        return m, c, i
+
+    def plan(self, k=0):
+        n = np.zeros(1, np.int32)
+        _chk(self.L, self.L.lmh_get_plan(self.h, k, None, None, 0, _p(n), None))
+        zx, zy, fc = np.zeros(int(n[0])), np.zeros(int(n[0])), np.zeros(40)
+        _chk(self.L, self.L.lmh_get_plan(self.h, k, _p(zx), _p(zy), int(n[0]), _p(n), _p(fc)))
+        return zx, zy, fc.reshape(2, 20)
+
+    def set_plans(self, zmp_x, zmp_y, foot_coef, plan_ids=None):
+        zx = np.ascontiguousarray(np.atleast_2d(zmp_x), np.float64)
+        zy = np.ascontiguousarray(np.atleast_2d(zmp_y), np.float64)
+        fc = np.ascontiguousarray(foot_coef, np.float64).reshape(zx.shape[0], 40)
+        ids = None if plan_ids is None else np.ascontiguousarray(plan_ids, np.int32)
+        _chk(self.L, self.L.lmh_set_plans(self.h, zx.shape[0], zx.shape[1], _p(zx), _p(zy), _p(fc), _p(ids)))
+
+    # ---- state
+    def reset(self):
+        _chk(self.L, self.L.lmh_reset(self.h))
+
+    def set_state(self, x=None, v_held=None, t=None):
+        a = [None if v is None else np.ascontiguousarray(v, np.float64) for v in (x, v_held, t)]
+        for arr, n in zip(a, (60, 30, 1)):
+            if arr is not None and arr.size != self.n_env * n:
+                raise LmhError("set_state: wrong array size")
+        _chk(self.L, self.L.lmh_set_state(self.h, _p(a[0]), _p(a[1]), _p(a[2])))
+        _chk(self.L, self.L.lmh_sync(self.h))
+
+    def get_state(self):
+        x, vh, t = np.zeros((self.n_env, 60)), np.zeros((self.n_env, 30)), np.zeros(self.n_env)
+        _chk(self.L, self.L.lmh_get_state(self.h, _p(x), _p(vh), _p(t)))
+        return x, vh, t
+
+    def set_pushes(self, push_step, push_dv6):
+        ps = None if push_step is None else np.ascontiguousarray(push_step, np.int32)
+        dv = None if push_dv6 is None else np.ascontiguousarray(push_dv6, np.float64)
+        _chk(self.L, self.L.lmh_set_pushes(self.h, _p(ps), _p(dv)))
+
+    def set_step_counter(self, step):
+        _chk(self.L, self.L.lmh_set_step_counter(self.h, int(step)))
+
+    # ---- compute
+    def stage(self, dump=True):
+        d = np.zeros(self.n_env, STAGE_DTYPE) if dump else None
+        _chk(self.L, self.L.lmh_stage(self.h, _p(d)))
+        return d
+
+    def step(self, n_steps, sync=True):
+        _chk(self.L, self.L.lmh_step(self.h, int(n_steps)))
+        if sync:
+            _chk(self.L, self.L.lmh_sync(self.h))
+
+    def step_timed(self, n_steps):
+        ms = np.zeros(1)
+        _chk(self.L, self.L.lmh_step_timed(self.h, int(n_steps), _p(ms)))
+        return float(ms[0])
+
+    def sync(self):
+        _chk(self.L, self.L.lmh_sync(self.h))
+
+    def stats(self):
+        s = np.zeros(self.n_env, STATS_DTYPE)
+        _chk(self.L, self.L.lmh_get_stats(self.h, _p(s)))
+        return s
+
+    def log(self, first=0, n=None):
+        n = self.cfg.log_steps - first if n is None else n
+        out = np.zeros((n, self.n_env), STEPLOG_DTYPE)
+        _chk(self.L, self.L.lmh_get_log(self.h, first, n, _p(out)))
+        return out
+
+    def com(self):
+        c = np.zeros((self.n_env, 3))
+        _chk(self.L, self.L.lmh_get_com(self.h, _p(c)))
+        return c
+
+    def launch_info(self):
+        v = [np.zeros(1, np.int32) for _ in range(5)]
+        _chk(self.L, self.L.lmh_launch_info(self.h, *[_p(a) for a in v]))
+        return dict(zip(("threads_per_env", "envs_per_block", "smem_bytes", "blocks", "launches"),
+                        (int(a[0]) for a in v)))
+
+    def device_pointers(self):
+        x, vh, t, s = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _chk(self.L, self.L.lmh_state_dev(self.h, C.byref(x), C.byref(vh), C.byref(t), C.byref(s)))
+        return x.value, vh.value, t.value, s.value
+
+    # raw-pointer variants for pinned host buffers (used by the end-to-end bench leg)
+    def set_state_ptr(self, x_ptr):
+        _chk(self.L, self.L.lmh_set_state(self.h, C.c_void_p(x_ptr), None, None))
+
+    def get_state_ptr(self, x_ptr):
+        _chk(self.L, self.L.lmh_get_state(self.h, C.c_void_p(x_ptr), None, None))
+
+    def get_stats_ptr(self, s_ptr):
+        _chk(self.L, self.L.lmh_get_stats(self.h, C.c_void_p(s_ptr)))

@@ -1,0 +1,518 @@
+// lmh_capi.cu -- kernels and C ABI of liblmh_b200.so (see include/lmh_capi.h).
+//
+// Execution model: one thread block per environment, NT = 32 / 64 / 128 threads cooperating on the
+// environment's workspace in shared memory (lmh_model.cuh).  A launch advances every environment by
+// n_steps RK4 steps with the state, the stage intermediates and the QP working set resident on chip;
+// HBM is touched once per launch for the 60+30+1 state doubles (and once per step for the optional
+// log record).  Environments never communicate.
+#include "lmh_setup.hpp"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+
+using namespace lmh;
+
+namespace {
+
+thread_local std::string g_err;
+int32_t fail(int32_t code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? LMH_ENODEVICE : LMH_ECUDA, \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                        \
+    } while (0)
+
+struct Params {
+    const Consts* K;
+    Plan plan;
+    const int32_t* plan_id;
+    double* x;          // [E][60]
+    double* vh;         // [E][30]
+    double* t;          // [E]
+    const int32_t* push_step;
+    const double* push_dv;   // [E][6]
+    LmhStats* stats;
+    LmhStepLog* log;    // [log_cap][E] or null
+    LmhStageDump* dump; // [E] or null
+    double* com;        // [E][3]
+    int32_t n_env, n_steps, step0, log_cap;
+};
+
+constexpr int kExtraDoubles = 2 * 60;   // x and the RK4 accumulator
+
+template <int NT>
+__global__ void __launch_bounds__(NT) rollout_kernel(Params p) {
+    extern __shared__ double smem[];
+    EnvWS& w = *reinterpret_cast<EnvWS*>(smem);
+    double* x = smem + (sizeof(EnvWS) + 7) / 8;
+    double* kacc = x + 60;
+    const int env = blockIdx.x;
+    if (env >= p.n_env) return;
+    Ctx<NT> cx{(int)threadIdx.x, 0};
+    const Consts& K = *p.K;
+    for (int i = threadIdx.x; i < 60; i += NT) x[i] = p.x[(size_t)env * 60 + i];
+    for (int i = threadIdx.x; i < 30; i += NT) w.vh[i] = p.vh[(size_t)env * 30 + i];
+    double t = p.t[env];
+    const int plan_id = p.plan_id ? p.plan_id[env] : 0;
+    const int push_at = p.push_step ? p.push_step[env] : -1;
+    StatsAcc st;
+    {
+        const LmhStats& s0 = p.stats[env];
+        st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
+        st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive;
+    }
+    cx.sync();
+    for (int s = 0; s < p.n_steps; ++s) {
+        const int gstep = p.step0 + s;
+        if (gstep == push_at) {
+            for (int k = threadIdx.x; k < 6; k += NT) x[30 + k] += p.push_dv[(size_t)env * 6 + k];
+            cx.sync();
+        }
+        LmhStepLog* lg = (p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
+        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, lg, &st);
+    }
+    for (int i = threadIdx.x; i < 60; i += NT) p.x[(size_t)env * 60 + i] = x[i];
+    for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];
+    for (int i = threadIdx.x; i < 3; i += NT) p.com[(size_t)env * 3 + i] = w.com[i];
+    if (threadIdx.x == 0) {
+        p.t[env] = t;
+        LmhStats& s1 = p.stats[env];
+        s1.max_abs_tau = st.max_tau; s1.max_com_err = st.max_err; s1.max_abs_qpp = st.max_qpp;
+        s1.qp_iters = st.qp_iters; s1.qp_fail = st.qp_fail; s1.steps = st.steps; s1.alive = st.alive;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) stage_kernel(Params p) {
+    extern __shared__ double smem[];
+    EnvWS& w = *reinterpret_cast<EnvWS*>(smem);
+    const int env = blockIdx.x;
+    if (env >= p.n_env) return;
+    Ctx<NT> cx{(int)threadIdx.x, 0};
+    for (int i = threadIdx.x; i < 30; i += NT) {
+        w.q[i] = p.x[(size_t)env * 60 + i];
+        w.v[i] = p.x[(size_t)env * 60 + 30 + i];
+        w.vh[i] = p.vh[(size_t)env * 30 + i];
+    }
+    if (threadIdx.x == 0) w.t = p.t[env];
+    cx.sync();
+    stage_eval(cx, w, *p.K, p.plan, p.plan_id ? p.plan_id[env] : 0, p.dump ? p.dump + env : nullptr);
+    for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];
+    for (int i = threadIdx.x; i < 3; i += NT) p.com[(size_t)env * 3 + i] = w.com[i];
+}
+
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+struct LmhBatch {
+    LmhConfig cfg;
+    HostModel* hm = nullptr;
+    int32_t n_env = 0, nt = 64, smem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Consts* dK = nullptr;
+    double *d_x = nullptr, *d_vh = nullptr, *d_t = nullptr, *d_push_dv = nullptr, *d_com = nullptr;
+    double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr;
+    int32_t *d_plan_id = nullptr, *d_push_step = nullptr;
+    LmhStats* d_stats = nullptr;
+    LmhStepLog* d_log = nullptr;
+    LmhStageDump* d_dump = nullptr;
+    int32_t n_plans = 1, zmp_len = 0, step_counter = 0, launches = 0;
+    std::vector<double> h_zmp_x, h_zmp_y, h_foot;
+    bool has_pushes = false, has_plan_ids = false;
+};
+
+namespace {
+
+Params make_params(LmhBatch* h) {
+    Params p;
+    p.K = h->dK;
+    p.plan.zmp_x = h->d_zmp_x; p.plan.zmp_y = h->d_zmp_y; p.plan.foot_coef = h->d_foot; p.plan.zmp_len = h->zmp_len;
+    p.plan_id = h->has_plan_ids ? h->d_plan_id : nullptr;
+    p.x = h->d_x; p.vh = h->d_vh; p.t = h->d_t;
+    p.push_step = h->has_pushes ? h->d_push_step : nullptr;
+    p.push_dv = h->d_push_dv;
+    p.stats = h->d_stats; p.log = h->d_log; p.dump = nullptr; p.com = h->d_com;
+    p.n_env = h->n_env; p.n_steps = 0; p.step0 = h->step_counter; p.log_cap = h->cfg.log_steps;
+    return p;
+}
+
+template <int NT>
+int32_t configure_kernels(int smem) {
+    CU(cudaFuncSetAttribute(rollout_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(stage_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return LMH_OK;
+}
+
+int32_t upload_plans(LmhBatch* h) {
+    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot);
+    h->d_zmp_x = h->d_zmp_y = h->d_foot = nullptr;
+    size_t nz = (size_t)h->n_plans * h->zmp_len * sizeof(double), nf = (size_t)h->n_plans * 40 * sizeof(double);
+    CU(cudaMalloc(&h->d_zmp_x, nz)); CU(cudaMalloc(&h->d_zmp_y, nz)); CU(cudaMalloc(&h->d_foot, nf));
+    CU(cudaMemcpyAsync(h->d_zmp_x, h->h_zmp_x.data(), nz, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_zmp_y, h->h_zmp_y.data(), nz, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_foot, h->h_foot.data(), nf, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t launch_rollout(LmhBatch* h, int32_t n_steps) {
+    Params p = make_params(h);
+    p.n_steps = n_steps;
+    dim3 grid(h->n_env), block(h->nt);
+    if (h->nt == 32) rollout_kernel<32><<<grid, block, h->smem, h->stream>>>(p);
+    else if (h->nt == 64) rollout_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
+    else rollout_kernel<128><<<grid, block, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    h->step_counter += n_steps;
+    h->launches += 1;
+    return LMH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lmh_last_error(void) { return g_err.c_str(); }
+
+void lmh_default_config(LmhConfig* c) {
+    Scenario s;
+    std::memset(c, 0, sizeof(*c));
+    c->dt = s.dt; c->sim_time = s.sim_time; c->time_horizon = s.time_horizon;
+    for (int k = 0; k < 3; ++k) c->com[k] = s.com[k];
+    for (int k = 0; k < 6; ++k) { c->rf[k] = s.rf[k]; c->lf[k] = s.lf[k]; }
+    c->mu = s.mu; c->mpc_alpha = s.mpc_alpha; c->mpc_beta = s.mpc_beta;
+    c->qp_max_iter = s.qp_max_iter;
+    c->threads_per_env = 0; c->device = 0; c->log_steps = 0;
+}
+
+int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
+    if (!cfg || !out || n_env <= 0) return fail(LMH_EINVAL, "lmh_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(LMH_ENODEVICE, std::string("lmh_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(LMH_EINVAL, "lmh_create: device ordinal out of range");
+    CU(cudaSetDevice(cfg->device));
+    LmhBatch* h = new LmhBatch;
+    h->cfg = *cfg;
+    h->n_env = n_env;
+    h->nt = cfg->threads_per_env == 0 ? 64 : cfg->threads_per_env;
+    if (h->nt != 32 && h->nt != 64 && h->nt != 128) { delete h; return fail(LMH_EINVAL, "lmh_create: threads_per_env must be 32, 64 or 128"); }
+    try {
+        Scenario s;
+        s.dt = cfg->dt; s.sim_time = cfg->sim_time; s.time_horizon = cfg->time_horizon;
+        for (int k = 0; k < 3; ++k) s.com[k] = cfg->com[k];
+        for (int k = 0; k < 6; ++k) { s.rf[k] = cfg->rf[k]; s.lf[k] = cfg->lf[k]; }
+        s.mu = cfg->mu; s.mpc_alpha = cfg->mpc_alpha; s.mpc_beta = cfg->mpc_beta;
+        s.qp_max_iter = cfg->qp_max_iter > 0 ? cfg->qp_max_iter : 200;
+        h->hm = new HostModel(s);
+    } catch (const std::exception& ex) {
+        delete h;
+        return fail(LMH_EINVAL, std::string("lmh_create: setup failed: ") + ex.what());
+    }
+    h->smem = (int32_t)(((sizeof(EnvWS) + 7) / 8 + kExtraDoubles) * sizeof(double));
+    int32_t rc = h->nt == 32 ? configure_kernels<32>(h->smem) : h->nt == 64 ? configure_kernels<64>(h->smem) : configure_kernels<128>(h->smem);
+    if (rc != LMH_OK) { delete h->hm; delete h; return rc; }
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+    size_t E = (size_t)n_env;
+    CU(cudaMalloc(&h->dK, sizeof(Consts)));
+    CU(cudaMemcpy(h->dK, &h->hm->K, sizeof(Consts), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->d_x, E * 60 * sizeof(double))); CU(cudaMalloc(&h->d_vh, E * 30 * sizeof(double)));
+    CU(cudaMalloc(&h->d_t, E * sizeof(double))); CU(cudaMalloc(&h->d_push_dv, E * 6 * sizeof(double)));
+    CU(cudaMalloc(&h->d_com, E * 3 * sizeof(double)));
+    CU(cudaMalloc(&h->d_plan_id, E * sizeof(int32_t))); CU(cudaMalloc(&h->d_push_step, E * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_stats, E * sizeof(LmhStats)));
+    CU(cudaMalloc(&h->d_dump, E * sizeof(LmhStageDump)));
+    if (cfg->log_steps > 0) CU(cudaMalloc(&h->d_log, (size_t)cfg->log_steps * E * sizeof(LmhStepLog)));
+    h->n_plans = 1;
+    h->zmp_len = (int32_t)h->hm->zmp_x.size();
+    h->h_zmp_x = h->hm->zmp_x; h->h_zmp_y = h->hm->zmp_y; h->h_foot = h->hm->foot_coef;
+    rc = upload_plans(h);
+    if (rc != LMH_OK) return rc;
+    *out = h;
+    return lmh_reset(h);
+}
+
+void lmh_destroy(LmhBatch* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
+    cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_dump); cudaFree(h->d_log);
+    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h->hm;
+    delete h;
+}
+
+int32_t lmh_n_env(const LmhBatch* h) { return h ? h->n_env : 0; }
+
+int32_t lmh_get_nominal(const LmhBatch* h, double* q0, double* zcom, double* mass, int32_t* ik) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    if (q0) for (int i = 0; i < NQ; ++i) q0[i] = h->hm->q0[i];
+    if (zcom) *zcom = h->hm->K.mpc_zcom;
+    if (mass) *mass = h->hm->K.mass;
+    if (ik) *ik = h->hm->ik_iterations;
+    return LMH_OK;
+}
+
+int32_t lmh_get_mpc_gain(const LmhBatch* h, double* r, int32_t cap, int32_t* n1, double* rPx2) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    const Consts& K = h->hm->K;
+    if (n1) *n1 = K.mpc_n1;
+    if (r) for (int i = 0; i < K.mpc_n1 && i < cap; ++i) r[i] = K.mpc_r[i];
+    if (rPx2) { rPx2[0] = K.mpc_rPx[0]; rPx2[1] = K.mpc_rPx[1]; }
+    return LMH_OK;
+}
+
+int32_t lmh_get_link_tables(const LmhBatch* h, double* mass, double* com, double* isp) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    const Consts& K = h->hm->K;
+    for (int i = 0; i < 28; ++i) {
+        if (mass) mass[i] = K.mc[4 * i + 3];
+        if (com) for (int k = 0; k < 3; ++k) com[3 * i + k] = K.mc[4 * i + k];
+    }
+    if (isp) std::memcpy(isp, K.Isp, sizeof(double) * 28 * 36);
+    return LMH_OK;
+}
+
+int32_t lmh_set_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zx, const double* zy,
+                      const double* foot, const int32_t* plan_ids) {
+    if (!h || n_plans <= 0 || zmp_len < h->hm->K.mpc_n1 || !zx || !zy || !foot)
+        return fail(LMH_EINVAL, "lmh_set_plans: bad arguments (zmp_len must cover horizon+1 samples)");
+    CU(cudaSetDevice(h->cfg.device));
+    if (plan_ids)
+        for (int e = 0; e < h->n_env; ++e)
+            if (plan_ids[e] < 0 || plan_ids[e] >= n_plans) return fail(LMH_EINVAL, "lmh_set_plans: plan id out of range");
+    h->n_plans = n_plans; h->zmp_len = zmp_len;
+    h->h_zmp_x.assign(zx, zx + (size_t)n_plans * zmp_len);
+    h->h_zmp_y.assign(zy, zy + (size_t)n_plans * zmp_len);
+    h->h_foot.assign(foot, foot + (size_t)n_plans * 40);
+    int32_t rc = upload_plans(h);
+    if (rc != LMH_OK) return rc;
+    h->has_plan_ids = plan_ids != nullptr;
+    if (plan_ids) {
+        CU(cudaMemcpyAsync(h->d_plan_id, plan_ids, sizeof(int32_t) * h->n_env, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return LMH_OK;
+}
+
+int32_t lmh_get_plan(const LmhBatch* h, int32_t plan, double* zx, double* zy, int32_t cap, int32_t* zmp_len, double* foot40) {
+    if (!h || plan < 0 || plan >= h->n_plans) return fail(LMH_EINVAL, "lmh_get_plan: bad arguments");
+    if (zmp_len) *zmp_len = h->zmp_len;
+    for (int i = 0; i < h->zmp_len && i < cap; ++i) {
+        if (zx) zx[i] = h->h_zmp_x[(size_t)plan * h->zmp_len + i];
+        if (zy) zy[i] = h->h_zmp_y[(size_t)plan * h->zmp_len + i];
+    }
+    if (foot40) std::memcpy(foot40, h->h_foot.data() + (size_t)plan * 40, 40 * sizeof(double));
+    return LMH_OK;
+}
+
+int32_t lmh_set_state(LmhBatch* h, const double* x, const double* vh, const double* t) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    size_t E = (size_t)h->n_env;
+    if (x) CU(cudaMemcpyAsync(h->d_x, x, E * 60 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (vh) CU(cudaMemcpyAsync(h->d_vh, vh, E * 30 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (t) CU(cudaMemcpyAsync(h->d_t, t, E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_get_state(LmhBatch* h, double* x, double* vh, double* t) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    size_t E = (size_t)h->n_env;
+    if (x) CU(cudaMemcpyAsync(x, h->d_x, E * 60 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (vh) CU(cudaMemcpyAsync(vh, h->d_vh, E * 30 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (t) CU(cudaMemcpyAsync(t, h->d_t, E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_reset(LmhBatch* h) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    size_t E = (size_t)h->n_env;
+    std::vector<double> x(E * 60, 0.0);
+    for (size_t e = 0; e < E; ++e) for (int i = 0; i < NQ; ++i) x[e * 60 + i] = h->hm->q0[i];
+    CU(cudaMemcpyAsync(h->d_x, x.data(), E * 60 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->d_vh, 0, E * 30 * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_t, 0, E * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->d_com, 0, E * 3 * sizeof(double), h->stream));
+    std::vector<LmhStats> st(E);
+    std::memset(st.data(), 0, E * sizeof(LmhStats));
+    for (size_t e = 0; e < E; ++e) st[e].alive = 1;
+    CU(cudaMemcpyAsync(h->d_stats, st.data(), E * sizeof(LmhStats), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->step_counter = 0;
+    return LMH_OK;
+}
+
+int32_t lmh_set_pushes(LmhBatch* h, const int32_t* push_step, const double* push_dv6) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    h->has_pushes = push_step != nullptr && push_dv6 != nullptr;
+    if (h->has_pushes) {
+        CU(cudaMemcpyAsync(h->d_push_step, push_step, sizeof(int32_t) * h->n_env, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_push_dv, push_dv6, sizeof(double) * 6 * h->n_env, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return LMH_OK;
+}
+
+int32_t lmh_set_step_counter(LmhBatch* h, int32_t step) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    h->step_counter = step;
+    return LMH_OK;
+}
+
+int32_t lmh_stage(LmhBatch* h, LmhStageDump* dumps) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    Params p = make_params(h);
+    p.dump = dumps ? h->d_dump : nullptr;
+    dim3 grid(h->n_env), block(h->nt);
+    if (h->nt == 32) stage_kernel<32><<<grid, block, h->smem, h->stream>>>(p);
+    else if (h->nt == 64) stage_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
+    else stage_kernel<128><<<grid, block, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    if (dumps) CU(cudaMemcpyAsync(dumps, h->d_dump, (size_t)h->n_env * sizeof(LmhStageDump), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_step(LmhBatch* h, int32_t n_steps) {
+    if (!h || n_steps < 0) return fail(LMH_EINVAL, "lmh_step: bad arguments");
+    if (n_steps == 0) return LMH_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    return launch_rollout(h, n_steps);
+}
+
+int32_t lmh_step_timed(LmhBatch* h, int32_t n_steps, double* ms) {
+    if (!h || n_steps <= 0) return fail(LMH_EINVAL, "lmh_step_timed: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    int32_t rc = launch_rollout(h, n_steps);
+    if (rc != LMH_OK) return rc;
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    if (ms) *ms = f;
+    return LMH_OK;
+}
+
+int32_t lmh_sync(LmhBatch* h) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_get_stats(LmhBatch* h, LmhStats* stats) {
+    if (!h || !stats) return fail(LMH_EINVAL, "lmh_get_stats: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(stats, h->d_stats, (size_t)h->n_env * sizeof(LmhStats), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_get_log(LmhBatch* h, int32_t first, int32_t n, LmhStepLog* out) {
+    if (!h || !out || first < 0 || n < 0 || first + n > h->cfg.log_steps) return fail(LMH_EINVAL, "lmh_get_log: range outside the log");
+    if (!h->d_log) return fail(LMH_ESTATE, "lmh_get_log: logging is off (log_steps = 0)");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(out, h->d_log + (size_t)first * h->n_env, (size_t)n * h->n_env * sizeof(LmhStepLog), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_get_com(LmhBatch* h, double* com) {
+    if (!h || !com) return fail(LMH_EINVAL, "lmh_get_com: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(com, h->d_com, (size_t)h->n_env * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_state_dev(LmhBatch* h, double** x, double** vh, double** t, void** stream) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    if (x) *x = h->d_x;
+    if (vh) *vh = h->d_vh;
+    if (t) *t = h->d_t;
+    if (stream) *stream = (void*)h->stream;
+    return LMH_OK;
+}
+
+int32_t lmh_stats_dev(LmhBatch* h, LmhStats** s) {
+    if (!h || !s) return fail(LMH_EINVAL, "bad arguments");
+    *s = h->d_stats;
+    return LMH_OK;
+}
+
+int32_t lmh_launch_info(const LmhBatch* h, int32_t* nt, int32_t* epb, int32_t* smem, int32_t* blocks, int32_t* launches) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    if (nt) *nt = h->nt;
+    if (epb) *epb = 1;
+    if (smem) *smem = h->smem;
+    if (blocks) *blocks = h->n_env;
+    if (launches) *launches = h->launches;
+    return LMH_OK;
+}
+
+int32_t lmh_measure_fp64_peak(int32_t device, double* tflops, double* sm_mhz, int32_t* sm_count) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fail(LMH_ENODEVICE, "lmh_measure_fp64_peak: no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(a));
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double flops = 2.0 * 64.0 * iters * (double)threads * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    CU(cudaGetLastError());
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    if (tflops) *tflops = best;
+    int clk = 0;
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, device);
+    if (sm_mhz) *sm_mhz = clk / 1000.0;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return LMH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1156 @@
+// lmh_model.cuh -- per-environment closed-loop stage pipeline of the batched NAO controller/simulator.
+//
+// One environment is evaluated by a GROUP of NT cooperating threads (NT = 32: one warp per env,
+// __syncwarp between phases; NT = 64/128: named barriers) over a workspace that lives in shared
+// memory.  Every phase is a parallel-for over independent work items followed by a group sync.
+// The same source compiles for the host with NT = 1 (sequential loops): that build is used by the
+// setup code (inverse kinematics of the initial posture) and by the CPU unit tests of the kernel
+// logic; it is never a fallback for the GPU path.
+//
+// What is computed follows the reference (paths relative to the upstream repo):
+//   Robot::updateState            src/Robot.cpp:45-160,176-238,264-298
+//   Dynamics::computeAll          src/Dynamics.cpp:4-216   (RNEA bias, CRBA, centroidal, Jdot*qdot)
+//   Kinematics::computeAll        src/invKinematics.cpp:72-149,271-276
+//   Robot::updateVelocityState    src/Robot.cpp:271-274,300-310
+//   Mpc3dLip::compute             src/mpcLinearPendulum.cpp:78-133
+//   Controller::WBC / solveQP     src/controller.cpp:81-154,156-294,296-479
+//   dynamics() closure, rk4Step   apps/offline/main.cpp:91-122, include/.../general/rk4.hpp:5-18
+// How it is computed is not: spatial transforms are kept as (R,p) pairs, the gravity bias uses the
+// linearity of RNEA in the base acceleration, the MPC is a precomputed gain vector, and the WBC QP is
+// solved in a reduced space (see qp_* below) by a primal active-set method on the 32 contact
+// coefficients.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "lmh_capi.h"
+
+#if defined(__CUDACC__)
+#define LMH_HD __host__ __device__ __forceinline__
+#define LMH_HDN __host__ __device__
+#else
+#define LMH_HD inline
+#define LMH_HDN
+#endif
+
+namespace lmh {
+
+constexpr int NQ = 30;      // generalized coordinates (6 base + 24 joints), Robot.hpp:11
+constexpr int NJ = 24;      // actuated joints, Robot.hpp:12
+constexpr int NF = 27;      // frames that matter (frame 27 of the reference is massless, unactuated, unused)
+constexpr int NCH = 5;      // kinematic chains hanging off the torso
+constexpr int MAXDEPTH = 7;
+constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyramid edges)
+constexpr int MPC_MAXN = 320;
+constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
+constexpr int LDQ = 33;
+
+// chain c: frames chain_first[c] .. chain_first[c]+chain_len[c]-1, depth 1..chain_len[c]
+LMH_HD int chain_first(int c) { return c == 0 ? 1 : c == 1 ? 8 : c == 2 ? 15 : c == 3 ? 20 : 25; }
+LMH_HD int chain_len(int c) { return c < 2 ? 7 : c < 4 ? 5 : 2; }     // frames (legs include the sole)
+LMH_HD int chain_nact(int c) { return c < 2 ? 6 : c < 4 ? 5 : 2; }    // actuated frames
+LMH_HD int chain_joint0(int c) { return c == 0 ? 0 : c == 1 ? 6 : c == 2 ? 12 : c == 3 ? 17 : 22; }
+// actuated joint index (0..23) of a frame, or -1 (src/Robot.cpp:169-174)
+LMH_HD int frame_joint(int i) {
+    if (i == 0 || i == 7 || i == 14) return -1;
+    return i < 7 ? i - 1 : i < 14 ? i - 2 : i - 3;
+}
+LMH_HD int frame_parent(int i) { return (i == 1 || i == 8 || i == 15 || i == 20 || i == 25) ? 0 : i - 1; }
+LMH_HD int joint_chain(int a) { return a < 6 ? 0 : a < 12 ? 1 : a < 17 ? 2 : a < 22 ? 3 : 4; }
+
+// ------------------------------------------------------------------------------------------------
+// Constants shared by every environment of a batch (device global memory, read-only).
+struct Consts {
+    double Isp[28 * 36];      // spatial inertia of each frame, joint frame, row-major 6x6 (Dynamics.cpp:4-13)
+    double mc[28 * 4];        // {com_x, com_y, com_z, mass} in the joint frame
+    double th_off[24];        // theta offset of each joint's DH transform (Robot.cpp:59-87)
+    double dh_ca[24], dh_sa[24], dh_r[24], dh_d[24];   // cos/sin(alpha), r, d (Robot.cpp:180-196)
+    double pre[NCH * 12];     // fixed transform between the torso and each chain's first joint (R row-major, p)
+    double sole_x;            // sole offset along x of the ankle-roll frame (Robot.cpp:106-117)
+    double mass, gravity;
+    double qdes[NQ];          // Robot::desiredPosture (Robot.cpp:253-262)
+    double Rdes[9];           // desired sole orientation (Robot.cpp:28-31)
+    double Gf[6 * 16];        // per-foot wrench generators: rows 0-2 moment, 3-5 force (controller.cpp:156-294)
+    double GtG[16 * 16];      // Gf' Gf
+    double KpJ, KdJ, KpM, KdM, KpF, KdF;                                    // controller.hpp:100-111
+    double wCoML, wCoMK, wBasePos, wBaseAng, wJoints, wForce, wFoot, epsC;   // controller.hpp:118-124, controller.cpp:109-123
+    // LIPM MPC (mpcLinearPendulum.cpp:41-68,89-101): u0 = -(rPx . [pos,vel]) + sum_i r[i]*zmp[k+i]
+    double mpc_dt, mpc_A[4], mpc_B[2], mpc_rPx[2], mpc_zcom;
+    int32_t mpc_n1;           // horizon + 1
+    int32_t qp_max_iter;
+    double mpc_r[MPC_MAXN];
+    double dt;                // integrator step (Clock.hpp)
+};
+
+// Per-environment plan data shared through plan ids (global memory).
+struct Plan {
+    const double* zmp_x;      // [n_plans][zmp_len]
+    const double* zmp_y;
+    const double* foot_coef;  // [n_plans][2 feet][20] : x(6) y(6) z(8), ascending powers (footRefTrajectory.cpp:4-47)
+    int32_t zmp_len;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Workspace of one environment (shared memory on the device).  Regions are reused across the
+// model / assembly / QP phases; see DESIGN.md for the lifetime table.
+struct EnvWS {
+    // ---- state of the stage being evaluated
+    double q[NQ], v[NQ], vh[NQ];   // vh: velocity held by the Robot object from the PREVIOUS stage (controller.cpp:48-79)
+    double vb[NQ], vhb[NQ];        // the same with the base twist as [omega; v] in the base frame
+    double t;
+    // ---- persistent through a stage
+    double R0[9], p0[3];           // torso pose
+    double Rs[2][9], ps[2][3];     // sole poses (frames 7, 14)
+    double M6[6 * NQ];             // rows 0..5 of the mass matrix [Ic0 | F2]
+    double Hc[NCH * 36];           // joint-space inertia, one 6x6 block per chain (chains do not couple)
+    double C[NQ], Cg[NQ];
+    double AG[6 * NQ], AGpqp[6];
+    double JF[12 * NQ], Jpqp[12];
+    double com[3], comVel[3], angMom[3], xRef[3], yRef[3];
+    double qppRef[NQ], hGpRef[6], footAccRef[12];
+    double ga[NQ], a[NQ], f12[12], qpp[NQ], tau[NJ], xdot[2 * NQ];
+    double Y[7 * NQ];              // rows 0..5: (La^-1 M6')', row 6: (La^-1 ga)'
+    double Sa[36], Ls[36], rhs[6], sv[6], lam[6];
+    double c[NC], cs[NC], pq[NC], mu[NC], zq[NC], qdiag[NC], ldiag[NC], piv[NC], ladiag[NQ];
+    double red[64];                // reduction scratch
+    int32_t free_mask[NC];
+    int32_t k_index, qp_iters, qp_status, pad_;
+    // ---- phase-overlaid scratch
+    union {
+        struct {                       // model phase
+            double Tw[NF * 12];        // world transforms (R row-major 9, p 3)
+            double Xl[NF * 12];        // local transform first, then parent-relative (R_rel, p_rel)
+            double vel[NF * 6], acc[NF * 6], frc[NF * 6];
+            double Ic[NF * 36];
+            double Xd[NCH * 36], Yt[NCH * 36];
+            double Fb[2][NJ * 6];
+            double Xn[2][2 * 18];      // running sole_X_j as (E, B) for both feet, double buffered
+        } m;
+        struct {                       // assembly + QP phase
+            double Ha[NQ * LDM];       // H_a, then its Cholesky factor (lower)
+            double Wm[6 * NC];         // Ls^-1 Jb' G
+            double Q[NC * LDQ];        // upper: Q = wF G'G + Wm'Wm + eps I ; lower: masked Cholesky factor
+        } s;
+    } u;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int NT_>
+struct Ctx {
+    static constexpr int NT = NT_;
+    int tid;
+    int bar_id;
+    LMH_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+        if (NT == 32) __syncwarp();
+        else if (NT > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT_) : "memory");
+#endif
+    }
+};
+#define LMH_FOR(i, n) for (int i = cx.tid; i < (n); i += Cx::NT)
+
+LMH_HD void lmh_sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// y = R x (R row-major 3x3), one component
+LMH_HD double rot_row(const double* R, int k, const double* x) { return R[3 * k] * x[0] + R[3 * k + 1] * x[1] + R[3 * k + 2] * x[2]; }
+// y = R' x, one component
+LMH_HD double rotT_row(const double* R, int k, const double* x) { return R[k] * x[0] + R[3 + k] * x[1] + R[6 + k] * x[2]; }
+LMH_HD double cross_k(const double* a, const double* b, int k) {
+    return k == 0 ? a[1] * b[2] - a[2] * b[1] : k == 1 ? a[2] * b[0] - a[0] * b[2] : a[0] * b[1] - a[1] * b[0];
+}
+// Motion transform of the reference, X = [[E,0],[-E p^,E]] with E = R', applied to [w; u] (generalizedFunctions.cpp:11-19)
+LMH_HD double xmotion_k(const double* Rp, const double* m, int k) {
+    const double* R = Rp;
+    const double* p = Rp + 9;
+    if (k < 3) return rotT_row(R, k, m);
+    double u[3] = {m[3] + cross_k(m, p, 0), m[4] + cross_k(m, p, 1), m[5] + cross_k(m, p, 2)};   // v + w x p
+    return rotT_row(R, k - 3, u);
+}
+// Its transpose applied to a force [n; f]:  [R n + p x (R f); R f]
+LMH_HD double xforceT_k(const double* Rp, const double* f, int k) {
+    const double* R = Rp;
+    const double* p = Rp + 9;
+    if (k >= 3) return rot_row(R, k - 3, f + 3);
+    double rf[3] = {rot_row(R, 0, f + 3), rot_row(R, 1, f + 3), rot_row(R, 2, f + 3)};
+    return rot_row(R, k, f) + cross_k(p, rf, k);
+}
+// dense 6x6 entry of X (row a, col b)
+LMH_HD double xdense(const double* Rp, int a, int b) {
+    const double* R = Rp;
+    const double* p = Rp + 9;
+    int ar = a % 3, bc = b % 3;
+    if (a < 3) return b < 3 ? R[3 * bc + ar] : 0.0;
+    if (b >= 3) return R[3 * bc + ar];
+    // -(E p^)[ar][bc] = -sum_k E[ar][k] * cm[k][bc], cm = crossMatrix(p)
+    double e0 = R[ar], e1 = R[3 + ar], e2 = R[6 + ar];
+    return bc == 0 ? -(e1 * p[2] - e2 * p[1]) : bc == 1 ? -(-e0 * p[2] + e2 * p[0]) : -(e0 * p[1] - e1 * p[0]);
+}
+
+// ================================================================================================
+// Phase 1: forward kinematics, parent-relative transforms, CoM.
+template <class Cx>
+LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    double* Tw = w.u.m.Tw;
+    double* Xl = w.u.m.Xl;
+    // torso pose (generalizedFunctions.cpp:52-72) and local DH transforms (Robot.cpp:176-223)
+    LMH_FOR(i, NF) {
+        if (i == 0) {
+            double sr, cr, sp, cp, sy, cy;
+            lmh_sincos(w.q[3], &sr, &cr);
+            lmh_sincos(w.q[4], &sp, &cp);
+            lmh_sincos(w.q[5], &sy, &cy);
+            double* R = Tw;
+            R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+            R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+            R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+            R[9] = w.q[0]; R[10] = w.q[1]; R[11] = w.q[2];
+            for (int k = 0; k < 9; ++k) w.R0[k] = R[k];
+            for (int k = 0; k < 3; ++k) w.p0[k] = R[9 + k];
+        } else if (i == 7 || i == 14) {
+            double* L = Xl + 12 * i;
+            L[0] = 1; L[1] = 0; L[2] = 0; L[3] = 0; L[4] = 1; L[5] = 0; L[6] = 0; L[7] = 0; L[8] = 1;
+            L[9] = K.sole_x; L[10] = 0; L[11] = 0;
+        } else {
+            int a = frame_joint(i);
+            double st, ct;
+            lmh_sincos(w.q[6 + a] + K.th_off[a], &st, &ct);
+            double ca = K.dh_ca[a], sa = K.dh_sa[a], r = K.dh_r[a], d = K.dh_d[a];
+            double L[12] = {ct, -st, 0.0, ca * st, ca * ct, -sa, sa * st, sa * ct, ca, d, -r * sa, r * ca};
+            double* O = Xl + 12 * i;
+            int c = (i == 1) ? 0 : (i == 8) ? 1 : (i == 15) ? 2 : (i == 20) ? 3 : (i == 25) ? 4 : -1;
+            if (c < 0) {
+                for (int k = 0; k < 12; ++k) O[k] = L[k];
+            } else {   // fold the fixed torso->chain transform into the first joint of the chain
+                const double* P = K.pre + 12 * c;
+                for (int r3 = 0; r3 < 3; ++r3) {
+                    for (int cc = 0; cc < 3; ++cc)
+                        O[3 * r3 + cc] = P[3 * r3] * L[cc] + P[3 * r3 + 1] * L[3 + cc] + P[3 * r3 + 2] * L[6 + cc];
+                    O[9 + r3] = P[3 * r3] * L[9] + P[3 * r3 + 1] * L[10] + P[3 * r3 + 2] * L[11] + P[9 + r3];
+                }
+            }
+        }
+    }
+    cx.sync();
+    // chained world transforms, one tree level per pass
+    for (int d = 1; d <= MAXDEPTH; ++d) {
+        LMH_FOR(it, NCH * 12) {
+            int c = it / 12, e = it % 12;
+            if (d <= chain_len(c)) {
+                int i = chain_first(c) + d - 1;
+                const double* P = Tw + 12 * frame_parent(i);
+                const double* L = Xl + 12 * i;
+                double* O = Tw + 12 * i;
+                if (e < 9) {
+                    int r3 = e / 3, cc = e % 3;
+                    O[e] = P[3 * r3] * L[cc] + P[3 * r3 + 1] * L[3 + cc] + P[3 * r3 + 2] * L[6 + cc];
+                } else {
+                    int r3 = e - 9;
+                    O[e] = P[3 * r3] * L[9] + P[3 * r3 + 1] * L[10] + P[3 * r3 + 2] * L[11] + P[9 + r3];
+                }
+            }
+        }
+        cx.sync();
+    }
+    // parent-relative transform "inverse-by-transpose(T_parent) * T_i" (Robot.cpp:276-298, generalizedFunctions.cpp:21-27)
+    LMH_FOR(it, NF * 12) {
+        int i = it / 12, e = it % 12;
+        double* O = Xl + 12 * i;
+        const double* Ti = Tw + 12 * i;
+        if (i == 0) {
+            O[e] = Ti[e];
+        } else {
+            const double* P = Tw + 12 * frame_parent(i);
+            if (e < 9) {
+                int r3 = e / 3, cc = e % 3;
+                O[e] = P[r3] * Ti[cc] + P[3 + r3] * Ti[3 + cc] + P[6 + r3] * Ti[6 + cc];
+            } else {
+                int r3 = e - 9;
+                double pi = P[r3] * Ti[9] + P[3 + r3] * Ti[10] + P[6 + r3] * Ti[11];
+                double pp = P[r3] * P[9] + P[3 + r3] * P[10] + P[6 + r3] * P[11];
+                O[e] = pi - pp;
+            }
+        }
+    }
+    // centre of mass partial sums (Robot.cpp:225-238); 3 components x 8 partials
+    LMH_FOR(it, 24) {
+        int k = it % 3, part = it / 3;
+        double s = 0.0;
+        for (int i = part; i < NF; i += 8) {
+            const double* Ti = Tw + 12 * i;
+            const double* mc = K.mc + 4 * i;
+            s += mc[3] * (Ti[3 * k] * mc[0] + Ti[3 * k + 1] * mc[1] + Ti[3 * k + 2] * mc[2] + Ti[9 + k]);
+        }
+        w.red[it] = s;
+    }
+    LMH_FOR(it, 2 * 12) {   // keep the sole poses
+        int s = it / 12, e = it % 12;
+        const double* Ti = Tw + 12 * (s == 0 ? 7 : 14);
+        if (e < 9) w.Rs[s][e] = Ti[e]; else w.ps[s][e - 9] = Ti[e];
+    }
+    cx.sync();
+    LMH_FOR(k, 3) {
+        double s = 0.0;
+        for (int part = 0; part < 8; ++part) s += w.red[3 * part + k];
+        w.com[k] = s / K.mass;
+    }
+    cx.sync();
+}
+
+// base twist of a generalized velocity into the torso frame: [w; v] -> X0 [w; v]  (generalizedFunctions.cpp:195-206)
+template <class Cx>
+LMH_HDN void base_twist_phase(const Cx& cx, EnvWS& w) {
+    LMH_FOR(it, 2 * NQ) {
+        int which = it / NQ, k = it % NQ;
+        const double* src = which == 0 ? w.v : w.vh;
+        double* dst = which == 0 ? w.vb : w.vhb;
+        if (k >= 6) dst[k] = src[k];
+        else {
+            double m[6] = {src[3], src[4], src[5], src[0], src[1], src[2]};
+            double Rp[12];
+            for (int e = 0; e < 9; ++e) Rp[e] = w.R0[e];
+            for (int e = 0; e < 3; ++e) Rp[9 + e] = w.p0[e];
+            dst[k] = xmotion_k(Rp, m, k);
+        }
+    }
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 2: RNEA with zero base acceleration on the HELD velocity -> Cg, Jdot*qdot of both soles
+// (Dynamics.cpp:29-60,124-200).
+template <class Cx>
+LMH_HDN void rnea_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    double* vel = w.u.m.vel;
+    double* acc = w.u.m.acc;
+    double* frc = w.u.m.frc;
+    const double* Xl = w.u.m.Xl;
+    LMH_FOR(k, 6) { vel[k] = w.vhb[k]; acc[k] = 0.0; }
+    cx.sync();
+    for (int d = 1; d <= MAXDEPTH; ++d) {
+        LMH_FOR(it, NCH * 6) {
+            int c = it / 6, k = it % 6;
+            if (d <= chain_len(c)) {
+                int i = chain_first(c) + d - 1;
+                int a = frame_joint(i);
+                double x = xmotion_k(Xl + 12 * i, vel + 6 * frame_parent(i), k);
+                if (a >= 0 && k == 2) x += w.vhb[6 + a];
+                vel[6 * i + k] = x;
+            }
+        }
+        cx.sync();
+        LMH_FOR(it, NCH * 6) {
+            int c = it / 6, k = it % 6;
+            if (d <= chain_len(c)) {
+                int i = chain_first(c) + d - 1;
+                int a = frame_joint(i);
+                double x = xmotion_k(Xl + 12 * i, acc + 6 * frame_parent(i), k);
+                if (a >= 0) {   // + (v x S) qd with S = e_z
+                    double qd = w.vhb[6 + a];
+                    const double* vi = vel + 6 * i;
+                    double col = k == 0 ? vi[1] : k == 1 ? -vi[0] : k == 3 ? vi[4] : k == 4 ? -vi[3] : 0.0;
+                    x += col * qd;
+                }
+                acc[6 * i + k] = x;
+            }
+        }
+        cx.sync();
+    }
+    // h = I v  (into frc), then f = I a + v x* h
+    LMH_FOR(it, NF * 6) {
+        int i = it / 6, k = it % 6;
+        const double* I = K.Isp + 36 * i + 6 * k;
+        const double* vi = vel + 6 * i;
+        frc[it] = I[0] * vi[0] + I[1] * vi[1] + I[2] * vi[2] + I[3] * vi[3] + I[4] * vi[4] + I[5] * vi[5];
+    }
+    cx.sync();
+    double fnew[(NF * 6 + Cx::NT - 1) / Cx::NT];
+    {
+        int n = 0;
+        LMH_FOR(it, NF * 6) {
+            int i = it / 6, k = it % 6;
+            const double* I = K.Isp + 36 * i + 6 * k;
+            const double* ai = acc + 6 * i;
+            const double* vi = vel + 6 * i;
+            const double* h = frc + 6 * i;
+            double x = I[0] * ai[0] + I[1] * ai[1] + I[2] * ai[2] + I[3] * ai[3] + I[4] * ai[4] + I[5] * ai[5];
+            // crf(v) h = [w x n + u x f ; w x f]
+            if (k < 3) x += cross_k(vi, h, k) + cross_k(vi + 3, h + 3, k);
+            else x += cross_k(vi, h + 3, k - 3);
+            fnew[n++] = x;
+        }
+    }
+    cx.sync();
+    {
+        int n = 0;
+        LMH_FOR(it, NF * 6) frc[it] = fnew[n++];
+    }
+    cx.sync();
+    // backward pass, deepest level first; the soles carry no force
+    for (int d = MAXDEPTH; d >= 2; --d) {
+        LMH_FOR(it, NCH * 6) {
+            int c = it / 6, k = it % 6;
+            if (d <= chain_nact(c)) {
+                int i = chain_first(c) + d - 1;
+                frc[6 * (i - 1) + k] += xforceT_k(Xl + 12 * i, frc + 6 * i, k);
+            }
+        }
+        cx.sync();
+    }
+    LMH_FOR(k, 6) {
+        double s = frc[k];
+        for (int c = NCH - 1; c >= 0; --c) s += xforceT_k(Xl + 12 * chain_first(c), frc + 6 * chain_first(c), k);
+        w.Cg[k] = s;
+    }
+    LMH_FOR(a, NJ) {
+        int c = joint_chain(a);
+        int i = chain_first(c) + (a - chain_joint0(c));
+        w.Cg[6 + a] = frc[6 * i + 2];
+    }
+    // Jdot*qdot = world-rotated spatial acceleration of the soles (Dynamics.cpp:165-200)
+    LMH_FOR(it, 12) {
+        int s = it / 6, k = it % 6;
+        const double* ai = acc + 6 * (s == 0 ? 7 : 14) + (k < 3 ? 0 : 3);
+        w.Jpqp[it] = rot_row(w.Rs[s], k % 3, ai);
+    }
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 3: CRBA (Dynamics.cpp:62-101) -> M6 = [Ic0 | F2], Hc (per-chain joint blocks).
+template <class Cx>
+LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    double* Ic = w.u.m.Ic;
+    double* Xd = w.u.m.Xd;
+    double* Yt = w.u.m.Yt;
+    const double* Xl = w.u.m.Xl;
+    LMH_FOR(it, NF * 36) Ic[it] = K.Isp[it];
+    LMH_FOR(it, NCH * 36) w.Hc[it] = 0.0;
+    cx.sync();
+    int cur = 0;
+    for (int d = MAXDEPTH - 1; d >= 1; --d) {   // actuated depths 6..1
+        // (a) dense X of this level's frames; new F vector of each frame = column 2 of its final Ic
+        LMH_FOR(it, NCH * 36) {
+            int c = it / 36, e = it % 36;
+            if (d <= chain_nact(c)) Xd[it] = xdense(Xl + 12 * (chain_first(c) + d - 1), e / 6, e % 6);
+        }
+        LMH_FOR(it, NCH * 6) {
+            int c = it / 6, k = it % 6;
+            if (d <= chain_nact(c)) {
+                int i = chain_first(c) + d - 1;
+                int a = chain_joint0(c) + d - 1;
+                double fk = Ic[36 * i + 6 * k + 2];
+                w.u.m.Fb[cur][6 * a + k] = fk;
+                if (k == 2) w.Hc[36 * c + 7 * (d - 1)] = fk;
+            }
+        }
+        cx.sync();
+        // (b) Yt = Ic_i X_i ; F vectors of every joint at depth >= d move one frame up: F <- X_i' F
+        LMH_FOR(it, NCH * 36) {
+            int c = it / 36, e = it % 36;
+            if (d <= chain_nact(c)) {
+                int r = e / 6, cc = e % 6;
+                const double* I = Ic + 36 * (chain_first(c) + d - 1) + 6 * r;
+                const double* X = Xd + 36 * c + cc;
+                Yt[it] = I[0] * X[0] + I[1] * X[6] + I[2] * X[12] + I[3] * X[18] + I[4] * X[24] + I[5] * X[30];
+            }
+        }
+        LMH_FOR(it, NJ * 6) {
+            int a = it / 6, k = it % 6;
+            int c = joint_chain(a);
+            int da = a - chain_joint0(c) + 1;       // depth of joint a
+            if (da >= d) {
+                int i = chain_first(c) + d - 1;     // frame being crossed
+                double x = xforceT_k(Xl + 12 * i, w.u.m.Fb[cur] + 6 * a, k);
+                w.u.m.Fb[cur ^ 1][it] = x;
+                if (d > 1 && k == 2) {              // H(parent joint, a), symmetric
+                    int pj = d - 2, aj = da - 1;
+                    w.Hc[36 * c + 6 * pj + aj] = x;
+                    w.Hc[36 * c + 6 * aj + pj] = x;
+                }
+                if (d == 1) w.M6[NQ * k + 6 + a] = x;   // F2 column
+            }
+        }
+        cx.sync();
+        // (c) Ic_parent += X' Yt
+        if (d > 1) {
+            LMH_FOR(it, NCH * 36) {
+                int c = it / 36, e = it % 36;
+                if (d <= chain_nact(c)) {
+                    int r = e / 6, cc = e % 6;
+                    const double* X = Xd + 36 * c + r;
+                    const double* Y = Yt + 36 * c + cc;
+                    Ic[36 * (chain_first(c) + d - 2) + e] +=
+                        X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
+                }
+            }
+        } else {
+            LMH_FOR(e, 36) {
+                int r = e / 6, cc = e % 6;
+                double s = Ic[e];
+                for (int c = NCH - 1; c >= 0; --c) {
+                    const double* X = Xd + 36 * c + r;
+                    const double* Y = Yt + 36 * c + cc;
+                    s += X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
+                }
+                w.M6[NQ * r + cc] = s;   // Ic0
+            }
+        }
+        cx.sync();
+        cur ^= 1;
+    }
+}
+
+// mass matrix entry M(6+a, 6+b)
+LMH_HD double hjoint(const EnvWS& w, int a, int b) {
+    int c = joint_chain(a);
+    if (joint_chain(b) != c) return 0.0;
+    return w.Hc[36 * c + 6 * (a - chain_joint0(c)) + (b - chain_joint0(c))];
+}
+
+// ================================================================================================
+// Phase 4: gravity bias by linearity, centroidal matrix (Dynamics.cpp:103-121), sole Jacobians
+// (invKinematics.cpp:72-149), CoM velocity / angular momentum (Robot.cpp:300-310).
+template <class Cx>
+LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    const double* Xl = w.u.m.Xl;
+    // C = Cg + M[:,3:6] * (R0' g e_z)   (RNEA is linear in the base acceleration; Dynamics.cpp:34-35,52)
+    LMH_FOR(i, NQ) {
+        double g0 = K.gravity * w.R0[6], g1 = K.gravity * w.R0[7], g2 = K.gravity * w.R0[8];
+        double m0, m1, m2;
+        if (i < 6) { m0 = w.M6[NQ * i + 3]; m1 = w.M6[NQ * i + 4]; m2 = w.M6[NQ * i + 5]; }
+        else { m0 = w.M6[NQ * 3 + i]; m1 = w.M6[NQ * 4 + i]; m2 = w.M6[NQ * 5 + i]; }
+        w.C[i] = w.Cg[i] + (m0 * g0 + m1 * g1 + m2 * g2);
+    }
+    // AG = X1G M6, AGpqp = X1G Cg[0:6], X1G = [[R0, -R0 p1G^],[0, R0]]
+    LMH_FOR(j, NQ + 1) {
+        double p1G[3] = {w.M6[NQ * 2 + 4] / K.mass, w.M6[NQ * 0 + 5] / K.mass, w.M6[NQ * 1 + 3] / K.mass};
+        double top[3], bot[3];
+        if (j < NQ) for (int k = 0; k < 3; ++k) { top[k] = w.M6[NQ * k + j]; bot[k] = w.M6[NQ * (3 + k) + j]; }
+        else for (int k = 0; k < 3; ++k) { top[k] = w.Cg[k]; bot[k] = w.Cg[3 + k]; }
+        double u[3] = {top[0] - cross_k(p1G, bot, 0), top[1] - cross_k(p1G, bot, 1), top[2] - cross_k(p1G, bot, 2)};
+        for (int k = 0; k < 3; ++k) {
+            double a = rot_row(w.R0, k, u), b = rot_row(w.R0, k, bot);
+            if (j < NQ) { w.AG[NQ * k + j] = a; w.AG[NQ * (3 + k) + j] = b; }
+            else { w.AGpqp[k] = a; w.AGpqp[3 + k] = b; }
+        }
+    }
+    LMH_FOR(it, 12 * NQ) w.JF[it] = 0.0;
+    // running sole_X_j = (E, B) for both feet, starting from the sole frame
+    LMH_FOR(it, 36) {
+        int s = it / 18, e = it % 18;
+        const double* Rp = Xl + 12 * (s == 0 ? 7 : 14);
+        w.u.m.Xn[0][it] = e < 9 ? xdense(Rp, e / 3, e % 3) : xdense(Rp, 3 + (e - 9) / 3, (e - 9) % 3);
+    }
+    cx.sync();
+    int cur = 0;
+    for (int step = 0; step < 6; ++step) {   // j = ankle roll ... hip yaw-pitch
+        LMH_FOR(it, 36) {
+            int s = it / 18, e = it % 18;
+            int j = (s == 0 ? 6 : 13) - step;
+            const double* Xc = w.u.m.Xn[cur] + 18 * s;     // E (9), B (9)
+            const double* Rp = Xl + 12 * j;
+            int r = (e % 9) / 3, cc = e % 3;
+            double x;
+            if (e < 9) {     // E_new = E * Ej
+                x = Xc[3 * r] * xdense(Rp, 0, cc) + Xc[3 * r + 1] * xdense(Rp, 1, cc) + Xc[3 * r + 2] * xdense(Rp, 2, cc);
+            } else {         // B_new = B * Ej + E * Bj
+                x = Xc[9 + 3 * r] * xdense(Rp, 0, cc) + Xc[9 + 3 * r + 1] * xdense(Rp, 1, cc) + Xc[9 + 3 * r + 2] * xdense(Rp, 2, cc) +
+                    Xc[3 * r] * xdense(Rp, 3, cc) + Xc[3 * r + 1] * xdense(Rp, 4, cc) + Xc[3 * r + 2] * xdense(Rp, 5, cc);
+            }
+            w.u.m.Xn[cur ^ 1][it] = x;
+        }
+        // joint column of frame j = world-rotated column 2 of the current sole_X_(j)
+        LMH_FOR(it, 12) {
+            int s = it / 6, k = it % 6;
+            int j = (s == 0 ? 6 : 13) - step;
+            const double* Xc = w.u.m.Xn[cur] + 18 * s;
+            const double* col = k < 3 ? Xc : Xc + 9;
+            double cv[3] = {col[2], col[5], col[8]};
+            w.JF[NQ * (6 * s + k) + 6 + frame_joint(j)] = rot_row(w.Rs[s], k % 3, cv);
+        }
+        cx.sync();
+        cur ^= 1;
+    }
+    // base block: rotated sole_X_base = [[E,0],[B,E]]
+    LMH_FOR(it, 72) {
+        int s = it / 36, k = (it % 36) / 6, b = it % 6;
+        const double* Xc = w.u.m.Xn[cur] + 18 * s;
+        double cv[3];
+        if (k < 3) { if (b < 3) { cv[0] = Xc[b]; cv[1] = Xc[3 + b]; cv[2] = Xc[6 + b]; } else { cv[0] = cv[1] = cv[2] = 0.0; } }
+        else { const double* S = b < 3 ? Xc + 9 : Xc; int bb = b % 3; cv[0] = S[bb]; cv[1] = S[3 + bb]; cv[2] = S[6 + bb]; }
+        w.JF[NQ * (6 * s + k) + b] = rot_row(w.Rs[s], k % 3, cv);
+    }
+    cx.sync();
+    // h = AG vb (current velocity)
+    LMH_FOR(k, 6) {
+        double s = 0.0;
+        for (int j = 0; j < NQ; ++j) s += w.AG[NQ * k + j] * w.vb[j];
+        if (k < 3) w.angMom[k] = s; else w.comVel[k - 3] = s / K.mass;
+    }
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 5: LIPM MPC as a precomputed gain (mpcLinearPendulum.cpp:78-109) + PD references
+// (controller.cpp:296-386).
+template <class Cx>
+LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
+    const int n1 = K.mpc_n1;
+    int kidx = (int)(w.t / K.mpc_dt);                // mpcLinearPendulum.cpp:92 -- same FP64 expression
+    int k0 = kidx;
+    if (k0 < 0) k0 = 0;
+    if (k0 + n1 > P.zmp_len) k0 = P.zmp_len - n1;    // the reference would read out of bounds here; we clamp
+    LMH_FOR(it, 32) {
+        int ax = it / 16, part = it % 16;
+        const double* z = (ax == 0 ? P.zmp_x : P.zmp_y) + (size_t)plan_id * P.zmp_len + k0;
+        double s = 0.0;
+        for (int i = part; i < n1; i += 16) s += K.mpc_r[i] * z[i];
+        w.red[it] = s;
+    }
+    cx.sync();
+    LMH_FOR(ax, 2) {
+        double s = 0.0;
+        for (int part = 0; part < 16; ++part) s += w.red[16 * ax + part];
+        double p = w.com[ax], vv = w.comVel[ax];
+        double u = s - (K.mpc_rPx[0] * p + K.mpc_rPx[1] * vv);
+        double* ref = ax == 0 ? w.xRef : w.yRef;
+        ref[0] = K.mpc_A[0] * p + K.mpc_A[1] * vv + K.mpc_B[0] * u;
+        ref[1] = K.mpc_A[2] * p + K.mpc_A[3] * vv + K.mpc_B[1] * u;
+        ref[2] = u;
+        if (ax == 0) w.k_index = kidx;
+    }
+    // joint-space PD (controller.cpp:296-309): world-form errors, 3<->3 swap of the base slots
+    LMH_FOR(i, NQ) {
+        int src = i < 3 ? i + 3 : i < 6 ? i - 3 : i;
+        w.qppRef[i] = K.KpJ * (K.qdes[src] - w.q[src]) + K.KdJ * (0.0 - w.v[src]);
+    }
+    cx.sync();
+    // centroidal momentum rate (controller.cpp:311-327)
+    LMH_FOR(k, 6) {
+        if (k < 3) w.hGpRef[k] = K.KdM * (0.0 - w.angMom[k]);
+        else {
+            int j = k - 3;
+            double pr = j == 0 ? w.xRef[0] : j == 1 ? w.yRef[0] : K.mpc_zcom;
+            double vr = j == 0 ? w.xRef[1] : j == 1 ? w.yRef[1] : 0.0;
+            double ar = j == 0 ? w.xRef[2] : j == 1 ? w.yRef[2] : 0.0;
+            w.hGpRef[k] = K.mass * (K.KpM * (pr - w.com[j]) + K.KdM * (vr - w.comVel[j]) + ar);
+        }
+    }
+    // feet (controller.cpp:329-386)
+    LMH_FOR(it, 12) {
+        int s = it / 6, k = it % 6;
+        double velk = 0.0;
+        for (int j = 0; j < NQ; ++j) velk += w.JF[NQ * it + j] * w.vb[j];
+        double out;
+        if (k < 3) {
+            // e = -Rdes * log(Rdes' R)
+            double E[9];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) E[3 * r + c] = K.Rdes[r] * w.Rs[s][c] + K.Rdes[3 + r] * w.Rs[s][3 + c] + K.Rdes[6 + r] * w.Rs[s][6 + c];
+            double tr = E[0] + E[4] + E[8];
+            double cth = fmax(-1.0, fmin(1.0, (tr - 1.0) / 2.0));
+            double phi = acos(cth);
+            double ax[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
+            double sc = phi < 1e-6 ? 0.5 : phi / (2.0 * sin(phi));
+            double l[3] = {sc * ax[0], sc * ax[1], sc * ax[2]};
+            double eo = -rot_row(K.Rdes, k, l);
+            out = K.KpF * eo + K.KdF * (0.0 - velk) + 0.0;
+        } else {
+            int j = k - 3;
+            const double* cf = P.foot_coef + ((size_t)plan_id * 2 + s) * 20 + (j == 0 ? 0 : j == 1 ? 6 : 12);
+            int nc = j == 2 ? 8 : 6;
+            double pos = 0.0, vr = 0.0, ar = 0.0, tp = 1.0, tv = 1.0, ta = 1.0;
+            for (int i = 0; i < nc; ++i) { pos += cf[i] * tp; tp *= w.t; }
+            for (int i = 1; i < nc; ++i) { vr += (double)i * cf[i] * tv; tv *= w.t; }
+            for (int i = 2; i < nc; ++i) { ar += (double)(i - 1) * ((double)i * cf[i]) * ta; ta *= w.t; }
+            out = K.KpF * (pos - w.ps[s][j]) + K.KdF * (vr - velk) + ar;
+        }
+        w.footAccRef[it] = out;
+    }
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 6: QP data.  H_a = AG' Wc AG + Wj + JF' Wf JF, g_a (controller.cpp:94-132).  Overwrites
+// the model scratch (union), so everything it needs was copied to the persistent part.
+template <class Cx>
+LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    double* Ha = w.u.s.Ha;
+    LMH_FOR(it, NQ * (NQ + 1) / 2) {
+        // unrank the lower-triangular index
+        int i = (int)((sqrt(8.0 * it + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= it) ++i;
+        while (i * (i + 1) / 2 > it) --i;
+        int j = it - i * (i + 1) / 2;
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += K.wCoMK * w.AG[NQ * k + i] * w.AG[NQ * k + j];
+        for (int k = 3; k < 6; ++k) s += K.wCoML * w.AG[NQ * k + i] * w.AG[NQ * k + j];
+        double sj = 0.0;
+        for (int k = 0; k < 12; ++k) sj += w.JF[NQ * k + i] * w.JF[NQ * k + j];
+        s += K.wFoot * sj;
+        if (i == j) s += i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
+        Ha[LDM * i + j] = s;
+    }
+    LMH_FOR(i, NQ) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += (k < 3 ? K.wCoMK : K.wCoML) * w.AG[NQ * k + i] * (w.AGpqp[k] - w.hGpRef[k]);
+        double sj = 0.0;
+        for (int k = 0; k < 12; ++k) sj += w.JF[NQ * k + i] * (w.Jpqp[k] - w.footAccRef[k]);
+        double wj = i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
+        w.ga[i] = s - wj * w.qppRef[i] + K.wFoot * sj;
+    }
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 7: the WBC QP (controller.cpp:388-479) in reduced form.
+//   variables a (30), c (32);  f12 = G c eliminated (controller.cpp:156-294 rows 6..17)
+//   min 1/2 a'Ha a + ga'a + 1/2 wF |G c|^2 + 1/2 eps |c|^2   s.t.  M6 a - Jb' G c = -C6,  c >= 0
+// a is eliminated through the Cholesky factor of Ha and the 6x6 Schur complement Sa = M6 Ha^-1 M6',
+// leaving   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I,
+// which a primal active-set method solves exactly (masked Cholesky of Q per working set).
+template <class Cx>
+LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    double* Ha = w.u.s.Ha;
+    double* Y = w.Y;
+    // rows 30..36 of the augmented matrix: M6 and ga' ; left-looking Cholesky carries them along so
+    // that they come out as (La^-1 M6')' and (La^-1 ga)'.
+    LMH_FOR(it, 7 * NQ) Y[it] = it < 6 * NQ ? w.M6[it] : w.ga[it - 6 * NQ];
+    cx.sync();
+    for (int k = 0; k < NQ; ++k) {
+        // column k: s_i = A[i][k] - sum_{m<k} L[i][m] L[k][m]   (element (i,k) is touched by item i only)
+        LMH_FOR(i0, NQ + 7 - k) {
+            int i = k + i0;
+            double* ri = i < NQ ? Ha + LDM * i : Y + NQ * (i - NQ);
+            const double* rk = Ha + LDM * k;
+            double s0 = ri[k], s1 = 0.0;
+            int m = 0;
+            for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
+            if (m < k) s0 -= ri[m] * rk[m];
+            ri[k] = s0 + s1;
+        }
+        cx.sync();
+        double dk = sqrt(Ha[LDM * k + k]);     // nobody writes the pivot in the next loop
+        LMH_FOR(i0, NQ + 7 - k) {
+            int i = k + i0;
+            if (i == k) w.ladiag[k] = dk;
+            else {
+                double* ri = i < NQ ? Ha + LDM * i : Y + NQ * (i - NQ);
+                ri[k] = ri[k] / dk;
+            }
+        }
+        cx.sync();
+    }
+    // Sa = Y Y' (6x6), rhs = C6 - Y w
+    LMH_FOR(it, 42) {
+        int r = it / 6, c = it % 6;
+        double s = 0.0;
+        if (r < 6) {
+            for (int m = 0; m < NQ; ++m) s += Y[NQ * r + m] * Y[NQ * c + m];
+            w.Sa[it] = s;
+        } else {
+            for (int m = 0; m < NQ; ++m) s += Y[NQ * c + m] * Y[NQ * 6 + m];
+            w.rhs[c] = w.C[c] - s;
+        }
+    }
+    cx.sync();
+    // Ls = chol(Sa), sv = Ls^-1 rhs -- 6x6, every thread redundantly in registers
+    double Ls[36];
+    {
+        for (int e = 0; e < 36; ++e) Ls[e] = w.Sa[e];
+        for (int k = 0; k < 6; ++k) {
+            double s = Ls[7 * k];
+            for (int m = 0; m < k; ++m) s -= Ls[6 * k + m] * Ls[6 * k + m];
+            double dk = sqrt(s);
+            Ls[7 * k] = dk;
+            for (int i = k + 1; i < 6; ++i) {
+                double t = Ls[6 * i + k];
+                for (int m = 0; m < k; ++m) t -= Ls[6 * i + m] * Ls[6 * k + m];
+                Ls[6 * i + k] = t / dk;
+            }
+        }
+    }
+    // Wm = Ls^-1 Jb' G  (6 x 32; Jb = JF[:,0:6]) and pq = Wm' sv
+    LMH_FOR(i, NC + 1) {
+        double col[6];
+        if (i < NC) {
+            int foot = i / 16, gi = i % 16;
+            for (int r = 0; r < 6; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < 6; ++k) s += w.JF[NQ * (6 * foot + k) + r] * K.Gf[16 * k + gi];
+                col[r] = s;
+            }
+        } else {
+            for (int r = 0; r < 6; ++r) col[r] = w.rhs[r];
+        }
+        for (int r = 0; r < 6; ++r) {
+            double s = col[r];
+            for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * col[m];
+            col[r] = s / Ls[7 * r];
+        }
+        if (i < NC) for (int r = 0; r < 6; ++r) w.u.s.Wm[NC * r + i] = col[r];
+        else for (int r = 0; r < 6; ++r) w.sv[r] = col[r];
+    }
+    cx.sync();
+    double* Q = w.u.s.Q;
+    const double* Wm = w.u.s.Wm;
+    LMH_FOR(it, NC * (NC + 1) / 2) {
+        int i = (int)((sqrt(8.0 * it + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= it) ++i;
+        while (i * (i + 1) / 2 > it) --i;
+        int j = it - i * (i + 1) / 2;     // j <= i ; store at the UPPER position (j,i)
+        double s = 0.0;
+        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * Wm[NC * r + j];
+        if (i / 16 == j / 16) s += K.wForce * K.GtG[16 * (i % 16) + (j % 16)];
+        if (i == j) { w.qdiag[i] = s + K.epsC; }
+        else Q[LDQ * j + i] = s;
+    }
+    LMH_FOR(i, NC) {
+        double s = 0.0;
+        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * w.sv[r];
+        w.pq[i] = s;
+        w.free_mask[i] = 1;
+        w.c[i] = 0.0;
+    }
+    cx.sync();
+
+    // ---- primal active set on c >= 0
+    int iters = 0, status = 0;
+    bool have_feasible = false;
+    while (true) {
+        ++iters;
+        // masked left-looking Cholesky of Q_FF in the lower triangle, forward substitution of pq fused
+        for (int k = 0; k < NC; ++k) {
+            const bool fk = w.free_mask[k] != 0;
+            LMH_FOR(i0, NC + 1 - k) {
+                int i = k + i0;   // i == NC : the rhs row
+                double s0 = 0.0;
+                if (fk) {
+                    if (i < NC) {
+                        if (w.free_mask[i]) {
+                            s0 = i == k ? w.qdiag[k] : Q[LDQ * k + i];
+                            const double* ri = Q + LDQ * i;
+                            const double* rk = Q + LDQ * k;
+                            double s1 = 0.0;
+                            int m = 0;
+                            for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
+                            if (m < k) s0 -= ri[m] * rk[m];
+                            s0 += s1;
+                        }
+                    } else {
+                        s0 = w.pq[k];
+                        const double* rk = Q + LDQ * k;
+                        for (int m = 0; m < k; ++m) s0 -= w.zq[m] * rk[m];
+                    }
+                }
+                if (i == k) w.piv[k] = fk ? s0 : 1.0;
+                else if (i < NC) Q[LDQ * i + k] = s0;
+                else w.zq[k] = s0;
+            }
+            cx.sync();
+            double pv = w.piv[k];
+            double dk = sqrt(pv > 0.0 ? pv : 1e-300);
+            LMH_FOR(i0, NC + 1 - k) {
+                int i = k + i0;
+                if (i == k) w.ldiag[k] = dk;
+                else if (i < NC) Q[LDQ * i + k] = Q[LDQ * i + k] / dk;
+                else w.zq[k] = w.zq[k] / dk;
+            }
+            cx.sync();
+        }
+        // back substitution L' cs = zq (column oriented)
+        for (int k = NC - 1; k >= 0; --k) {
+            double xk = w.zq[k] / w.ldiag[k];
+            LMH_FOR(i, k + 1) {
+                if (i == k) w.cs[k] = w.free_mask[k] ? xk : 0.0;
+                else w.zq[i] -= Q[LDQ * k + i] * xk;
+            }
+            cx.sync();
+        }
+        // gradient on the working set: mu = Q cs - pq
+        LMH_FOR(i, NC) {
+            double s = -w.pq[i];
+            for (int j = 0; j < NC; ++j) {
+                double qij = i == j ? w.qdiag[i] : (i < j ? Q[LDQ * i + j] : Q[LDQ * j + i]);
+                s += qij * w.cs[j];
+            }
+            w.mu[i] = s;
+        }
+        cx.sync();
+        // decisions are taken redundantly by every thread from the shared vectors
+        double cmin = 0.0, pmax = 1.0;
+        for (int i = 0; i < NC; ++i) {
+            if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
+            pmax = fmax(pmax, fabs(w.pq[i]));
+        }
+        bool done = false;
+        int change = -1, to_free = 0;
+        double alpha = 1.0;
+        if (!have_feasible) {
+            if (cmin >= 0.0) {
+                have_feasible = true;     // unconstrained minimiser is feasible: check multipliers (none active) -> optimal
+                done = true;
+                for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < -1e-12 * pmax) done = false;
+                if (!done) { double worst = 0.0; for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; } to_free = 1; }
+                alpha = 1.0;
+            } else {
+                // first iterate: project onto the orthant, working set = the clipped coefficients
+                have_feasible = true;
+                alpha = -1.0;             // marker: projection step
+            }
+        } else if (cmin >= 0.0) {
+            double worst = -1e-12 * pmax;
+            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
+            if (change < 0) done = true; else to_free = 1;
+            alpha = 1.0;
+        } else {
+            double best = 2.0;
+            for (int i = 0; i < NC; ++i)
+                if (w.free_mask[i] && w.cs[i] < 0.0) {
+                    double dl = w.c[i] - w.cs[i];
+                    double r = dl > 0.0 ? w.c[i] / dl : 0.0;
+                    if (r < best) { best = r; change = i; }
+                }
+            alpha = best < 1.0 ? best : 1.0;
+            to_free = 0;
+        }
+        cx.sync();
+        LMH_FOR(i, NC) {
+            if (alpha < 0.0) {
+                double x = w.cs[i];
+                w.c[i] = x > 0.0 ? x : 0.0;
+                w.free_mask[i] = x > 0.0 ? 1 : 0;
+            } else {
+                double x = w.c[i] + alpha * (w.cs[i] - w.c[i]);
+                if (!w.free_mask[i]) x = 0.0;
+                if (i == change) {
+                    if (to_free) w.free_mask[i] = 1;
+                    else { w.free_mask[i] = 0; x = 0.0; }
+                }
+                w.c[i] = x > 0.0 ? x : 0.0;
+            }
+        }
+        cx.sync();
+        if (done) break;
+        if (iters >= K.qp_max_iter) { status = 1; break; }
+    }
+    w.qp_iters = iters;
+    w.qp_status = status;
+    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12) ; a = -La^-T (wv + Y' lam)
+    LMH_FOR(r, 12) {
+        int foot = r / 6, k = r % 6;
+        double s = 0.0;
+        for (int gi = 0; gi < 16; ++gi) s += K.Gf[16 * k + gi] * w.c[16 * foot + gi];
+        w.f12[r] = s;
+    }
+    cx.sync();
+    {
+        double l[6];
+        for (int r = 0; r < 6; ++r) {
+            double s = w.rhs[r];
+            for (int k = 0; k < 12; ++k) s -= w.JF[NQ * k + r] * w.f12[k];
+            l[r] = s;
+        }
+        for (int r = 0; r < 6; ++r) { double s = l[r]; for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m]; l[r] = s / Ls[7 * r]; }
+        for (int r = 5; r >= 0; --r) { double s = l[r]; for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m]; l[r] = s / Ls[7 * r]; }
+        LMH_FOR(i, NQ) {
+            double s = Y[NQ * 6 + i];
+            for (int r = 0; r < 6; ++r) s += Y[NQ * r + i] * l[r];
+            w.a[i] = -s;
+        }
+        LMH_FOR(r, 6) w.lam[r] = l[r];
+    }
+    cx.sync();
+    for (int k = NQ - 1; k >= 0; --k) {     // La' a = rhs, column oriented
+        double xk = w.a[k] / w.ladiag[k];
+        cx.sync();
+        LMH_FOR(i, k + 1) {
+            if (i == k) w.a[k] = xk;
+            else w.a[i] -= Ha[LDM * k + i] * xk;
+        }
+        cx.sync();
+    }
+}
+
+// ================================================================================================
+// Phase 8: inverse dynamics to torques, base acceleration to the world frame, state derivative
+// (controller.cpp:137-147, apps/offline/main.cpp:107-121).
+template <class Cx>
+LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
+    LMH_FOR(j, NJ) {
+        double s = w.C[6 + j];
+        for (int k = 0; k < 6; ++k) s += w.M6[NQ * k + 6 + j] * w.a[k];
+        int c = joint_chain(j), j0 = chain_joint0(c), n = chain_nact(c);
+        for (int b = 0; b < n; ++b) s += w.Hc[36 * c + 6 * (j - j0) + b] * w.a[6 + j0 + b];
+        for (int k = 0; k < 12; ++k) s -= w.JF[NQ * k + 6 + j] * w.f12[k];
+        w.tau[j] = s;
+    }
+    LMH_FOR(i, NQ) {
+        double x;
+        if (i < 3) {         // linear part of X0^-1 a : R0 a_lin + p0 x (R0 a_ang)
+            double ra[3] = {rot_row(w.R0, 0, w.a), rot_row(w.R0, 1, w.a), rot_row(w.R0, 2, w.a)};
+            x = rot_row(w.R0, i, w.a + 3) + cross_k(w.p0, ra, i);
+        } else if (i < 6) x = rot_row(w.R0, i - 3, w.a);
+        else x = w.a[i];
+        w.qpp[i] = x;
+        w.xdot[NQ + i] = x;
+        double qd;
+        if (i < 3) qd = w.v[i] + cross_k(w.v + 3, w.q, i);       // v + w x p
+        else if (i < 6) {    // Euler rates (generalizedFunctions.cpp:43-50)
+            double s2, c2;
+            lmh_sincos(w.q[5], &s2, &c2);
+            double c1 = cos(w.q[4]), t1 = tan(w.q[4]);
+            const double* om = w.v + 3;
+            qd = i == 3 ? (c2 / c1) * om[0] + (s2 / c1) * om[1]
+               : i == 4 ? -s2 * om[0] + c2 * om[1]
+                        : c2 * t1 * om[0] + s2 * t1 * om[1] + om[2];
+        } else qd = w.v[i];
+        w.xdot[i] = qd;
+    }
+    cx.sync();
+}
+
+// Debug/parity dump of one stage (global memory on the device).
+template <class Cx>
+LMH_HDN void dump_assembly(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
+    LMH_FOR(it, NQ * NQ) {
+        int i = it / NQ, j = it % NQ;
+        d->Ha[it] = i >= j ? w.u.s.Ha[LDM * i + j] : w.u.s.Ha[LDM * j + i];
+    }
+    LMH_FOR(i, NQ) d->ga[i] = w.ga[i];
+    cx.sync();
+}
+template <class Cx>
+LMH_HDN void dump_stage(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
+    LMH_FOR(it, NQ * NQ) {
+        int i = it / NQ, j = it % NQ;
+        d->M[it] = i < 6 ? w.M6[NQ * i + j] : j < 6 ? w.M6[NQ * j + i] : hjoint(w, i - 6, j - 6);
+    }
+    LMH_FOR(i, NQ) { d->C[i] = w.C[i]; d->Cg[i] = w.Cg[i]; d->qppRef[i] = w.qppRef[i]; d->a[i] = w.a[i]; d->qpp[i] = w.qpp[i]; }
+    LMH_FOR(i, 6 * NQ) d->AG[i] = w.AG[i];
+    LMH_FOR(i, 12 * NQ) d->JFeet[i] = w.JF[i];
+    LMH_FOR(i, 2 * NQ) d->xdot[i] = w.xdot[i];
+    LMH_FOR(i, NC) d->c[i] = w.c[i];
+    LMH_FOR(i, NJ) d->tau[i] = w.tau[i];
+    LMH_FOR(i, 12) {
+        d->Jpqp[i] = w.Jpqp[i]; d->footAccRef[i] = w.footAccRef[i]; d->f[i] = w.f12[i];
+        d->T7[i] = i < 9 ? w.Rs[0][i] : w.ps[0][i - 9];
+        d->T14[i] = i < 9 ? w.Rs[1][i] : w.ps[1][i - 9];
+    }
+    LMH_FOR(i, 6) { d->AGpqp[i] = w.AGpqp[i]; d->hGpRef[i] = w.hGpRef[i]; d->lam[i] = w.lam[i]; }
+    LMH_FOR(i, 3) {
+        d->CoM[i] = w.com[i]; d->comVel[i] = w.comVel[i]; d->comAngMom[i] = w.angMom[i];
+        d->xRef[i] = w.xRef[i]; d->yRef[i] = w.yRef[i];
+    }
+    LMH_FOR(i, 1) { d->k_index = w.k_index; d->qp_status = w.qp_status; d->qp_iters = w.qp_iters; d->pad = 0; }
+    cx.sync();
+}
+
+// One dynamics(x,t) evaluation.  On entry w.q, w.v, w.vh, w.t are set; on exit w.xdot, w.tau, w.f12,
+// w.qpp (and every intermediate) are valid and w.vh has been advanced to this stage's velocity.
+template <class Cx>
+LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, LmhStageDump* dump = nullptr) {
+    fk_phase(cx, w, K);
+    base_twist_phase(cx, w);
+    rnea_phase(cx, w, K);
+    crba_phase(cx, w, K);
+    centroidal_jacobian_phase(cx, w, K);
+    mpc_pd_phase(cx, w, K, P, plan_id);
+    assemble_phase(cx, w, K);
+    if (dump) dump_assembly(cx, w, dump);
+    qp_phase(cx, w, K);
+    output_phase(cx, w);
+    if (dump) dump_stage(cx, w, dump);
+    LMH_FOR(i, NQ) w.vh[i] = w.v[i];     // Robot::updateVelocityState (Robot.cpp:271-274)
+    cx.sync();
+}
+
+// a + b*c with the product rounded before the sum, as the reference's (unfused) CPU arithmetic does
+LMH_HD double mul_then_add(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, __dmul_rn(b, c));
+#else
+    volatile double p = b * c;
+    return a + p;
+#endif
+}
+
+// Running statistics of one environment (kept by thread 0 of the group).
+struct StatsAcc {
+    double max_tau, max_err, max_qpp;
+    int32_t qp_iters, qp_fail, steps, alive;
+};
+
+// One RK4 step (rk4.hpp:5-18) + Clock::step (Clock.hpp:11).  x: [60] state in shared memory, kacc:
+// [60] scratch, t: the env clock (same value in every thread of the group).
+template <class Cx>
+LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t, const Consts& K, const Plan& P,
+                      int plan_id, LmhStepLog* log, StatsAcc* st) {
+    const double dt = K.dt;
+    const double half = 0.5 * dt;
+    int iters = 0, fails = 0;
+    for (int stage = 0; stage < 4; ++stage) {
+        const double cstage = stage == 0 ? 0.0 : stage == 3 ? dt : half;
+        LMH_FOR(i, 2 * NQ) {
+            double xi = stage == 0 ? x[i] : mul_then_add(x[i], cstage, w.xdot[i]);
+            if (i < NQ) w.q[i] = xi; else w.v[i - NQ] = xi;
+        }
+        LMH_FOR(i, 1) w.t = stage == 0 ? t : mul_then_add(t, stage == 3 ? 1.0 : 0.5, dt);
+        cx.sync();
+        stage_eval(cx, w, K, P, plan_id);
+        LMH_FOR(i, 2 * NQ) {
+            double k = w.xdot[i];
+            kacc[i] = stage == 0 ? k : stage == 3 ? kacc[i] + k : mul_then_add(kacc[i], 2.0, k);
+        }
+        iters += w.qp_iters;
+        fails += w.qp_status != 0;
+        if (log) {
+            LMH_FOR(i, 1) log->k_index[stage] = w.k_index;
+            if (stage == 0) { LMH_FOR(i, NJ) log->tau_k1[i] = w.tau[i]; }
+        }
+        if (st && stage == 0) {
+            LMH_FOR(i, 1) {
+                double m = st->max_tau, a = st->max_qpp;
+                for (int j = 0; j < NJ; ++j) m = fmax(m, fabs(w.tau[j]));
+                for (int j = 0; j < NQ; ++j) a = fmax(a, fabs(w.qpp[j]));
+                st->max_tau = m; st->max_qpp = a;
+            }
+        }
+        cx.sync();
+    }
+    const double sixth = dt / 6.0;
+    LMH_FOR(i, 2 * NQ) x[i] = mul_then_add(x[i], sixth, kacc[i]);
+    t = t + dt;
+    if (log) {
+        LMH_FOR(i, 3) { log->com_k4[i] = w.com[i]; log->rfoot[i] = w.ps[0][i]; log->lfoot[i] = w.ps[1][i]; }
+        LMH_FOR(i, 1) { log->qp_iters = iters; log->qp_fail = fails; }
+    }
+    if (st) {
+        LMH_FOR(i, 1) {
+            int k0 = w.k_index;
+            if (k0 < 0) k0 = 0;
+            if (k0 >= P.zmp_len) k0 = P.zmp_len - 1;
+            double ex = w.com[0] - P.zmp_x[(size_t)plan_id * P.zmp_len + k0];
+            double ey = w.com[1] - P.zmp_y[(size_t)plan_id * P.zmp_len + k0];
+            st->max_err = fmax(st->max_err, sqrt(ex * ex + ey * ey));
+            st->qp_iters += iters; st->qp_fail += fails; st->steps += 1;
+        }
+    }
+    cx.sync();
+    if (st) {
+        LMH_FOR(i, 1) {
+            bool ok = x[2] > 0.15;
+            for (int j = 0; j < 2 * NQ; ++j) ok = ok && (fabs(x[j]) < 1e6);
+            if (!ok) st->alive = 0;
+        }
+    }
+    cx.sync();
+}
+
+}  // namespace lmh

@@ -1,0 +1,382 @@
+// lmh_setup.hpp -- host-side, run-once setup of a batch: the constants every environment shares
+// (robot tables, gains, the MPC gain vector), the nominal plan (ZMP reference, foot polynomials) and
+// the initial posture by inverse kinematics.  Mirrors what apps/offline/main.cpp:12-64 does before it
+// enters the loop.  Setup only: nothing here runs per step.
+//
+//   Robot::Robot                      src/Robot.cpp:5-43          -> build_robot_tables
+//   Kinematics::compute (Newton IK)   src/invKinematics.cpp:11-70,151-267 -> solve_initial_posture
+//   Mpc3dLip::initialize              src/mpcLinearPendulum.cpp:41-76 -> build_mpc_gain
+//   footCoeffTrajectory/findPolyCoeff src/footRefTrajectory.cpp:4-47, generalizedFunctions.cpp:103-163
+//   ZMP::stanceZMP                    src/zmpGeneration.cpp:39-60
+#pragma once
+#include "lmh_model.cuh"
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+namespace lmh {
+
+struct Scenario {                       // literals of apps/offline/main.cpp:13-56
+    double dt = 0.01, sim_time = 5.0, time_horizon = 0.5;
+    double com[3] = {-0.02, 0.0, 0.26};
+    double rf[6] = {0, -0.05, 0, 0, 0, 0};
+    double lf[6] = {0, 0.05, 0, 0, 0, 0};
+    double mu = 0.7;                    // controller.hpp:81
+    double mpc_alpha = 1e-3, mpc_beta = 1.0;   // mpcLinearPendulum.hpp:47-48
+    int qp_max_iter = 200;
+};
+
+struct NaoLinkRow { double m; double c[3]; double I[9]; };
+static const NaoLinkRow kNaoLinks[28] = {
+#include "lmh_nao_table.inc"
+};
+
+// dense solve A x = b (n x n, row-major), Gaussian elimination with partial pivoting.  Stands in for
+// the reference's colPivHouseholderQr().solve on well-posed square systems.
+inline bool dense_solve(int n, std::vector<double> A, std::vector<double> b, double* x) {
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        for (int i = k + 1; i < n; ++i) if (std::fabs(A[i * n + k]) > std::fabs(A[p * n + k])) p = i;
+        if (A[p * n + k] == 0.0) return false;
+        if (p != k) { for (int j = 0; j < n; ++j) std::swap(A[k * n + j], A[p * n + j]); std::swap(b[k], b[p]); }
+        for (int i = k + 1; i < n; ++i) {
+            double f = A[i * n + k] / A[k * n + k];
+            if (f == 0.0) continue;
+            for (int j = k; j < n; ++j) A[i * n + j] -= f * A[k * n + j];
+            b[i] -= f * b[k];
+        }
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * x[j];
+        x[i] = s / A[i * n + i];
+    }
+    return true;
+}
+
+// boundary-value polynomial, ascending powers (generalizedFunctions.cpp:103-163)
+inline std::vector<double> poly_fit(const std::vector<double>& pt, const std::vector<double>& pv,
+                                    const std::vector<double>& vt, const std::vector<double>& vv,
+                                    const std::vector<double>& at, const std::vector<double>& av) {
+    int n = (int)(pt.size() + vt.size() + at.size());
+    std::vector<double> A((size_t)n * n, 0.0), b(n, 0.0), c(n, 0.0);
+    int row = 0;
+    for (size_t i = 0; i < pt.size(); ++i, ++row) { double tp = 1; for (int j = 0; j < n; ++j) { A[row * n + j] = tp; tp *= pt[i]; } b[row] = pv[i]; }
+    for (size_t i = 0; i < vt.size(); ++i, ++row) { double tp = 1; for (int j = 1; j < n; ++j) { A[row * n + j] = j * tp; tp *= vt[i]; } b[row] = vv[i]; }
+    for (size_t i = 0; i < at.size(); ++i, ++row) { double tp = 1; for (int j = 2; j < n; ++j) { A[row * n + j] = j * (j - 1) * tp; tp *= at[i]; } b[row] = av[i]; }
+    if (!dense_solve(n, A, b, c.data())) throw std::runtime_error("lmh: singular polynomial fit");
+    return c;
+}
+
+// 20 coefficients of one foot: x(6), y(6), z(8) (footRefTrajectory.cpp:4-47)
+inline void foot_coefficients(const double cur[3], const double des[3], double step_height, double T, double* out20) {
+    std::vector<double> t2 = {0, T}, z2 = {0, 0}, t3 = {0, T / 2, T}, z3 = {0, 0, 0};
+    std::vector<double> x = poly_fit(t2, {cur[0], des[0]}, t2, z2, t2, z2);
+    std::vector<double> y = poly_fit(t2, {cur[1], des[1]}, t2, z2, t2, z2);
+    std::vector<double> z = poly_fit(t3, {cur[2], step_height, des[2]}, t3, z3, t2, z2);
+    for (int i = 0; i < 6; ++i) { out20[i] = x[i]; out20[6 + i] = y[i]; }
+    for (int i = 0; i < 8; ++i) out20[12 + i] = z[i];
+}
+
+class HostModel {
+public:
+    Consts K;
+    std::vector<double> zmp_x, zmp_y, foot_coef;   // nominal plan 0
+    double q0[NQ];
+    int ik_iterations = 0;
+    Scenario sc;
+
+    explicit HostModel(const Scenario& s = Scenario()) : sc(s), ws_(new EnvWS) {
+        std::memset(&K, 0, sizeof(K));
+        std::memset(ws_.get(), 0, sizeof(EnvWS));
+        build_robot_tables();
+        build_controller_tables();
+        // stand task: constant ZMP in the middle of the support zone (zmpGeneration.cpp:39-60)
+        int samples = static_cast<int>((sc.sim_time + 0.5) / sc.dt);
+        zmp_x.assign(samples, 0.0);
+        zmp_y.assign(samples, 0.0);
+        foot_coef.assign(40, 0.0);
+        foot_coefficients(sc.rf, sc.rf, 0.0, sc.sim_time, foot_coef.data());
+        foot_coefficients(sc.lf, sc.lf, 0.0, sc.sim_time, foot_coef.data() + 20);
+        solve_initial_posture();
+        build_mpc_gain(ws_->com[2]);     // zCom = CoM height after IK (main.cpp:39)
+    }
+
+    // model phases of one configuration on the host (used by the IK and by tools)
+    EnvWS& evaluate_model(const double* q, const double* v) {
+        EnvWS& w = *ws_;
+        for (int i = 0; i < NQ; ++i) { w.q[i] = q[i]; w.v[i] = v ? v[i] : 0.0; w.vh[i] = w.v[i]; }
+        Ctx<1> cx{0, 0};
+        fk_phase(cx, w, K);
+        base_twist_phase(cx, w);
+        rnea_phase(cx, w, K);
+        crba_phase(cx, w, K);
+        centroidal_jacobian_phase(cx, w, K);
+        return w;
+    }
+    EnvWS& workspace() { return *ws_; }
+
+private:
+    std::unique_ptr<EnvWS> ws_;
+
+    void build_robot_tables() {
+        const double kPi = 3.14159265358979323846;   // Robot.cpp:3
+        const double h = kPi / 2;
+        // modified-DH rows of the 24 joint transforms (Robot.cpp:180-196)
+        const double r[24] = {-0.07071, 0, 0, 0, 0, 0, 0.07071, 0, 0, 0, 0, 0, 0, 0, 0.105, 0, 0.05595, 0, 0, 0.105, 0, 0.05595, 0, 0};
+        const double d[24] = {0, 0, 0, -0.1, -0.1029, 0, 0, 0, 0, -0.1, -0.1029, 0, 0, 0, -0.015, 0, 0, 0, 0, -0.015, 0, 0, 0, 0};
+        const double al[24] = {0, h, h, 0, 0, -h, -h, -h, h, 0, 0, -h, -h, h, h, -h, h, h, h, h, -h, h, 0, -h};
+        for (int i = 0; i < 24; ++i) {
+            K.dh_r[i] = r[i]; K.dh_d[i] = d[i];
+            K.dh_ca[i] = std::cos(al[i]); K.dh_sa[i] = std::sin(al[i]);   // cos(pi/2) residue kept, as upstream
+            K.th_off[i] = 0.0;
+        }
+        K.th_off[1] = (3.0 / 4) * kPi; K.th_off[6] = -(1.0 / 2) * kPi; K.th_off[7] = (1.0 / 4) * kPi;   // Robot.cpp:59-87
+        K.th_off[13] = (1.0 / 2) * kPi; K.th_off[18] = (1.0 / 2) * kPi; K.th_off[23] = -(1.0 / 2) * kPi;
+        const double a = 0.7071;   // sic (Robot.cpp:92-103): the hip pre-rotations are not exactly orthonormal
+        const double pre[NCH][12] = {
+            {0, -1, 0, a, 0, a, -a, 0, a, 0, 0, 0},
+            {1, 0, 0, 0, a, a, 0, -a, a, 0, 0, 0},
+            {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, -0.098, 0.13591},
+            {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0.098, 0.13591},
+            {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.1615}};
+        for (int c = 0; c < NCH; ++c) for (int k = 0; k < 12; ++k) K.pre[12 * c + k] = pre[c][k];
+        K.sole_x = -0.0452;
+        K.gravity = 9.81;
+        const double q0n[NQ] = {-0.0185, 0, 0.282, 0, 0, 0, 0, 0, -0.5, 0.8, -0.3, 0, 0, 0, -0.5,
+                                0.8, -0.3, 0, 1.6, 0, 0, 0, 0, -1.6, 0, 0, 0, 0, 0, 0};   // Robot.cpp:242-262
+        for (int i = 0; i < NQ; ++i) { K.qdes[i] = q0n[i]; q0[i] = q0n[i]; }
+        const double rd[9] = {0, 0, 1, 0, -1, 0, 1, 0, 0};
+        for (int k = 0; k < 9; ++k) K.Rdes[k] = rd[k];
+
+        // inertial data are given in world-aligned frames at q = 0: re-express in the joint frames (Robot.cpp:14-22)
+        EnvWS& w = *ws_;
+        for (int i = 0; i < NQ; ++i) { w.q[i] = 0.0; w.v[i] = 0.0; w.vh[i] = 0.0; }
+        for (int i = 0; i < 28; ++i) { K.mc[4 * i + 3] = kNaoLinks[i].m; }   // masses first: fk_phase sums the CoM
+        K.mass = 1.0;
+        Ctx<1> cx{0, 0};
+        fk_phase(cx, w, K);
+        double mass = 0.0;
+        for (int i = 0; i < 28; ++i) {
+            const NaoLinkRow& L = kNaoLinks[i];
+            double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            if (i < NF) for (int k = 0; k < 9; ++k) R[k] = w.u.m.Tw[12 * i + k];
+            double cj[3], RtI[9], Ij[9];
+            for (int r3 = 0; r3 < 3; ++r3) cj[r3] = R[r3] * L.c[0] + R[3 + r3] * L.c[1] + R[6 + r3] * L.c[2];
+            for (int r3 = 0; r3 < 3; ++r3) for (int c = 0; c < 3; ++c) RtI[3 * r3 + c] = R[r3] * L.I[c] + R[3 + r3] * L.I[3 + c] + R[6 + r3] * L.I[6 + c];
+            for (int r3 = 0; r3 < 3; ++r3) for (int c = 0; c < 3; ++c) Ij[3 * r3 + c] = RtI[3 * r3] * R[c] + RtI[3 * r3 + 1] * R[3 + c] + RtI[3 * r3 + 2] * R[6 + c];
+            mass += L.m;
+            K.mc[4 * i + 0] = cj[0]; K.mc[4 * i + 1] = cj[1]; K.mc[4 * i + 2] = cj[2]; K.mc[4 * i + 3] = L.m;
+            // spatial inertia (Dynamics.cpp:4-13) for the torso and the actuated frames only (Dynamics.cpp:15-27)
+            double* S = K.Isp + 36 * i;
+            for (int k = 0; k < 36; ++k) S[k] = 0.0;
+            bool used = (i == 0) || (i < NF && frame_joint(i) >= 0);
+            if (!used) continue;
+            double cx3[9] = {0, -cj[2], cj[1], cj[2], 0, -cj[0], -cj[1], cj[0], 0};
+            double mcx[9], mcc[9];
+            for (int k = 0; k < 9; ++k) mcx[k] = L.m * cx3[k];
+            for (int r3 = 0; r3 < 3; ++r3) for (int c = 0; c < 3; ++c) mcc[3 * r3 + c] = mcx[3 * r3] * cx3[c] + mcx[3 * r3 + 1] * cx3[3 + c] + mcx[3 * r3 + 2] * cx3[6 + c];
+            for (int r3 = 0; r3 < 3; ++r3)
+                for (int c = 0; c < 3; ++c) {
+                    S[6 * r3 + c] = Ij[3 * r3 + c] - mcc[3 * r3 + c];
+                    S[6 * r3 + 3 + c] = mcx[3 * r3 + c];
+                    S[6 * (3 + r3) + c] = -mcx[3 * r3 + c];
+                    S[6 * (3 + r3) + 3 + c] = r3 == c ? L.m : 0.0;
+                }
+        }
+        K.mass = mass;
+    }
+
+    void build_controller_tables() {
+        K.KpJ = 300; K.KdJ = 34; K.KpM = 10; K.KdM = 6.32; K.KpF = 500; K.KdF = 44;        // controller.hpp:100-111
+        K.wCoML = 4000; K.wCoMK = 0; K.wBasePos = 10; K.wBaseAng = 10; K.wJoints = 1;      // controller.hpp:118-124
+        K.wForce = 1; K.wFoot = 100000; K.epsC = 1e-8;                                      // controller.cpp:109-123
+        K.qp_max_iter = sc.qp_max_iter;
+        K.dt = sc.dt;
+        // friction pyramid edges and contact vertices (controller.cpp:33-36, Robot.cpp:38-42)
+        const double mu = sc.mu;
+        const double B[4][3] = {{mu, 0, 1}, {0, mu, 1}, {-mu, 0, 1}, {0, -mu, 1}};
+        const double V[4][3] = {{0.1, 0.025, 0}, {0.1, -0.025, 0}, {-0.05, 0.025, 0}, {-0.05, -0.025, 0}};
+        for (int v = 0; v < 4; ++v)
+            for (int e = 0; e < 4; ++e) {
+                const double* p = V[v];
+                const double* b = B[e];
+                double mom[3] = {p[1] * b[2] - p[2] * b[1], p[2] * b[0] - p[0] * b[2], p[0] * b[1] - p[1] * b[0]};
+                for (int k = 0; k < 3; ++k) { K.Gf[16 * k + 4 * v + e] = mom[k]; K.Gf[16 * (3 + k) + 4 * v + e] = b[k]; }
+            }
+        for (int i = 0; i < 16; ++i)
+            for (int j = 0; j < 16; ++j) {
+                double s = 0;
+                for (int k = 0; k < 6; ++k) s += K.Gf[16 * k + i] * K.Gf[16 * k + j];
+                K.GtG[16 * i + j] = s;
+            }
+    }
+
+    // u0 = -e0' H^-1 beta Pu' (Px x - z)  with H = alpha I + beta Pu'Pu constant  =>  gain vector r = beta Pu H^-1 e0
+    void build_mpc_gain(double zcom) {
+        const double dt = sc.dt;
+        int N = static_cast<int>(sc.time_horizon / dt);     // mpcLinearPendulum.hpp:49
+        int n = N + 1;
+        if (n > MPC_MAXN) throw std::runtime_error("lmh: MPC horizon too long");
+        const double A[4] = {1, dt, 0, 1}, Bv[2] = {dt * dt / 2, dt};
+        const double D = -zcom / 9.81;
+        std::vector<double> Px((size_t)n * 2), Pu((size_t)n * n, 0.0);
+        double Ap[4] = {1, 0, 0, 1};
+        Px[0] = 1; Px[1] = 0; Pu[0] = D;
+        for (int i = 1; i <= N; ++i) {
+            double T[4] = {Ap[0] * A[0] + Ap[1] * A[2], Ap[0] * A[1] + Ap[1] * A[3], Ap[2] * A[0] + Ap[3] * A[2], Ap[2] * A[1] + Ap[3] * A[3]};
+            std::memcpy(Ap, T, sizeof(T));
+            Px[2 * i] = Ap[0]; Px[2 * i + 1] = Ap[1];
+            Pu[(size_t)i * n + i] = D;
+        }
+        // Pu[i+j][i-1] = C A^j B
+        double Aj[4] = {1, 0, 0, 1};
+        for (int j = 0; j <= N - 1; ++j) {
+            double cab = Aj[0] * Bv[0] + Aj[1] * Bv[1];
+            for (int i = 1; i + j <= N; ++i) Pu[(size_t)(i + j) * n + (i - 1)] = cab;
+            double T[4] = {Aj[0] * A[0] + Aj[1] * A[2], Aj[0] * A[1] + Aj[1] * A[3], Aj[2] * A[0] + Aj[3] * A[2], Aj[2] * A[1] + Aj[3] * A[3]};
+            std::memcpy(Aj, T, sizeof(T));
+        }
+        std::vector<double> H((size_t)n * n), e0(n, 0.0), h(n);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double s = 0;
+                for (int k = 0; k < n; ++k) s += Pu[(size_t)k * n + i] * Pu[(size_t)k * n + j];
+                H[(size_t)i * n + j] = sc.mpc_beta * s + (i == j ? sc.mpc_alpha : 0.0);
+            }
+        e0[0] = 1.0;
+        if (!dense_solve(n, H, e0, h.data())) throw std::runtime_error("lmh: singular MPC Hessian");
+        K.mpc_rPx[0] = K.mpc_rPx[1] = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double s = 0;
+            for (int k = 0; k < n; ++k) s += Pu[(size_t)i * n + k] * h[k];
+            K.mpc_r[i] = sc.mpc_beta * s;
+            K.mpc_rPx[0] += K.mpc_r[i] * Px[2 * i];
+            K.mpc_rPx[1] += K.mpc_r[i] * Px[2 * i + 1];
+        }
+        K.mpc_n1 = n; K.mpc_dt = dt; K.mpc_zcom = zcom;
+        for (int k = 0; k < 4; ++k) K.mpc_A[k] = A[k];
+        K.mpc_B[0] = Bv[0]; K.mpc_B[1] = Bv[1];
+    }
+
+    static void euler_from(const double* R, const double* ref, double* eta) {   // invKinematics.cpp:257-267
+        double N[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) N[3 * r + c] = R[3 * r] * ref[c] + R[3 * r + 1] * ref[3 + c] + R[3 * r + 2] * ref[6 + c];
+        eta[2] = std::atan2(N[3], N[0]);
+        eta[1] = std::atan2(-N[6], std::cos(eta[2]) * N[0] + std::sin(eta[2]) * N[3]);
+        eta[0] = std::atan2(std::sin(eta[2]) * N[2] - std::cos(eta[2]) * N[5], -std::sin(eta[2]) * N[1] + std::cos(eta[2]) * N[4]);
+    }
+    static void omega_map(const double* eta, double* O) {   // generalizedFunctions.cpp:43-50
+        double c2 = std::cos(eta[2]), s2 = std::sin(eta[2]), c1 = std::cos(eta[1]), t1 = std::tan(eta[1]);
+        O[0] = c2 / c1; O[1] = s2 / c1; O[2] = 0; O[3] = -s2; O[4] = c2; O[5] = 0; O[6] = c2 * t1; O[7] = s2 * t1; O[8] = 1;
+    }
+    static void inv3(const double* m, double* o) {
+        double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[2] * m[7] - m[1] * m[8], c02 = m[1] * m[5] - m[2] * m[4];
+        double c10 = m[5] * m[6] - m[3] * m[8], c11 = m[0] * m[8] - m[2] * m[6], c12 = m[2] * m[3] - m[0] * m[5];
+        double c20 = m[3] * m[7] - m[4] * m[6], c21 = m[1] * m[6] - m[0] * m[7], c22 = m[0] * m[4] - m[1] * m[3];
+        double det = m[0] * c00 + m[1] * c10 + m[2] * c20;
+        double c[9] = {c00, c01, c02, c10, c11, c12, c20, c21, c22};
+        for (int k = 0; k < 9; ++k) o[k] = c[k] / det;
+    }
+    void operational_state(const EnvWS& w, double* Q) const {   // invKinematics.cpp:54-70
+        for (int s = 0; s < 2; ++s) {
+            for (int k = 0; k < 3; ++k) Q[6 * s + k] = w.ps[s][k];
+            euler_from(w.Rs[s], K.Rdes, Q + 6 * s + 3);
+        }
+        for (int k = 0; k < 12; ++k) Q[12 + k] = w.q[18 + k];
+        for (int k = 0; k < 3; ++k) Q[24 + k] = w.q[3 + k];
+        for (int k = 0; k < 3; ++k) Q[27 + k] = w.com[k];
+    }
+    // Newton iteration on [feet poses, arm+head joints, base attitude, CoM] (invKinematics.cpp:27-52,151-245)
+    void solve_initial_posture() {
+        double des[NQ], cur[NQ], q[NQ];
+        for (int i = 0; i < NQ; ++i) q[i] = q0[i];
+        for (int k = 0; k < 6; ++k) { des[k] = sc.rf[k]; des[6 + k] = sc.lf[k]; }
+        for (int k = 0; k < 12; ++k) des[12 + k] = q[18 + k];
+        for (int k = 0; k < 3; ++k) des[24 + k] = 0.0;       // desiredOperationalState leaves the attitude slots at zero
+        for (int k = 0; k < 3; ++k) des[27 + k] = sc.com[k];
+        ik_iterations = 0;
+        for (;;) {
+            EnvWS& w = evaluate_model(q, nullptr);
+            operational_state(w, cur);
+            std::vector<double> e(NQ);
+            double emax = 0;
+            for (int i = 0; i < NQ; ++i) { e[i] = des[i] - cur[i]; emax = std::fmax(emax, std::fabs(e[i])); }
+            if (!(emax > 1e-10) || ik_iterations >= 200) break;
+            std::vector<double> J((size_t)NQ * NQ, 0.0);
+            double Om[9], Omi[9];
+            omega_map(w.q + 3, Om);
+            inv3(Om, Omi);
+            // feet rows: [ang;lin]->[lin;ang], base cols [ang|lin]->[lin|ang], attitude cols through Omega^-1
+            for (int s = 0; s < 2; ++s) {
+                double etaF[3], OmF[9];
+                euler_from(w.Rs[s], K.Rdes, etaF);
+                omega_map(etaF, OmF);
+                for (int half = 0; half < 2; ++half)          // half 0: linear rows (from JF rows 3..5), half 1: angular rows
+                    for (int r = 0; r < 3; ++r) {
+                        double row[NQ];
+                        for (int c = 0; c < NQ; ++c) {
+                            int src_c = c < 3 ? c + 3 : c < 6 ? c - 3 : c;
+                            row[c] = w.JF[NQ * (6 * s + (half == 0 ? 3 + r : r)) + src_c];
+                        }
+                        double att[3] = {row[3], row[4], row[5]};
+                        for (int c = 0; c < 3; ++c) row[3 + c] = att[0] * Omi[c] + att[1] * Omi[3 + c] + att[2] * Omi[6 + c];
+                        for (int c = 0; c < NQ; ++c) J[(size_t)(6 * s + 3 * half + r) * NQ + c] = row[c];
+                    }
+                // angular rows of this foot premultiplied by the foot's own Omega, attitude columns only (invKinematics.cpp:151-206)
+                double blk[9];
+                for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) blk[3 * r + c] = J[(size_t)(6 * s + 3 + r) * NQ + 3 + c];
+                for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+                    J[(size_t)(6 * s + 3 + r) * NQ + 3 + c] = OmF[3 * r] * blk[c] + OmF[3 * r + 1] * blk[3 + c] + OmF[3 * r + 2] * blk[6 + c];
+            }
+            for (int k = 0; k < 12; ++k) J[(size_t)(12 + k) * NQ + 18 + k] = 1.0;
+            for (int k = 0; k < 3; ++k) J[(size_t)(24 + k) * NQ + 3 + k] = 1.0;
+            // CoM Jacobian (invKinematics.cpp:208-245)
+            {
+                const double* Tw = w.u.m.Tw;
+                double Jc[3 * NQ];
+                for (int k = 0; k < 3 * NQ; ++k) Jc[k] = 0.0;
+                for (int i = 0; i < NF; ++i) {
+                    double m = K.mc[4 * i + 3];
+                    if (m == 0) continue;
+                    const double* Ti = Tw + 12 * i;
+                    double pc[3];
+                    for (int k = 0; k < 3; ++k) pc[k] = Ti[3 * k] * K.mc[4 * i] + Ti[3 * k + 1] * K.mc[4 * i + 1] + Ti[3 * k + 2] * K.mc[4 * i + 2] + Ti[9 + k];
+                    double JX[3 * NQ];
+                    for (int k = 0; k < 3 * NQ; ++k) JX[k] = 0.0;
+                    for (int k = 0; k < 3; ++k) JX[NQ * k + k] = 1.0;
+                    double dp[3] = {Tw[9] - pc[0], Tw[10] - pc[1], Tw[11] - pc[2]};
+                    double cm[9] = {0, -dp[2], dp[1], dp[2], 0, -dp[0], -dp[1], dp[0], 0};
+                    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) JX[NQ * r + 3 + c] = cm[3 * r + c];
+                    for (int j = i; j != 0; j = frame_parent(j)) {
+                        int a = frame_joint(j);
+                        if (a < 0) continue;
+                        const double* Tj = Tw + 12 * j;
+                        double z[3] = {Tj[2], Tj[5], Tj[8]};
+                        double d[3] = {pc[0] - Tj[9], pc[1] - Tj[10], pc[2] - Tj[11]};
+                        JX[NQ * 0 + 6 + a] = z[1] * d[2] - z[2] * d[1];
+                        JX[NQ * 1 + 6 + a] = z[2] * d[0] - z[0] * d[2];
+                        JX[NQ * 2 + 6 + a] = z[0] * d[1] - z[1] * d[0];
+                    }
+                    for (int k = 0; k < 3 * NQ; ++k) Jc[k] += m * JX[k];
+                }
+                for (int k = 0; k < 3 * NQ; ++k) Jc[k] /= K.mass;
+                for (int r = 0; r < 3; ++r) {
+                    double att[3] = {Jc[NQ * r + 3], Jc[NQ * r + 4], Jc[NQ * r + 5]};
+                    for (int c = 0; c < 3; ++c) Jc[NQ * r + 3 + c] = att[0] * Omi[c] + att[1] * Omi[3 + c] + att[2] * Omi[6 + c];
+                    for (int c = 0; c < NQ; ++c) J[(size_t)(27 + r) * NQ + c] = Jc[NQ * r + c];
+                }
+            }
+            double dq[NQ];
+            if (!dense_solve(NQ, J, e, dq)) throw std::runtime_error("lmh: singular IK Jacobian");
+            for (int i = 0; i < NQ; ++i) q[i] += dq[i];
+            ++ik_iterations;
+        }
+        for (int i = 0; i < NQ; ++i) q0[i] = q[i];
+        evaluate_model(q0, nullptr);
+    }
+};
+
+}  // namespace lmh

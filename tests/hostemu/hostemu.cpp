@@ -1,0 +1,66 @@
+// TEST TOOL -- host build (NT = 1, sequential loops) of the device source lmh_model.cuh, so that the
+// kernel logic can be unit-tested against the oracle on machines without a GPU.  Not linked into, loaded
+// by, or reachable from the product library.
+#include "lmh_setup.hpp"
+#include <cstring>
+
+using namespace lmh;
+
+struct Emu {
+    HostModel hm;
+    Plan plan;
+    explicit Emu(const Scenario& s) : hm(s) {
+        plan.zmp_x = hm.zmp_x.data();
+        plan.zmp_y = hm.zmp_y.data();
+        plan.foot_coef = hm.foot_coef.data();
+        plan.zmp_len = (int32_t)hm.zmp_x.size();
+    }
+};
+
+extern "C" {
+void* emu_create(double dt, double sim_time, double horizon, const double* com3) {
+    Scenario s;
+    s.dt = dt; s.sim_time = sim_time; s.time_horizon = horizon;
+    if (com3) for (int k = 0; k < 3; ++k) s.com[k] = com3[k];
+    return new Emu(s);
+}
+void emu_destroy(void* p) { delete static_cast<Emu*>(p); }
+void emu_nominal(void* p, double* q0, double* zcom, double* mass, int32_t* ik_iters) {
+    Emu* e = static_cast<Emu*>(p);
+    for (int i = 0; i < NQ; ++i) q0[i] = e->hm.q0[i];
+    *zcom = e->hm.K.mpc_zcom; *mass = e->hm.K.mass; *ik_iters = e->hm.ik_iterations;
+}
+void emu_tables(void* p, double* mass28, double* com28x3, double* isp28x36, double* mpc_r, int32_t* n1, double* rPx, double* foot40) {
+    Emu* e = static_cast<Emu*>(p);
+    for (int i = 0; i < 28; ++i) { mass28[i] = e->hm.K.mc[4 * i + 3]; for (int k = 0; k < 3; ++k) com28x3[3 * i + k] = e->hm.K.mc[4 * i + k]; }
+    std::memcpy(isp28x36, e->hm.K.Isp, sizeof(double) * 28 * 36);
+    *n1 = e->hm.K.mpc_n1;
+    for (int i = 0; i < e->hm.K.mpc_n1; ++i) mpc_r[i] = e->hm.K.mpc_r[i];
+    rPx[0] = e->hm.K.mpc_rPx[0]; rPx[1] = e->hm.K.mpc_rPx[1];
+    std::memcpy(foot40, e->hm.foot_coef.data(), sizeof(double) * 40);
+}
+// one dynamics(x,t) evaluation; vheld is read and advanced
+void emu_stage(void* p, const double* x60, double* vheld30, double t, LmhStageDump* dump) {
+    Emu* e = static_cast<Emu*>(p);
+    EnvWS& w = e->hm.workspace();
+    for (int i = 0; i < NQ; ++i) { w.q[i] = x60[i]; w.v[i] = x60[NQ + i]; w.vh[i] = vheld30[i]; }
+    w.t = t;
+    Ctx<1> cx{0, 0};
+    stage_eval(cx, w, e->hm.K, e->plan, 0, dump);
+    for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
+}
+void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps, LmhStepLog* logs, LmhStats* stats) {
+    Emu* e = static_cast<Emu*>(p);
+    EnvWS& w = e->hm.workspace();
+    for (int i = 0; i < NQ; ++i) w.vh[i] = vheld30[i];
+    double kacc[60];
+    StatsAcc st{0, 0, 0, 0, 0, 0, 1};
+    Ctx<1> cx{0, 0};
+    for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, logs ? logs + s : nullptr, &st);
+    for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
+    if (stats) {
+        stats->max_abs_tau = st.max_tau; stats->max_com_err = st.max_err; stats->max_abs_qpp = st.max_qpp;
+        stats->qp_iters = st.qp_iters; stats->qp_fail = st.qp_fail; stats->steps = st.steps; stats->alive = st.alive;
+    }
+}
+}
