@@ -132,6 +132,13 @@ int32_t lmh_get_com(LmhBatch* h, double* com);
  * x [n_env][60], v_held [n_env][30], t [n_env], and the stream (cudaStream_t) the handle launches on. */
 int32_t lmh_state_dev(LmhBatch* h, double** x_dev, double** v_held_dev, double** t_dev, void** stream);
 int32_t lmh_stats_dev(LmhBatch* h, LmhStats** stats_dev);
+/* Device-to-device restore of the state from caller-owned device buffers (NULL = leave), on the handle's stream. */
+int32_t lmh_set_state_dev(LmhBatch* h, const double* x_dev, const double* v_held_dev, const double* t_dev);
+/* Zero the statistics and the step counter (pushes fire relative to it) without touching the state. */
+int32_t lmh_reset_stats(LmhBatch* h);
+/* CUDA-event stopwatch on the handle's stream (torch.cuda.Event only sees torch's current stream). */
+int32_t lmh_timer_start(LmhBatch* h);
+int32_t lmh_timer_stop(LmhBatch* h, double* elapsed_ms);
 
 /* Launch geometry actually used. */
 int32_t lmh_launch_info(const LmhBatch* h, int32_t* threads_per_env, int32_t* envs_per_block, int32_t* smem_bytes,

@@ -42,7 +42,8 @@ SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", 
            "lmh_get_mpc_gain", "lmh_get_link_tables", "lmh_set_plans", "lmh_get_plan", "lmh_set_state",
            "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
            "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
-           "lmh_stats_dev", "lmh_launch_info", "lmh_measure_fp64_peak"]
+           "lmh_stats_dev", "lmh_set_state_dev", "lmh_reset_stats", "lmh_timer_start", "lmh_timer_stop",
+           "lmh_launch_info", "lmh_measure_fp64_peak"]
 
 
 def build_library(force=False, verbose=False):
@@ -97,6 +98,10 @@ def load_library():
     L.lmh_get_com.argtypes = [vp, vp]
     L.lmh_state_dev.argtypes = [vp, vp, vp, vp, vp]
     L.lmh_stats_dev.argtypes = [vp, vp]
+    L.lmh_set_state_dev.argtypes = [vp, vp, vp, vp]
+    L.lmh_reset_stats.argtypes = [vp]
+    L.lmh_timer_start.argtypes = [vp]
+    L.lmh_timer_stop.argtypes = [vp, vp]
     L.lmh_launch_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.lmh_measure_fp64_peak.argtypes = [_i32, vp, vp, vp]
     _lib = L
@@ -256,9 +261,26 @@ class Batch:
         _chk(self.L, self.L.lmh_state_dev(self.h, C.byref(x), C.byref(vh), C.byref(t), C.byref(s)))
         return x.value, vh.value, t.value, s.value
 
+    def set_state_dev(self, x_ptr=None, vh_ptr=None, t_ptr=None):
+        """device-to-device restore from caller-owned device buffers (e.g. torch tensors' data_ptr())"""
+        _chk(self.L, self.L.lmh_set_state_dev(self.h, C.c_void_p(x_ptr) if x_ptr else None,
+                                              C.c_void_p(vh_ptr) if vh_ptr else None, C.c_void_p(t_ptr) if t_ptr else None))
+
+    def reset_stats(self):
+        _chk(self.L, self.L.lmh_reset_stats(self.h))
+
+    def timer_start(self):
+        _chk(self.L, self.L.lmh_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = np.zeros(1)
+        _chk(self.L, self.L.lmh_timer_stop(self.h, _p(ms)))
+        return float(ms[0])
+
     # raw-pointer variants for pinned host buffers (used by the end-to-end bench leg)
-    def set_state_ptr(self, x_ptr):
-        _chk(self.L, self.L.lmh_set_state(self.h, C.c_void_p(x_ptr), None, None))
+    def set_state_ptr(self, x_ptr, vh_ptr=None, t_ptr=None):
+        _chk(self.L, self.L.lmh_set_state(self.h, C.c_void_p(x_ptr), C.c_void_p(vh_ptr) if vh_ptr else None,
+                                          C.c_void_p(t_ptr) if t_ptr else None))
 
     def get_state_ptr(self, x_ptr):
         _chk(self.L, self.L.lmh_get_state(self.h, C.c_void_p(x_ptr), None, None))

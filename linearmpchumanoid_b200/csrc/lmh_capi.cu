@@ -130,6 +130,8 @@ struct LmhBatch {
     double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr;
     int32_t *d_plan_id = nullptr, *d_push_step = nullptr;
     LmhStats* d_stats = nullptr;
+    LmhStats* d_stats0 = nullptr;
+    std::vector<LmhStats> h_stats0;
     LmhStepLog* d_log = nullptr;
     LmhStageDump* d_dump = nullptr;
     int32_t n_plans = 1, zmp_len = 0, step_counter = 0, launches = 0;
@@ -256,7 +258,7 @@ void lmh_destroy(LmhBatch* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
-    cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_dump); cudaFree(h->d_log);
+    cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
     cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -468,6 +470,49 @@ int32_t lmh_state_dev(LmhBatch* h, double** x, double** vh, double** t, void** s
 int32_t lmh_stats_dev(LmhBatch* h, LmhStats** s) {
     if (!h || !s) return fail(LMH_EINVAL, "bad arguments");
     *s = h->d_stats;
+    return LMH_OK;
+}
+
+int32_t lmh_set_state_dev(LmhBatch* h, const double* x, const double* vh, const double* t) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    size_t E = (size_t)h->n_env;
+    if (x) CU(cudaMemcpyAsync(h->d_x, x, E * 60 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (vh) CU(cudaMemcpyAsync(h->d_vh, vh, E * 30 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (t) CU(cudaMemcpyAsync(h->d_t, t, E * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_reset_stats(LmhBatch* h) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if (h->h_stats0.size() != (size_t)h->n_env) {
+        h->h_stats0.resize(h->n_env);
+        std::memset(h->h_stats0.data(), 0, h->n_env * sizeof(LmhStats));
+        for (auto& s : h->h_stats0) s.alive = 1;
+        CU(cudaMalloc(&h->d_stats0, h->n_env * sizeof(LmhStats)));
+        CU(cudaMemcpy(h->d_stats0, h->h_stats0.data(), h->n_env * sizeof(LmhStats), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpyAsync(h->d_stats, h->d_stats0, (size_t)h->n_env * sizeof(LmhStats), cudaMemcpyDeviceToDevice, h->stream));
+    h->step_counter = 0;
+    return LMH_OK;
+}
+
+int32_t lmh_timer_start(LmhBatch* h) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_timer_stop(LmhBatch* h, double* ms) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    if (ms) *ms = f;
     return LMH_OK;
 }
 

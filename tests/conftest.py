@@ -1,0 +1,53 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """CPU restatement of the reference (oracle/liblmh_oracle.so): the CHECKER, never the thing under test."""
+    import orc_py
+    orc_py.build()
+    return orc_py.oracle()
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    """The reference's own sources built against shim headers (oracle/_ref), if present or buildable."""
+    import orc_py
+    return orc_py.reference()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="session")
+def qp_exact():
+    return np.load(os.path.join(ROOT, "tests", "golden", "qp_exact.npz"))
+
+
+@pytest.fixture(scope="session")
+def hostemu():
+    """Host build (NT = 1) of the device source lmh_model.cuh: a TEST TOOL for the kernel logic."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostemu")], check=True, capture_output=True)
+    import hostemu_py
+    return hostemu_py
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))

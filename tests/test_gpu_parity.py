@@ -1,0 +1,215 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (liblmh_b200.so), against the oracle on the
+same seeded inputs, against the committed reference vectors, against 60-digit QP solutions, and -- at the full
+BASELINE sizes -- through size-independent properties.  Tolerances are the north star's: single-step torques,
+joint accelerations and contact forces 1e-6 relative; 1 s closed-loop CoM and foot trajectories 1e-4 m; integer
+work (ZMP window index, step counters, push steps) bit-exact.  What we actually assert is much tighter."""
+import numpy as np
+import pytest
+
+import linearmpchumanoid_b200 as lmh
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+MODEL = ["M", "C", "Cg", "AG", "AGpqp", "Jpqp", "JFeet", "CoM", "comVel", "comAngMom", "xRef", "yRef", "qppRef",
+         "hGpRef", "footAccRef"]
+
+
+def _t34(T):
+    return np.concatenate([T[:3, :3].ravel(), T[:3, 3]])
+
+
+@pytest.fixture(scope="module", params=[32, 64, 128])
+def nt(request):
+    return request.param
+
+
+def test_native_library_is_the_thing_running():
+    info = lmh.Batch(2).launch_info()
+    assert info["threads_per_env"] in (32, 64, 128) and info["smem_bytes"] > 30000
+
+
+def test_setup_matches_reference_vectors(golden):
+    b = lmh.Batch(3)
+    q0, zcom, mass, it = b.nominal()
+    assert np.abs(q0 - golden["x0"][:30]).max() < 1e-13 and it == 4
+    assert abs(zcom - float(golden["zcom"])) < 1e-14 and abs(mass - float(golden["mass"])) < 1e-14
+    zx, zy, fc = b.plan(0)
+    assert len(zx) == int(golden["zmp_len"]) and (zx == 0).all() and (zy == 0).all()
+    assert np.abs(fc.ravel() - golden["foot_coef"]).max() < 1e-12
+    x, vh, t = b.get_state()
+    assert np.abs(x - np.concatenate([q0, np.zeros(30)])).max() == 0 and (vh == 0).all() and (t == 0).all()
+
+
+def test_stage_against_reference_vectors(golden, nt):
+    n = len(golden["stage_t"])
+    b = lmh.Batch(n, threads_per_env=nt)
+    b.set_state(golden["stage_x"], golden["stage_vh"], golden["stage_t"])
+    d = b.stage()
+    for i in range(n):
+        for k in MODEL:
+            assert relerr(d[k][i], golden["stage_" + k][i]) < 1e-12, (i, k)
+        assert relerr(d["T7"][i], _t34(golden["stage_T7"][i])) < 1e-13
+        assert relerr(d["Ha"][i], golden["stage_Ha"][i]) < 1e-12 and relerr(d["ga"][i], golden["stage_g"][i][:30]) < 1e-11
+        for k in ("qpp", "tau", "f", "xdot"):
+            assert relerr(d[k][i], golden["stage_" + k][i]) < 1e-8, (i, k)     # north star: 1e-6
+        assert d["k_index"][i] == golden["stage_k_index"][i]                  # bit exact
+    _, vh, _ = b.get_state()
+    assert np.array_equal(vh, golden["stage_x"][:, 30:])                      # held velocity advanced like Robot::v_
+
+
+def test_stage_against_oracle_random_states(oracle, nt):
+    E = 96
+    s = oracle.sim()
+    x0, _, _ = s.get_state()
+    rng = np.random.default_rng(1234)
+    X, VH, T = np.tile(x0, (E, 1)), np.zeros((E, 30)), np.zeros(E)
+    for e in range(E):
+        sc = [0.0005, 0.002, 0.01, 0.04][e % 4]
+        X[e, :30] += sc * rng.standard_normal(30); X[e, 30:] = 3 * sc * rng.standard_normal(30)
+        VH[e] = X[e, 30:] + 0.2 * sc * rng.standard_normal(30); T[e] = 0.01 * (e % 40) + 0.005 * (e % 2)
+    b = lmh.Batch(E, threads_per_env=nt)
+    b.set_state(X, VH, T)
+    d = b.stage()
+    assert (d["qp_status"] == 0).all()
+    for e in range(E):
+        s.set_state(X[e], T[e], VH[e])
+        do = s.stage(X[e], T[e])
+        for k in MODEL:
+            assert relerr(d[k][e], do[k]) < 1e-12, (e, k)
+        for k in ("qpp", "tau", "f"):
+            assert relerr(d[k][e], do[k]) < 1e-7, (e, k)
+        assert d["k_index"][e] == do["k_index"]
+    assert d["qp_iters"].max() > 1                                            # the active-set path was exercised
+
+
+def test_qp_against_exact_solutions(qp_exact):
+    X = qp_exact["state"]
+    b = lmh.Batch(len(X))
+    b.set_state(X, X[:, 30:], np.zeros(len(X)))
+    d = b.stage()
+    assert (d["qp_status"] == 0).all() and (d["c"] >= 0).all()
+    for i in range(len(X)):
+        xe = qp_exact["x"][i]
+        assert relerr(d["a"][i], xe[:30]) < 1e-8 and relerr(d["f"][i], xe[30:42]) < 1e-8, (i, int(qp_exact["n_active"][i]))
+    assert int(qp_exact["n_active"].max()) >= 28                              # instances with nearly every bound active
+
+
+def test_closed_loop_1s_against_reference_vectors(golden, nt):
+    b = lmh.Batch(4, threads_per_env=nt, log_steps=100)
+    b.step(100)
+    lg = b.log(0, 100)
+    x, vh, t = b.get_state()
+    for e in range(4):
+        assert np.abs(lg["com_k4"][:, e] - golden["loop_com_k4"]).max() < 1e-10      # north star: 1e-4 m
+        assert np.abs(lg["rfoot"][:, e] - golden["loop_rfoot"]).max() < 1e-10
+        assert np.abs(lg["lfoot"][:, e] - golden["loop_lfoot"]).max() < 1e-10
+        assert relerr(lg["tau_k1"][:, e], golden["loop_tau_k1"]) < 1e-8
+        assert np.array_equal(lg["k_index"][:, e], golden["loop_k_index"])           # bit exact
+        assert np.abs(x[e] - golden["loop_x"][-1]).max() < 1e-9
+    assert t[0] == 100 * 0.01 or abs(t[0] - 1.0) < 1e-12
+    tt = 0.0
+    for _ in range(100):
+        tt += 0.01
+    assert t[0] == tt                                                                  # the clock accumulates like Clock::step
+
+
+def test_stand_5s_stream(golden):
+    """config 1: the reference run, 500 steps; CoM x as printed by main.cpp:86"""
+    b = lmh.Batch(1, log_steps=500)
+    b.step(500)
+    cx = b.log(0, 500)["com_k4"][:, 0, 0]
+    assert np.abs(cx - golden["stand_comx"]).max() < 5e-8                              # stream has 6 printed digits
+    st = b.stats()[0]
+    assert st["steps"] == 500 and st["qp_fail"] == 0 and st["alive"] == 1
+
+
+def test_pushed_rollout_against_oracle(oracle):
+    """config 2 in small: per-env pushes, 60 steps, every env against the CPU oracle"""
+    E, S = 48, 60
+    step, dv = lmh.push_plan(range(E), max_step=20)
+    b = lmh.Batch(E)
+    b.set_pushes(step, dv)
+    b.step(25)
+    b.step(S - 25)                                                                     # split launches: same result
+    x, vh, t = b.get_state()
+    xc, comc, stc, fails = oracle.batch_rollout(oracle.default_config(), E, S, push_step=step, push_dv=dv, n_threads=8)
+    assert fails == 0
+    assert np.abs(x - xc).max() < 1e-7
+    assert np.abs(b.com() - comc).max() < 1e-9
+    st = b.stats()
+    assert relerr(st["max_abs_tau"], stc[:, 0]) < 1e-7
+    assert (st["steps"] == S).all() and (st["alive"] == 1).all() and (st["qp_fail"] == 0).all()
+
+
+def test_full_size_properties():
+    """BASELINE size (4096 envs): properties that need no oracle"""
+    E, S = 4096, 30
+    step, dv = lmh.push_plan(range(E), max_step=10)
+    b = lmh.Batch(E)
+    b.set_pushes(step, dv)
+    b.step(S)
+    x, vh, t = b.get_state()
+    st = b.stats()
+    assert np.isfinite(x).all() and (st["alive"] == 1).all() and (st["qp_fail"] == 0).all() and (st["steps"] == S).all()
+    # sharding invariance: any contiguous shard, run on its own, reproduces its slice bit for bit
+    for lo, hi in ((0, 64), (1000, 1100), (4032, 4096)):
+        b2 = lmh.Batch(hi - lo)
+        b2.set_pushes(step[lo:hi], dv[lo:hi])
+        b2.step(S)
+        x2, _, _ = b2.get_state()
+        assert np.array_equal(x2, x[lo:hi])
+    # determinism: a second run of the same batch is bit-identical
+    b.reset(); b.set_pushes(step, dv); b.step(S)
+    assert np.array_equal(b.get_state()[0], x)
+    # unpushed-yet environments are still identical copies of each other
+    late = np.where(step >= S)[0]
+    if len(late) > 1:
+        assert np.array_equal(x[late[0]], x[late[1]])
+    # mirror symmetry of the scenario: pushes (vx, vy) and (vx, -vy) at the same step give mirrored CoM motion
+    b3 = lmh.Batch(2)
+    b3.set_pushes(np.array([2, 2], np.int32), np.array([[0.1, 0.08, 0, 0, 0, 0], [0.1, -0.08, 0, 0, 0, 0]]))
+    b3.step(40)
+    c = b3.com()
+    assert abs(c[0, 0] - c[1, 0]) < 1e-6 and abs(c[0, 1] + c[1, 1]) < 1e-6
+
+
+def test_thread_geometries_agree():
+    xs = []
+    for nt in (32, 64, 128):
+        b = lmh.Batch(16, threads_per_env=nt)
+        step, dv = lmh.push_plan(range(16), max_step=5)
+        b.set_pushes(step, dv)
+        b.step(20)
+        xs.append(b.get_state()[0])
+    assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[0], xs[2])
+
+
+def test_plans_and_edge_cases():
+    b = lmh.Batch(5)
+    zx, zy, fc = b.plan(0)
+    # two plans: the nominal one and a shifted ZMP reference; envs pick by id
+    b.set_plans(np.stack([zx, zx + 0.01]), np.stack([zy, zy]), np.stack([fc, fc]), plan_ids=[0, 1, 0, 1, 1])
+    d = b.stage()
+    assert np.abs(d["xRef"][0] - d["xRef"][2]).max() == 0 and abs(d["xRef"][1][2] - d["xRef"][0][2]) > 1e-3
+    with pytest.raises(lmh.LmhError):
+        b.set_plans(zx[:10], zy[:10], fc)                                              # shorter than the MPC window
+    with pytest.raises(lmh.LmhError):
+        b.set_plans(np.stack([zx, zx]), np.stack([zy, zy]), np.stack([fc, fc]), plan_ids=[0, 1, 2, 0, 0])
+    with pytest.raises(lmh.LmhError):
+        lmh.Batch(0)
+    with pytest.raises(lmh.LmhError):
+        lmh.Batch(4, threads_per_env=48)
+    b.step(0)                                                                          # empty rollout is a no-op
+    assert (b.get_state()[2] == 0).all()
+    # the ZMP window is clamped at the end of the reference array instead of reading past it
+    b.set_state(t=np.full(5, 5.4))
+    d = b.stage()
+    assert (d["k_index"] == int(5.4 / 0.01)).all() and np.isfinite(d["xRef"]).all()
+    # a hopeless state does not take the batch down: status is per env
+    x, vh, t = b.get_state()
+    x[3, :30] += 0.8
+    b.set_state(x, vh, np.zeros(5))
+    b.step(3)
+    st = b.stats()
+    assert np.isfinite(b.get_state()[0][[0, 1, 2, 4]]).all() and (st["steps"] == 3).all()

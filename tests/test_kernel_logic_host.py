@@ -1,0 +1,90 @@
+"""The device source (lmh_model.cuh + lmh_setup.hpp) compiled for the host with NT = 1 (tests/hostemu, a test
+tool) against the oracle and the reference vectors: kernel LOGIC parity without a GPU.  The GPU parity tests
+proper are in test_gpu_parity.py."""
+import numpy as np
+
+from conftest import relerr
+
+MODEL = ["M", "C", "Cg", "AG", "AGpqp", "Jpqp", "JFeet", "CoM", "comVel", "comAngMom", "xRef", "yRef", "qppRef",
+         "hGpRef", "footAccRef", "T7", "T14"]
+
+
+def _t34(T):          # oracle 4x4 -> (R row-major 9, p 3)
+    return np.concatenate([T[:3, :3].ravel(), T[:3, 3]])
+
+
+def test_setup_tables(hostemu, oracle, golden):
+    e = hostemu.Emu()
+    q0, zcom, mass, it = e.nominal()
+    assert np.abs(q0 - golden["x0"][:30]).max() < 1e-13 and it == 4          # Newton IK, same root
+    assert abs(zcom - float(golden["zcom"])) < 1e-14 and abs(mass - float(golden["mass"])) < 1e-14
+    tb = e.tables()
+    assert np.abs(tb["mass"] - golden["link_mass"]).max() == 0
+    assert np.abs(tb["com"] - golden["link_com"]).max() < 1e-16
+    assert np.abs(tb["foot_coef"] - golden["foot_coef"]).max() < 1e-12
+    # MPC gain vector against its definition r = beta Pu H^-1 e0 from the reference's Px/Pu
+    Pu, Px = golden["Pu"], golden["Px"]
+    H = 1e-3 * np.eye(51) + Pu.T @ Pu
+    r = Pu @ np.linalg.solve(H, np.eye(51)[0])
+    assert np.abs(tb["mpc_r"] - r).max() < 1e-12 and np.abs(tb["rPx"] - r @ Px).max() < 1e-11
+
+
+def test_stage_against_reference_vectors(hostemu, golden):
+    e = hostemu.Emu()
+    for i in range(len(golden["stage_t"])):
+        d, vh = e.stage(golden["stage_x"][i], golden["stage_vh"][i], float(golden["stage_t"][i]))
+        for k in MODEL:
+            ref = golden["stage_" + k][i]
+            if k in ("T7", "T14"):
+                ref = _t34(ref)
+            assert relerr(d[k], ref) < 1e-12, (i, k)
+        assert relerr(d["Ha"], golden["stage_Ha"][i]) < 1e-12 and relerr(d["ga"], golden["stage_g"][i][:30]) < 1e-11
+        for k in ("qpp", "tau", "f", "xdot"):                                # north-star tolerance: 1e-6 relative
+            assert relerr(d[k], golden["stage_" + k][i]) < 1e-8, (i, k)
+        assert d["k_index"] == int(golden["stage_k_index"][i])               # integer work: bit exact
+        assert np.array_equal(vh, golden["stage_x"][i][30:])                 # held velocity advanced
+
+
+def test_qp_against_exact_solutions(hostemu, qp_exact):
+    """(a, f) of the reduced primal active-set solve vs 60-digit certified minimisers, incl. 20-31 active bounds"""
+    e = hostemu.Emu()
+    worst = 0.0
+    for i in range(len(qp_exact["g"])):
+        x = qp_exact["state"][i]
+        d, _ = e.stage(x, x[30:], 0.0)
+        assert d["qp_status"] == 0
+        xe = qp_exact["x"][i]
+        worst = max(worst, relerr(d["a"], xe[:30]), relerr(d["f"], xe[30:42]))
+        assert d["c"].min() >= 0.0                                           # feasibility is exact by construction
+        assert ((d["c"] == 0) == (xe[42:] <= 1e-14)).all() or int(qp_exact["n_active"][i]) > 0
+    assert worst < 1e-8, worst
+
+
+def test_closed_loop_1s(hostemu, golden):
+    e = hostemu.Emu()
+    x, vh, t, lg, st = e.step(golden["x0"], np.zeros(30), 0.0, 100)
+    assert np.abs(lg["com_k4"] - golden["loop_com_k4"]).max() < 1e-10       # north star: 1e-4 m
+    assert np.abs(lg["rfoot"] - golden["loop_rfoot"]).max() < 1e-10
+    assert np.abs(lg["lfoot"] - golden["loop_lfoot"]).max() < 1e-10
+    assert np.abs(x - golden["loop_x"][-1]).max() < 1e-9
+    assert relerr(lg["tau_k1"], golden["loop_tau_k1"]) < 1e-8
+    assert np.array_equal(lg["k_index"], golden["loop_k_index"])           # bit exact
+    assert st["steps"] == 100 and st["qp_fail"] == 0 and st["alive"] == 1
+
+
+def test_random_states_against_oracle(hostemu, oracle):
+    e = hostemu.Emu()
+    s = oracle.sim()
+    x0, _, _ = s.get_state()
+    rng = np.random.default_rng(99)
+    for i in range(20):
+        sc = [0.001, 0.005, 0.02, 0.08][i % 4]
+        x = x0.copy(); x[:30] += sc * rng.standard_normal(30); x[30:] = 3 * sc * rng.standard_normal(30)
+        vh = x[30:] + 0.2 * sc * rng.standard_normal(30); t = 0.01 * i
+        s.set_state(x, t, vh)
+        do = s.stage(x, t)
+        d, _ = e.stage(x, vh, t)
+        for k in MODEL[:-2]:
+            assert relerr(d[k], do[k]) < 1e-12, (i, k)
+        for k in ("qpp", "tau", "f"):
+            assert relerr(d[k], do[k]) < 1e-7, (i, k, sc)
