@@ -215,7 +215,7 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     LmhBatch* h = new LmhBatch;
     h->cfg = *cfg;
     h->n_env = n_env;
-    h->nt = cfg->threads_per_env == 0 ? 64 : cfg->threads_per_env;
+    h->nt = cfg->threads_per_env == 0 ? 32 : cfg->threads_per_env;
     if (h->nt != 32 && h->nt != 64 && h->nt != 128) { delete h; return fail(LMH_EINVAL, "lmh_create: threads_per_env must be 32, 64 or 128"); }
     try {
         Scenario s;

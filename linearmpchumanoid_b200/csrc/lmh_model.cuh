@@ -71,6 +71,7 @@ struct Consts {
     double Rdes[9];           // desired sole orientation (Robot.cpp:28-31)
     double Gf[6 * 16];        // per-foot wrench generators: rows 0-2 moment, 3-5 force (controller.cpp:156-294)
     double GtG[16 * 16];      // Gf' Gf
+    double GGt[36];           // Gf Gf' (6 x 6), the all-free wrench Gram matrix of one foot
     double KpJ, KdJ, KpM, KdM, KpF, KdF;                                    // controller.hpp:100-111
     double wCoML, wCoMK, wBasePos, wBaseAng, wJoints, wForce, wFoot, epsC;   // controller.hpp:118-124, controller.cpp:109-123
     // LIPM MPC (mpcLinearPendulum.cpp:41-68,89-101): u0 = -(rPx . [pos,vel]) + sum_i r[i]*zmp[k+i]
@@ -776,6 +777,102 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             }
         }
     }
+    // ---- fast path: all 32 coefficients free.  With y = (Jb lam - wF f)/eps the stationarity in c reads
+    //   (P + (eps/wF)(I - Jb Z^-1 Jb')) y = Jb Z^-1 rhs,  Z = wF Sa + Jb'Jb,  P = G G' (constant, block diagonal),
+    // c = G'y.  12 x 12 and well conditioned while P has full rank, i.e. exactly in the all-free case.
+    double* Vy = w.u.s.Q;             // V = Lz^-1 Jb' (6 x 12)
+    double* Ay = Vy + 72;             // 12 x 13, lower triangle factorised in place, row 12 = rhs
+    double* uy = Ay + 13 * 13;        // Lz^-1 rhs (6)
+    {
+        double Lz[36];
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c <= r; ++c) {
+                double sj = 0.0;
+                for (int k = 0; k < 12; ++k) sj += w.JF[NQ * k + r] * w.JF[NQ * k + c];
+                Lz[6 * r + c] = K.wForce * w.Sa[6 * r + c] + sj;
+            }
+        for (int k = 0; k < 6; ++k) {
+            double sd = Lz[7 * k];
+            for (int m = 0; m < k; ++m) sd -= Lz[6 * k + m] * Lz[6 * k + m];
+            double dk = sqrt(sd);
+            Lz[7 * k] = dk;
+            for (int i = k + 1; i < 6; ++i) {
+                double t = Lz[6 * i + k];
+                for (int m = 0; m < k; ++m) t -= Lz[6 * i + m] * Lz[6 * k + m];
+                Lz[6 * i + k] = t / dk;
+            }
+        }
+        LMH_FOR(j, 13) {
+            double col[6];
+            for (int r = 0; r < 6; ++r) col[r] = j < 12 ? w.JF[NQ * j + r] : w.rhs[r];
+            for (int r = 0; r < 6; ++r) {
+                double sd = col[r];
+                for (int m = 0; m < r; ++m) sd -= Lz[6 * r + m] * col[m];
+                col[r] = sd / Lz[7 * r];
+            }
+            for (int r = 0; r < 6; ++r) { if (j < 12) Vy[12 * r + j] = col[r]; else uy[r] = col[r]; }
+        }
+    }
+    cx.sync();
+    LMH_FOR(it, 13 * 12) {
+        int i = it / 12, j = it % 12;
+        if (i < 12) {
+            if (j <= i) {
+                double sv_ = 0.0;
+                for (int r = 0; r < 6; ++r) sv_ += Vy[12 * r + i] * Vy[12 * r + j];
+                double kt = (i == j ? 1.0 : 0.0) - sv_;
+                double pij = (i / 6 == j / 6) ? K.GGt[6 * (i % 6) + (j % 6)] : 0.0;
+                Ay[13 * i + j] = pij + (K.epsC / K.wForce) * kt;
+            }
+        } else {
+            double sb = 0.0;
+            for (int r = 0; r < 6; ++r) sb += Vy[12 * r + j] * uy[r];
+            Ay[13 * 12 + j] = sb;
+        }
+    }
+    cx.sync();
+    for (int k = 0; k < 12; ++k) {
+        LMH_FOR(i0, 13 - k) {
+            int i = k + i0;
+            double* ri = Ay + 13 * i;
+            const double* rk = Ay + 13 * k;
+            double s0 = ri[k];
+            for (int m = 0; m < k; ++m) s0 -= ri[m] * rk[m];
+            ri[k] = s0;
+        }
+        cx.sync();
+        double dk = sqrt(Ay[13 * k + k]);
+        LMH_FOR(i0, 13 - k) {
+            int i = k + i0;
+            if (i == k) w.piv[k] = dk;
+            else Ay[13 * i + k] = Ay[13 * i + k] / dk;
+        }
+        cx.sync();
+    }
+    for (int k = 11; k >= 0; --k) {        // L' y = z (row 12 of Ay), column oriented
+        double xk = Ay[13 * 12 + k] / w.piv[k];
+        cx.sync();
+        LMH_FOR(i, k + 1) {
+            if (i == k) Ay[13 * 12 + k] = xk;
+            else Ay[13 * 12 + i] -= Ay[13 * k + i] * xk;
+        }
+        cx.sync();
+    }
+    LMH_FOR(i, NC) {
+        int foot = i / 16, gi = i % 16;
+        double sc = 0.0;
+        for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * Ay[13 * 12 + 6 * foot + k];
+        w.cs[i] = sc;
+    }
+    cx.sync();
+    bool all_free_ok = true;
+    for (int i = 0; i < NC; ++i) all_free_ok = all_free_ok && (w.cs[i] >= 0.0);
+    int iters = 1, status = 0;
+    cx.sync();
+    if (all_free_ok) {
+        LMH_FOR(i, NC) { w.c[i] = w.cs[i]; w.free_mask[i] = 1; }
+        cx.sync();
+    } else {
     // Wm = Ls^-1 Jb' G  (6 x 32; Jb = JF[:,0:6]) and pq = Wm' sv
     LMH_FOR(i, NC + 1) {
         double col[6];
@@ -815,14 +912,15 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         double s = 0.0;
         for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * w.sv[r];
         w.pq[i] = s;
-        w.free_mask[i] = 1;
-        w.c[i] = 0.0;
+        double x0 = w.cs[i];
+        w.free_mask[i] = x0 > 0.0 ? 1 : 0;
+        w.c[i] = x0 > 0.0 ? x0 : 0.0;
     }
     cx.sync();
 
     // ---- primal active set on c >= 0
-    int iters = 0, status = 0;
-    bool have_feasible = false;
+    // start from the projection of the all-free solution: working set = the clipped coefficients
+    bool have_feasible = true;
     while (true) {
         ++iters;
         // masked left-looking Cholesky of Q_FF in the lower triangle, forward substitution of pq fused
@@ -939,6 +1037,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         cx.sync();
         if (done) break;
         if (iters >= K.qp_max_iter) { status = 1; break; }
+    }
     }
     w.qp_iters = iters;
     w.qp_status = status;

@@ -212,6 +212,12 @@ private:
                 for (int k = 0; k < 6; ++k) s += K.Gf[16 * k + i] * K.Gf[16 * k + j];
                 K.GtG[16 * i + j] = s;
             }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+                double s = 0;
+                for (int k = 0; k < 16; ++k) s += K.Gf[16 * i + k] * K.Gf[16 * j + k];
+                K.GGt[6 * i + j] = s;
+            }
     }
 
     // u0 = -e0' H^-1 beta Pu' (Px x - z)  with H = alpha I + beta Pu'Pu constant  =>  gain vector r = beta Pu H^-1 e0
