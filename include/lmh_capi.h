@@ -78,6 +78,8 @@ typedef struct {
     double max_abs_qpp;
     int32_t qp_iters, qp_fail; /* totals over all stages */
     int32_t steps, alive;      /* steps run; alive = state still finite and torso above 0.15 m */
+    int32_t qp_fallback;       /* stages that needed the c-space fallback of the QP (rank-deficient contact set) */
+    int32_t pad;
 } LmhStats;
 
 const char* lmh_last_error(void);

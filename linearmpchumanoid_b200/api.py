@@ -35,7 +35,7 @@ STAGE_DTYPE = np.dtype([("M", "f8", (30, 30)), ("C", "f8", 30), ("Cg", "f8", 30)
 STEPLOG_DTYPE = np.dtype([("com_k4", "f8", 3), ("rfoot", "f8", 3), ("lfoot", "f8", 3), ("tau_k1", "f8", 24),
                           ("k_index", "i4", 4), ("qp_iters", "i4"), ("qp_fail", "i4")])
 STATS_DTYPE = np.dtype([("max_abs_tau", "f8"), ("max_com_err", "f8"), ("max_abs_qpp", "f8"), ("qp_iters", "i4"),
-                        ("qp_fail", "i4"), ("steps", "i4"), ("alive", "i4")])
+                        ("qp_fail", "i4"), ("steps", "i4"), ("alive", "i4"), ("qp_fallback", "i4"), ("pad", "i4")])
 
 # every symbol include/lmh_capi.h declares (checked by the CPU test-suite against the built library)
 SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", "lmh_n_env", "lmh_get_nominal",

@@ -37,6 +37,7 @@ struct Params {
     LmhStepLog* log;    // [log_cap][E] or null
     LmhStageDump* dump; // [E] or null
     double* com;        // [E][3]
+    double* qp_scratch; // [E][QP_SCRATCH_DOUBLES] global scratch of the rare c-space QP fallback
     int32_t n_env, n_steps, step0, log_cap;
 };
 
@@ -57,11 +58,12 @@ __global__ void __launch_bounds__(NT) rollout_kernel(Params p) {
     double t = p.t[env];
     const int plan_id = p.plan_id ? p.plan_id[env] : 0;
     const int push_at = p.push_step ? p.push_step[env] : -1;
+    double* gscratch = p.qp_scratch + (size_t)env * QP_SCRATCH_DOUBLES;
     StatsAcc st;
     {
         const LmhStats& s0 = p.stats[env];
         st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
-        st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive;
+        st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
     }
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(Params p) {
             cx.sync();
         }
         LmhStepLog* lg = (p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
-        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, lg, &st);
+        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, gscratch, lg, &st);
     }
     for (int i = threadIdx.x; i < 60; i += NT) p.x[(size_t)env * 60 + i] = x[i];
     for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(Params p) {
         p.t[env] = t;
         LmhStats& s1 = p.stats[env];
         s1.max_abs_tau = st.max_tau; s1.max_com_err = st.max_err; s1.max_abs_qpp = st.max_qpp;
-        s1.qp_iters = st.qp_iters; s1.qp_fail = st.qp_fail; s1.steps = st.steps; s1.alive = st.alive;
+        s1.qp_iters = st.qp_iters; s1.qp_fail = st.qp_fail; s1.steps = st.steps; s1.alive = st.alive; s1.qp_fallback = st.qp_fallback; s1.pad = 0;
     }
 }
 
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(NT) stage_kernel(Params p) {
     }
     if (threadIdx.x == 0) w.t = p.t[env];
     cx.sync();
-    stage_eval(cx, w, *p.K, p.plan, p.plan_id ? p.plan_id[env] : 0, p.dump ? p.dump + env : nullptr);
+    stage_eval(cx, w, *p.K, p.plan, p.plan_id ? p.plan_id[env] : 0, p.qp_scratch + (size_t)env * QP_SCRATCH_DOUBLES,
+               p.dump ? p.dump + env : nullptr);
     for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];
     for (int i = threadIdx.x; i < 3; i += NT) p.com[(size_t)env * 3 + i] = w.com[i];
 }
@@ -127,7 +130,7 @@ struct LmhBatch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
     double *d_x = nullptr, *d_vh = nullptr, *d_t = nullptr, *d_push_dv = nullptr, *d_com = nullptr;
-    double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr;
+    double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr, *d_qp_scratch = nullptr;
     int32_t *d_plan_id = nullptr, *d_push_step = nullptr;
     LmhStats* d_stats = nullptr;
     LmhStats* d_stats0 = nullptr;
@@ -149,7 +152,7 @@ Params make_params(LmhBatch* h) {
     p.x = h->d_x; p.vh = h->d_vh; p.t = h->d_t;
     p.push_step = h->has_pushes ? h->d_push_step : nullptr;
     p.push_dv = h->d_push_dv;
-    p.stats = h->d_stats; p.log = h->d_log; p.dump = nullptr; p.com = h->d_com;
+    p.stats = h->d_stats; p.log = h->d_log; p.dump = nullptr; p.com = h->d_com; p.qp_scratch = h->d_qp_scratch;
     p.n_env = h->n_env; p.n_steps = 0; p.step0 = h->step_counter; p.log_cap = h->cfg.log_steps;
     return p;
 }
@@ -240,6 +243,7 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     CU(cudaMalloc(&h->d_x, E * 60 * sizeof(double))); CU(cudaMalloc(&h->d_vh, E * 30 * sizeof(double)));
     CU(cudaMalloc(&h->d_t, E * sizeof(double))); CU(cudaMalloc(&h->d_push_dv, E * 6 * sizeof(double)));
     CU(cudaMalloc(&h->d_com, E * 3 * sizeof(double)));
+    CU(cudaMalloc(&h->d_qp_scratch, E * QP_SCRATCH_DOUBLES * sizeof(double)));
     CU(cudaMalloc(&h->d_plan_id, E * sizeof(int32_t))); CU(cudaMalloc(&h->d_push_step, E * sizeof(int32_t)));
     CU(cudaMalloc(&h->d_stats, E * sizeof(LmhStats)));
     CU(cudaMalloc(&h->d_dump, E * sizeof(LmhStageDump)));
@@ -257,7 +261,7 @@ void lmh_destroy(LmhBatch* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
+    cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com); cudaFree(h->d_qp_scratch);
     cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
     cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -43,6 +43,7 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+constexpr int QP_SCRATCH_DOUBLES = 6 * NC + NC * LDQ + 4 * NC;   // per-env global scratch of the rare c-space fallback
 
 // chain c: frames chain_first[c] .. chain_first[c]+chain_len[c]-1, depth 1..chain_len[c]
 LMH_HD int chain_first(int c) { return c == 0 ? 1 : c == 1 ? 8 : c == 2 ? 15 : c == 3 ? 20 : 25; }
@@ -96,7 +97,7 @@ struct Plan {
 struct EnvWS {
     // ---- state of the stage being evaluated
     double q[NQ], v[NQ], vh[NQ];   // vh: velocity held by the Robot object from the PREVIOUS stage (controller.cpp:48-79)
-    double vb[NQ], vhb[NQ];        // the same with the base twist as [omega; v] in the base frame
+    double vb6[6], vhb6[6];        // base twists of v and vh as [omega; v] in the torso frame (joint rates are unchanged)
     double t;
     // ---- persistent through a stage
     double R0[9], p0[3];           // torso pose
@@ -105,34 +106,53 @@ struct EnvWS {
     double Hc[NCH * 36];           // joint-space inertia, one 6x6 block per chain (chains do not couple)
     double C[NQ], Cg[NQ];
     double AG[6 * NQ], AGpqp[6];
-    double JF[12 * NQ], Jpqp[12];
+    double JFc[2 * 6 * 12];        // sole Jacobians, compact: [foot][row][0..5 base twist | 6..11 that leg's joints]
+    double Jpqp[12];
     double com[3], comVel[3], angMom[3], xRef[3], yRef[3];
     double qppRef[NQ], hGpRef[6], footAccRef[12];
-    double ga[NQ], a[NQ], f12[12], qpp[NQ], tau[NJ], xdot[2 * NQ];
-    double Y[7 * NQ];              // rows 0..5: (La^-1 M6')', row 6: (La^-1 ga)'
-    double Sa[36], Ls[36], rhs[6], sv[6], lam[6];
-    double c[NC], cs[NC], pq[NC], mu[NC], zq[NC], qdiag[NC], ldiag[NC], piv[NC], ladiag[NQ];
-    double red[64];                // reduction scratch
+    double ga[NQ], a[NQ], f12[12], tau[NJ], xdot[2 * NQ];
+    double Sa[36], rhs[6], sv[6], lam[6];
+    double c[NC], cs[NC], mu[NC], piv[NC], ladiag[NQ];
+    double red[32];                // reduction scratch
     int32_t free_mask[NC];
-    int32_t k_index, qp_iters, qp_status, pad_;
+    int32_t k_index, qp_iters, qp_status, qp_fallback;
     // ---- phase-overlaid scratch
     union {
         struct {                       // model phase
-            double Tw[NF * 12];        // world transforms (R row-major 9, p 3)
             double Xl[NF * 12];        // local transform first, then parent-relative (R_rel, p_rel)
-            double vel[NF * 6], acc[NF * 6], frc[NF * 6];
-            double Ic[NF * 36];
-            double Xd[NCH * 36], Yt[NCH * 36];
-            double Fb[2][NJ * 6];
-            double Xn[2][2 * 18];      // running sole_X_j as (E, B) for both feet, double buffered
+            union {
+                double Tw[NF * 12];    // world transforms (R row-major 9, p 3): forward kinematics only
+                struct { double vel[NF * 6], acc[NF * 6], frc[NF * 6]; } rnea;
+                struct {
+                    double IcIn[NCH * 36];     // composite inertia arriving from the level below
+                    double IcCur[NCH * 36];    // composite inertia of the level being processed
+                    double Xd[NCH * 36], Yt[NCH * 36];
+                    double Fb[2][NJ * 6];
+                } crba;
+                double Xn[2][2 * 18];  // running sole_X_j as (E, B) for both feet, double buffered
+            } p;
         } m;
         struct {                       // assembly + QP phase
             double Ha[NQ * LDM];       // H_a, then its Cholesky factor (lower)
-            double Wm[6 * NC];         // Ls^-1 Jb' G
-            double Q[NC * LDQ];        // upper: Q = wF G'G + Wm'Wm + eps I ; lower: masked Cholesky factor
+            double Y[7 * NQ];          // rows 0..5: (La^-1 M6')', row 6: (La^-1 ga)'
+            double Vy[6 * 12];         // Lz^-1 Jb'
+            double Ay[13 * 13];        // wrench-space system: lower triangle factorised in place, row 12 = rhs / y
+            double uy[6];              // Lz^-1 rhs
         } s;
     } u;
 };
+
+// compact column of generalized coordinate i in the Jacobian of foot s, or -1
+LMH_HD int jf_col(int s, int i) {
+    if (i < 6) return i;
+    int l = i - 6 - 6 * s;
+    return (l >= 0 && l < 6) ? 6 + l : -1;
+}
+LMH_HD double jf_full(const EnvWS& w, int row, int col) {
+    int s = row / 6, cc = jf_col(s, col);
+    return cc < 0 ? 0.0 : w.JFc[72 * s + 12 * (row % 6) + cc];
+}
+LMH_HD double vb_at(const EnvWS& w, int j) { return j < 6 ? w.vb6[j] : w.v[j]; }
 
 // ------------------------------------------------------------------------------------------------
 template <int NT_>
@@ -197,7 +217,7 @@ LMH_HD double xdense(const double* Rp, int a, int b) {
 // Phase 1: forward kinematics, parent-relative transforms, CoM.
 template <class Cx>
 LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
-    double* Tw = w.u.m.Tw;
+    double* Tw = w.u.m.p.Tw;
     double* Xl = w.u.m.Xl;
     // torso pose (generalizedFunctions.cpp:52-72) and local DH transforms (Robot.cpp:176-223)
     LMH_FOR(i, NF) {
@@ -306,18 +326,14 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
 // base twist of a generalized velocity into the torso frame: [w; v] -> X0 [w; v]  (generalizedFunctions.cpp:195-206)
 template <class Cx>
 LMH_HDN void base_twist_phase(const Cx& cx, EnvWS& w) {
-    LMH_FOR(it, 2 * NQ) {
-        int which = it / NQ, k = it % NQ;
+    LMH_FOR(it, 12) {
+        int which = it / 6, k = it % 6;
         const double* src = which == 0 ? w.v : w.vh;
-        double* dst = which == 0 ? w.vb : w.vhb;
-        if (k >= 6) dst[k] = src[k];
-        else {
-            double m[6] = {src[3], src[4], src[5], src[0], src[1], src[2]};
-            double Rp[12];
-            for (int e = 0; e < 9; ++e) Rp[e] = w.R0[e];
-            for (int e = 0; e < 3; ++e) Rp[9 + e] = w.p0[e];
-            dst[k] = xmotion_k(Rp, m, k);
-        }
+        double m[6] = {src[3], src[4], src[5], src[0], src[1], src[2]};
+        double Rp[12];
+        for (int e = 0; e < 9; ++e) Rp[e] = w.R0[e];
+        for (int e = 0; e < 3; ++e) Rp[9 + e] = w.p0[e];
+        (which == 0 ? w.vb6 : w.vhb6)[k] = xmotion_k(Rp, m, k);
     }
     cx.sync();
 }
@@ -327,11 +343,11 @@ LMH_HDN void base_twist_phase(const Cx& cx, EnvWS& w) {
 // (Dynamics.cpp:29-60,124-200).
 template <class Cx>
 LMH_HDN void rnea_phase(const Cx& cx, EnvWS& w, const Consts& K) {
-    double* vel = w.u.m.vel;
-    double* acc = w.u.m.acc;
-    double* frc = w.u.m.frc;
+    double* vel = w.u.m.p.rnea.vel;
+    double* acc = w.u.m.p.rnea.acc;
+    double* frc = w.u.m.p.rnea.frc;
     const double* Xl = w.u.m.Xl;
-    LMH_FOR(k, 6) { vel[k] = w.vhb[k]; acc[k] = 0.0; }
+    LMH_FOR(k, 6) { vel[k] = w.vhb6[k]; acc[k] = 0.0; }
     cx.sync();
     for (int d = 1; d <= MAXDEPTH; ++d) {
         LMH_FOR(it, NCH * 6) {
@@ -340,7 +356,7 @@ LMH_HDN void rnea_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                 int i = chain_first(c) + d - 1;
                 int a = frame_joint(i);
                 double x = xmotion_k(Xl + 12 * i, vel + 6 * frame_parent(i), k);
-                if (a >= 0 && k == 2) x += w.vhb[6 + a];
+                if (a >= 0 && k == 2) x += w.vh[6 + a];
                 vel[6 * i + k] = x;
             }
         }
@@ -352,7 +368,7 @@ LMH_HDN void rnea_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                 int a = frame_joint(i);
                 double x = xmotion_k(Xl + 12 * i, acc + 6 * frame_parent(i), k);
                 if (a >= 0) {   // + (v x S) qd with S = e_z
-                    double qd = w.vhb[6 + a];
+                    double qd = w.vh[6 + a];
                     const double* vi = vel + 6 * i;
                     double col = k == 0 ? vi[1] : k == 1 ? -vi[0] : k == 3 ? vi[4] : k == 4 ? -vi[3] : 0.0;
                     x += col * qd;
@@ -426,37 +442,41 @@ LMH_HDN void rnea_phase(const Cx& cx, EnvWS& w, const Consts& K) {
 // Phase 3: CRBA (Dynamics.cpp:62-101) -> M6 = [Ic0 | F2], Hc (per-chain joint blocks).
 template <class Cx>
 LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
-    double* Ic = w.u.m.Ic;
-    double* Xd = w.u.m.Xd;
-    double* Yt = w.u.m.Yt;
+    double* IcIn = w.u.m.p.crba.IcIn;
+    double* IcCur = w.u.m.p.crba.IcCur;
+    double* Xd = w.u.m.p.crba.Xd;
+    double* Yt = w.u.m.p.crba.Yt;
     const double* Xl = w.u.m.Xl;
-    LMH_FOR(it, NF * 36) Ic[it] = K.Isp[it];
-    LMH_FOR(it, NCH * 36) w.Hc[it] = 0.0;
+    LMH_FOR(it, NCH * 36) { IcIn[it] = 0.0; w.Hc[it] = 0.0; }
     cx.sync();
     int cur = 0;
-    for (int d = MAXDEPTH - 1; d >= 1; --d) {   // actuated depths 6..1
-        // (a) dense X of this level's frames; new F vector of each frame = column 2 of its final Ic
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int d = MAXDEPTH - 1; d >= 1; --d) {   // actuated depths 6..1; only two levels of composite inertia are alive
+        // (a) composite inertia of this level's frames = own inertia + what arrived from below; dense X;
+        //     new F vector of each frame = column 2 of its composite inertia
         LMH_FOR(it, NCH * 36) {
             int c = it / 36, e = it % 36;
-            if (d <= chain_nact(c)) Xd[it] = xdense(Xl + 12 * (chain_first(c) + d - 1), e / 6, e % 6);
-        }
-        LMH_FOR(it, NCH * 6) {
-            int c = it / 6, k = it % 6;
             if (d <= chain_nact(c)) {
                 int i = chain_first(c) + d - 1;
-                int a = chain_joint0(c) + d - 1;
-                double fk = Ic[36 * i + 6 * k + 2];
-                w.u.m.Fb[cur][6 * a + k] = fk;
-                if (k == 2) w.Hc[36 * c + 7 * (d - 1)] = fk;
+                double v = K.Isp[36 * i + e] + IcIn[it];
+                IcCur[it] = v;
+                Xd[it] = xdense(Xl + 12 * i, e / 6, e % 6);
+                if (e % 6 == 2) {
+                    int k = e / 6, a = chain_joint0(c) + d - 1;
+                    w.u.m.p.crba.Fb[cur][6 * a + k] = v;
+                    if (k == 2) w.Hc[36 * c + 7 * (d - 1)] = v;
+                }
             }
         }
         cx.sync();
-        // (b) Yt = Ic_i X_i ; F vectors of every joint at depth >= d move one frame up: F <- X_i' F
+        // (b) Yt = Ic X ; F vectors of every joint at depth >= d move one frame up: F <- X' F
         LMH_FOR(it, NCH * 36) {
             int c = it / 36, e = it % 36;
             if (d <= chain_nact(c)) {
                 int r = e / 6, cc = e % 6;
-                const double* I = Ic + 36 * (chain_first(c) + d - 1) + 6 * r;
+                const double* I = IcCur + 36 * c + 6 * r;
                 const double* X = Xd + 36 * c + cc;
                 Yt[it] = I[0] * X[0] + I[1] * X[6] + I[2] * X[12] + I[3] * X[18] + I[4] * X[24] + I[5] * X[30];
             }
@@ -467,8 +487,8 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             int da = a - chain_joint0(c) + 1;       // depth of joint a
             if (da >= d) {
                 int i = chain_first(c) + d - 1;     // frame being crossed
-                double x = xforceT_k(Xl + 12 * i, w.u.m.Fb[cur] + 6 * a, k);
-                w.u.m.Fb[cur ^ 1][it] = x;
+                double x = xforceT_k(Xl + 12 * i, w.u.m.p.crba.Fb[cur] + 6 * a, k);
+                w.u.m.p.crba.Fb[cur ^ 1][it] = x;
                 if (d > 1 && k == 2) {              // H(parent joint, a), symmetric
                     int pj = d - 2, aj = da - 1;
                     w.Hc[36 * c + 6 * pj + aj] = x;
@@ -478,7 +498,7 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             }
         }
         cx.sync();
-        // (c) Ic_parent += X' Yt
+        // (c) what the parent level receives: X' Yt
         if (d > 1) {
             LMH_FOR(it, NCH * 36) {
                 int c = it / 36, e = it % 36;
@@ -486,20 +506,19 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                     int r = e / 6, cc = e % 6;
                     const double* X = Xd + 36 * c + r;
                     const double* Y = Yt + 36 * c + cc;
-                    Ic[36 * (chain_first(c) + d - 2) + e] +=
-                        X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
+                    IcIn[it] = X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
                 }
             }
         } else {
             LMH_FOR(e, 36) {
                 int r = e / 6, cc = e % 6;
-                double s = Ic[e];
+                double sum = K.Isp[e];
                 for (int c = NCH - 1; c >= 0; --c) {
                     const double* X = Xd + 36 * c + r;
                     const double* Y = Yt + 36 * c + cc;
-                    s += X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
+                    sum += X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
                 }
-                w.M6[NQ * r + cc] = s;   // Ic0
+                w.M6[NQ * r + cc] = sum;   // Ic0
             }
         }
         cx.sync();
@@ -541,12 +560,11 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
             else { w.AGpqp[k] = a; w.AGpqp[3 + k] = b; }
         }
     }
-    LMH_FOR(it, 12 * NQ) w.JF[it] = 0.0;
     // running sole_X_j = (E, B) for both feet, starting from the sole frame
     LMH_FOR(it, 36) {
         int s = it / 18, e = it % 18;
         const double* Rp = Xl + 12 * (s == 0 ? 7 : 14);
-        w.u.m.Xn[0][it] = e < 9 ? xdense(Rp, e / 3, e % 3) : xdense(Rp, 3 + (e - 9) / 3, (e - 9) % 3);
+        w.u.m.p.Xn[0][it] = e < 9 ? xdense(Rp, e / 3, e % 3) : xdense(Rp, 3 + (e - 9) / 3, (e - 9) % 3);
     }
     cx.sync();
     int cur = 0;
@@ -554,7 +572,7 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
         LMH_FOR(it, 36) {
             int s = it / 18, e = it % 18;
             int j = (s == 0 ? 6 : 13) - step;
-            const double* Xc = w.u.m.Xn[cur] + 18 * s;     // E (9), B (9)
+            const double* Xc = w.u.m.p.Xn[cur] + 18 * s;     // E (9), B (9)
             const double* Rp = Xl + 12 * j;
             int r = (e % 9) / 3, cc = e % 3;
             double x;
@@ -564,16 +582,15 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
                 x = Xc[9 + 3 * r] * xdense(Rp, 0, cc) + Xc[9 + 3 * r + 1] * xdense(Rp, 1, cc) + Xc[9 + 3 * r + 2] * xdense(Rp, 2, cc) +
                     Xc[3 * r] * xdense(Rp, 3, cc) + Xc[3 * r + 1] * xdense(Rp, 4, cc) + Xc[3 * r + 2] * xdense(Rp, 5, cc);
             }
-            w.u.m.Xn[cur ^ 1][it] = x;
+            w.u.m.p.Xn[cur ^ 1][it] = x;
         }
         // joint column of frame j = world-rotated column 2 of the current sole_X_(j)
         LMH_FOR(it, 12) {
             int s = it / 6, k = it % 6;
-            int j = (s == 0 ? 6 : 13) - step;
-            const double* Xc = w.u.m.Xn[cur] + 18 * s;
+            const double* Xc = w.u.m.p.Xn[cur] + 18 * s;
             const double* col = k < 3 ? Xc : Xc + 9;
             double cv[3] = {col[2], col[5], col[8]};
-            w.JF[NQ * (6 * s + k) + 6 + frame_joint(j)] = rot_row(w.Rs[s], k % 3, cv);
+            w.JFc[72 * s + 12 * k + 11 - step] = rot_row(w.Rs[s], k % 3, cv);
         }
         cx.sync();
         cur ^= 1;
@@ -581,17 +598,17 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
     // base block: rotated sole_X_base = [[E,0],[B,E]]
     LMH_FOR(it, 72) {
         int s = it / 36, k = (it % 36) / 6, b = it % 6;
-        const double* Xc = w.u.m.Xn[cur] + 18 * s;
+        const double* Xc = w.u.m.p.Xn[cur] + 18 * s;
         double cv[3];
         if (k < 3) { if (b < 3) { cv[0] = Xc[b]; cv[1] = Xc[3 + b]; cv[2] = Xc[6 + b]; } else { cv[0] = cv[1] = cv[2] = 0.0; } }
         else { const double* S = b < 3 ? Xc + 9 : Xc; int bb = b % 3; cv[0] = S[bb]; cv[1] = S[3 + bb]; cv[2] = S[6 + bb]; }
-        w.JF[NQ * (6 * s + k) + b] = rot_row(w.Rs[s], k % 3, cv);
+        w.JFc[72 * s + 12 * k + b] = rot_row(w.Rs[s], k % 3, cv);
     }
     cx.sync();
     // h = AG vb (current velocity)
     LMH_FOR(k, 6) {
         double s = 0.0;
-        for (int j = 0; j < NQ; ++j) s += w.AG[NQ * k + j] * w.vb[j];
+        for (int j = 0; j < NQ; ++j) s += w.AG[NQ * k + j] * vb_at(w, j);
         if (k < 3) w.angMom[k] = s; else w.comVel[k - 3] = s / K.mass;
     }
     cx.sync();
@@ -647,7 +664,11 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
     LMH_FOR(it, 12) {
         int s = it / 6, k = it % 6;
         double velk = 0.0;
-        for (int j = 0; j < NQ; ++j) velk += w.JF[NQ * it + j] * w.vb[j];
+        {
+            const double* Jr = w.JFc + 72 * s + 12 * k;
+            for (int j = 0; j < 6; ++j) velk += Jr[j] * w.vb6[j];
+            for (int j = 0; j < 6; ++j) velk += Jr[6 + j] * w.v[6 + 6 * s + j];
+        }
         double out;
         if (k < 3) {
             // e = -Rdes * log(Rdes' R)
@@ -693,7 +714,13 @@ LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         for (int k = 0; k < 3; ++k) s += K.wCoMK * w.AG[NQ * k + i] * w.AG[NQ * k + j];
         for (int k = 3; k < 6; ++k) s += K.wCoML * w.AG[NQ * k + i] * w.AG[NQ * k + j];
         double sj = 0.0;
-        for (int k = 0; k < 12; ++k) sj += w.JF[NQ * k + i] * w.JF[NQ * k + j];
+        for (int f = 0; f < 2; ++f) {
+            int ci = jf_col(f, i), cj = jf_col(f, j);
+            if (ci >= 0 && cj >= 0) {
+                const double* Jf = w.JFc + 72 * f;
+                for (int k = 0; k < 6; ++k) sj += Jf[12 * k + ci] * Jf[12 * k + cj];
+            }
+        }
         s += K.wFoot * sj;
         if (i == j) s += i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
         Ha[LDM * i + j] = s;
@@ -702,11 +729,169 @@ LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         double s = 0.0;
         for (int k = 0; k < 6; ++k) s += (k < 3 ? K.wCoMK : K.wCoML) * w.AG[NQ * k + i] * (w.AGpqp[k] - w.hGpRef[k]);
         double sj = 0.0;
-        for (int k = 0; k < 12; ++k) sj += w.JF[NQ * k + i] * (w.Jpqp[k] - w.footAccRef[k]);
+        for (int f = 0; f < 2; ++f) {
+            int ci = jf_col(f, i);
+            if (ci >= 0)
+                for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + ci] * (w.Jpqp[6 * f + k] - w.footAccRef[6 * f + k]);
+        }
         double wj = i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
         w.ga[i] = s - wj * w.qppRef[i] + K.wFoot * sj;
     }
     cx.sync();
+}
+
+// c-space fallback of the WBC QP for working sets on which the wrench Gram matrix P_F is (nearly) singular
+// (a foot left with too few free generators, e.g. tipping on an edge):
+//   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I   (32 x 32),
+// masked Cholesky of Q per working set.  Q lives in a per-environment GLOBAL scratch buffer: this path is rare
+// and keeping it out of shared memory doubles the number of resident environments.  Continues the primal
+// active-set iteration from the current feasible point (w.c, w.free_mask).
+template <class Cx>
+LMH_HDN void qp_cspace_fallback(const Cx& cx, EnvWS& w, const Consts& K, const double* Ls, double* gs, int& iters, int& status) {
+    double* Wm = gs;               // 6 x 32
+    double* Q = gs + 6 * NC;       // upper: Q ; lower: masked factor
+    double* pq = Q + NC * LDQ;
+    double* zq = pq + NC;
+    double* qdiag = zq + NC;
+    double* ldiag = qdiag + NC;
+    LMH_FOR(i, NC + 1) {
+        double col[6];
+        if (i < NC) {
+            int foot = i / 16, gi = i % 16;
+            for (int r = 0; r < 6; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < 6; ++k) s += w.JFc[72 * foot + 12 * k + r] * K.Gf[16 * k + gi];
+                col[r] = s;
+            }
+        } else {
+            for (int r = 0; r < 6; ++r) col[r] = w.rhs[r];
+        }
+        for (int r = 0; r < 6; ++r) {
+            double s = col[r];
+            for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * col[m];
+            col[r] = s / Ls[7 * r];
+        }
+        if (i < NC) for (int r = 0; r < 6; ++r) Wm[NC * r + i] = col[r];
+        else for (int r = 0; r < 6; ++r) w.sv[r] = col[r];
+    }
+    cx.sync();
+    LMH_FOR(it, NC * (NC + 1) / 2) {
+        int i = (int)((sqrt(8.0 * it + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= it) ++i;
+        while (i * (i + 1) / 2 > it) --i;
+        int j = it - i * (i + 1) / 2;     // j <= i ; store at the UPPER position (j,i)
+        double s = 0.0;
+        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * Wm[NC * r + j];
+        if (i / 16 == j / 16) s += K.wForce * K.GtG[16 * (i % 16) + (j % 16)];
+        if (i == j) qdiag[i] = s + K.epsC;
+        else Q[LDQ * j + i] = s;
+    }
+    LMH_FOR(i, NC) {
+        double s = 0.0;
+        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * w.sv[r];
+        pq[i] = s;
+    }
+    cx.sync();
+    while (true) {
+        ++iters;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 0; k < NC; ++k) {
+            const bool fk = w.free_mask[k] != 0;
+            LMH_FOR(i0, NC + 1 - k) {
+                int i = k + i0;   // i == NC : the rhs row
+                double s0 = 0.0;
+                if (fk) {
+                    if (i < NC) {
+                        if (w.free_mask[i]) {
+                            s0 = i == k ? qdiag[k] : Q[LDQ * k + i];
+                            const double* ri = Q + LDQ * i;
+                            const double* rk = Q + LDQ * k;
+                            double s1 = 0.0;
+                            int m = 0;
+                            for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
+                            if (m < k) s0 -= ri[m] * rk[m];
+                            s0 += s1;
+                        }
+                    } else {
+                        s0 = pq[k];
+                        const double* rk = Q + LDQ * k;
+                        for (int m = 0; m < k; ++m) s0 -= zq[m] * rk[m];
+                    }
+                }
+                if (i == k) w.piv[k] = fk ? s0 : 1.0;
+                else if (i < NC) Q[LDQ * i + k] = s0;
+                else zq[k] = s0;
+            }
+            cx.sync();
+            double pv = w.piv[k];
+            double dk = sqrt(pv > 0.0 ? pv : 1e-300);
+            LMH_FOR(i0, NC + 1 - k) {
+                int i = k + i0;
+                if (i == k) ldiag[k] = dk;
+                else if (i < NC) Q[LDQ * i + k] = Q[LDQ * i + k] / dk;
+                else zq[k] = zq[k] / dk;
+            }
+            cx.sync();
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = NC - 1; k >= 0; --k) {      // L' cs = zq, column oriented
+            double xk = zq[k] / ldiag[k];
+            cx.sync();
+            LMH_FOR(i, k + 1) {
+                if (i == k) w.cs[k] = w.free_mask[k] ? xk : 0.0;
+                else zq[i] -= Q[LDQ * k + i] * xk;
+            }
+            cx.sync();
+        }
+        LMH_FOR(i, NC) {                          // gradient on the working set: mu = Q cs - pq
+            double s = -pq[i];
+            for (int j = 0; j < NC; ++j) {
+                double qij = i == j ? qdiag[i] : (i < j ? Q[LDQ * i + j] : Q[LDQ * j + i]);
+                s += qij * w.cs[j];
+            }
+            w.mu[i] = s;
+        }
+        cx.sync();
+        double cmin = 0.0, pmax = 1.0;
+        for (int i = 0; i < NC; ++i) {
+            if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
+            pmax = fmax(pmax, fabs(pq[i]));
+        }
+        bool done = false;
+        int change = -1, to_free = 0;
+        double alpha = 1.0;
+        if (cmin >= 0.0) {
+            double worst = -1e-12 * pmax;
+            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
+            if (change < 0) done = true; else to_free = 1;
+        } else {
+            double best = 2.0;
+            for (int i = 0; i < NC; ++i)
+                if (w.free_mask[i] && w.cs[i] < 0.0) {
+                    double dl = w.c[i] - w.cs[i];
+                    double r = dl > 0.0 ? w.c[i] / dl : 0.0;
+                    if (r < best) { best = r; change = i; }
+                }
+            alpha = best < 1.0 ? best : 1.0;
+        }
+        cx.sync();
+        LMH_FOR(i, NC) {
+            double x = w.c[i] + alpha * (w.cs[i] - w.c[i]);
+            if (!w.free_mask[i]) x = 0.0;
+            if (i == change) {
+                if (to_free) w.free_mask[i] = 1;
+                else { w.free_mask[i] = 0; x = 0.0; }
+            }
+            w.c[i] = x > 0.0 ? x : 0.0;
+        }
+        cx.sync();
+        if (done) { status = 0; break; }
+        if (iters >= K.qp_max_iter) { status = 1; break; }
+    }
 }
 
 // ================================================================================================
@@ -717,9 +902,9 @@ LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
 // leaving   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I,
 // which a primal active-set method solves exactly (masked Cholesky of Q per working set).
 template <class Cx>
-LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch) {
     double* Ha = w.u.s.Ha;
-    double* Y = w.Y;
+    double* Y = w.u.s.Y;
     // rows 30..36 of the augmented matrix: M6 and ga' ; left-looking Cholesky carries them along so
     // that they come out as (La^-1 M6')' and (La^-1 ga)'.
     LMH_FOR(it, 7 * NQ) Y[it] = it < 6 * NQ ? w.M6[it] : w.ga[it - 6 * NQ];
@@ -777,18 +962,20 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             }
         }
     }
-    // ---- fast path: all 32 coefficients free.  With y = (Jb lam - wF f)/eps the stationarity in c reads
-    //   (P + (eps/wF)(I - Jb Z^-1 Jb')) y = Jb Z^-1 rhs,  Z = wF Sa + Jb'Jb,  P = G G' (constant, block diagonal),
-    // c = G'y.  12 x 12 and well conditioned while P has full rank, i.e. exactly in the all-free case.
-    double* Vy = w.u.s.Q;             // V = Lz^-1 Jb' (6 x 12)
-    double* Ay = Vy + 72;             // 12 x 13, lower triangle factorised in place, row 12 = rhs
-    double* uy = Ay + 13 * 13;        // Lz^-1 rhs (6)
+    // ---- wrench-space solves.  With y = (Jb lam - wF f)/eps the stationarity in the free coefficients reads
+    //   (P_F + (eps/wF)(I - Jb Z^-1 Jb')) y = Jb Z^-1 rhs,  Z = wF Sa + Jb'Jb,  P_F = sum_{i free} g_i g_i',
+    // with c_F = G_F'y and multipliers -eps g_i'y on the working set.  12 x 12, and well conditioned as long
+    // as P_F keeps full rank (always in the all-free case; checked through the Cholesky pivots otherwise).
+    double* Vy = w.u.s.Vy;
+    double* Ay = w.u.s.Ay;
+    double* uy = w.u.s.uy;
     {
         double Lz[36];
         for (int r = 0; r < 6; ++r)
             for (int c = 0; c <= r; ++c) {
                 double sj = 0.0;
-                for (int k = 0; k < 12; ++k) sj += w.JF[NQ * k + r] * w.JF[NQ * k + c];
+                for (int f = 0; f < 2; ++f)
+                    for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + r] * w.JFc[72 * f + 12 * k + c];
                 Lz[6 * r + c] = K.wForce * w.Sa[6 * r + c] + sj;
             }
         for (int k = 0; k < 6; ++k) {
@@ -804,7 +991,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         }
         LMH_FOR(j, 13) {
             double col[6];
-            for (int r = 0; r < 6; ++r) col[r] = j < 12 ? w.JF[NQ * j + r] : w.rhs[r];
+            for (int r = 0; r < 6; ++r) col[r] = j < 12 ? w.JFc[72 * (j / 6) + 12 * (j % 6) + r] : w.rhs[r];
             for (int r = 0; r < 6; ++r) {
                 double sd = col[r];
                 for (int m = 0; m < r; ++m) sd -= Lz[6 * r + m] * col[m];
@@ -813,200 +1000,101 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             for (int r = 0; r < 6; ++r) { if (j < 12) Vy[12 * r + j] = col[r]; else uy[r] = col[r]; }
         }
     }
+    LMH_FOR(i, NC) { w.free_mask[i] = 1; w.c[i] = 0.0; }
     cx.sync();
-    LMH_FOR(it, 13 * 12) {
-        int i = it / 12, j = it % 12;
-        if (i < 12) {
-            if (j <= i) {
-                double sv_ = 0.0;
-                for (int r = 0; r < 6; ++r) sv_ += Vy[12 * r + i] * Vy[12 * r + j];
-                double kt = (i == j ? 1.0 : 0.0) - sv_;
-                double pij = (i / 6 == j / 6) ? K.GGt[6 * (i % 6) + (j % 6)] : 0.0;
-                Ay[13 * i + j] = pij + (K.epsC / K.wForce) * kt;
-            }
-        } else {
-            double sb = 0.0;
-            for (int r = 0; r < 6; ++r) sb += Vy[12 * r + j] * uy[r];
-            Ay[13 * 12 + j] = sb;
-        }
-    }
-    cx.sync();
-    for (int k = 0; k < 12; ++k) {
-        LMH_FOR(i0, 13 - k) {
-            int i = k + i0;
-            double* ri = Ay + 13 * i;
-            const double* rk = Ay + 13 * k;
-            double s0 = ri[k];
-            for (int m = 0; m < k; ++m) s0 -= ri[m] * rk[m];
-            ri[k] = s0;
-        }
-        cx.sync();
-        double dk = sqrt(Ay[13 * k + k]);
-        LMH_FOR(i0, 13 - k) {
-            int i = k + i0;
-            if (i == k) w.piv[k] = dk;
-            else Ay[13 * i + k] = Ay[13 * i + k] / dk;
-        }
-        cx.sync();
-    }
-    for (int k = 11; k >= 0; --k) {        // L' y = z (row 12 of Ay), column oriented
-        double xk = Ay[13 * 12 + k] / w.piv[k];
-        cx.sync();
-        LMH_FOR(i, k + 1) {
-            if (i == k) Ay[13 * 12 + k] = xk;
-            else Ay[13 * 12 + i] -= Ay[13 * k + i] * xk;
-        }
-        cx.sync();
-    }
-    LMH_FOR(i, NC) {
-        int foot = i / 16, gi = i % 16;
-        double sc = 0.0;
-        for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * Ay[13 * 12 + 6 * foot + k];
-        w.cs[i] = sc;
-    }
-    cx.sync();
-    bool all_free_ok = true;
-    for (int i = 0; i < NC; ++i) all_free_ok = all_free_ok && (w.cs[i] >= 0.0);
-    int iters = 1, status = 0;
-    cx.sync();
-    if (all_free_ok) {
-        LMH_FOR(i, NC) { w.c[i] = w.cs[i]; w.free_mask[i] = 1; }
-        cx.sync();
-    } else {
-    // Wm = Ls^-1 Jb' G  (6 x 32; Jb = JF[:,0:6]) and pq = Wm' sv
-    LMH_FOR(i, NC + 1) {
-        double col[6];
-        if (i < NC) {
-            int foot = i / 16, gi = i % 16;
-            for (int r = 0; r < 6; ++r) {
-                double s = 0.0;
-                for (int k = 0; k < 6; ++k) s += w.JF[NQ * (6 * foot + k) + r] * K.Gf[16 * k + gi];
-                col[r] = s;
-            }
-        } else {
-            for (int r = 0; r < 6; ++r) col[r] = w.rhs[r];
-        }
-        for (int r = 0; r < 6; ++r) {
-            double s = col[r];
-            for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * col[m];
-            col[r] = s / Ls[7 * r];
-        }
-        if (i < NC) for (int r = 0; r < 6; ++r) w.u.s.Wm[NC * r + i] = col[r];
-        else for (int r = 0; r < 6; ++r) w.sv[r] = col[r];
-    }
-    cx.sync();
-    double* Q = w.u.s.Q;
-    const double* Wm = w.u.s.Wm;
-    LMH_FOR(it, NC * (NC + 1) / 2) {
-        int i = (int)((sqrt(8.0 * it + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= it) ++i;
-        while (i * (i + 1) / 2 > it) --i;
-        int j = it - i * (i + 1) / 2;     // j <= i ; store at the UPPER position (j,i)
-        double s = 0.0;
-        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * Wm[NC * r + j];
-        if (i / 16 == j / 16) s += K.wForce * K.GtG[16 * (i % 16) + (j % 16)];
-        if (i == j) { w.qdiag[i] = s + K.epsC; }
-        else Q[LDQ * j + i] = s;
-    }
-    LMH_FOR(i, NC) {
-        double s = 0.0;
-        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * w.sv[r];
-        w.pq[i] = s;
-        double x0 = w.cs[i];
-        w.free_mask[i] = x0 > 0.0 ? 1 : 0;
-        w.c[i] = x0 > 0.0 ? x0 : 0.0;
-    }
-    cx.sync();
-
-    // ---- primal active set on c >= 0
-    // start from the projection of the all-free solution: working set = the clipped coefficients
-    bool have_feasible = true;
+    int iters = 0, status = 0;
+    bool have_point = false, fallback = false;
     while (true) {
         ++iters;
-        // masked left-looking Cholesky of Q_FF in the lower triangle, forward substitution of pq fused
-        for (int k = 0; k < NC; ++k) {
-            const bool fk = w.free_mask[k] != 0;
-            LMH_FOR(i0, NC + 1 - k) {
-                int i = k + i0;   // i == NC : the rhs row
-                double s0 = 0.0;
-                if (fk) {
-                    if (i < NC) {
-                        if (w.free_mask[i]) {
-                            s0 = i == k ? w.qdiag[k] : Q[LDQ * k + i];
-                            const double* ri = Q + LDQ * i;
-                            const double* rk = Q + LDQ * k;
-                            double s1 = 0.0;
-                            int m = 0;
-                            for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
-                            if (m < k) s0 -= ri[m] * rk[m];
-                            s0 += s1;
+        // A = P_F + (eps/wF)(I - V'V), rhs row = V'u
+        LMH_FOR(it, 13 * 12) {
+            int i = it / 12, j = it % 12;
+            if (i < 12) {
+                if (j <= i) {
+                    double sv_ = 0.0;
+                    for (int r = 0; r < 6; ++r) sv_ += Vy[12 * r + i] * Vy[12 * r + j];
+                    double kt = (i == j ? 1.0 : 0.0) - sv_;
+                    double pij = 0.0;
+                    if (i / 6 == j / 6) {
+                        if (!have_point) pij = K.GGt[6 * (i % 6) + (j % 6)];
+                        else {
+                            const int foot = i / 6;
+                            const double* gi = K.Gf + 16 * (i % 6);
+                            const double* gj = K.Gf + 16 * (j % 6);
+                            for (int g = 0; g < 16; ++g) if (w.free_mask[16 * foot + g]) pij += gi[g] * gj[g];
                         }
-                    } else {
-                        s0 = w.pq[k];
-                        const double* rk = Q + LDQ * k;
-                        for (int m = 0; m < k; ++m) s0 -= w.zq[m] * rk[m];
                     }
+                    Ay[13 * i + j] = pij + (K.epsC / K.wForce) * kt;
                 }
-                if (i == k) w.piv[k] = fk ? s0 : 1.0;
-                else if (i < NC) Q[LDQ * i + k] = s0;
-                else w.zq[k] = s0;
+            } else {
+                double sb = 0.0;
+                for (int r = 0; r < 6; ++r) sb += Vy[12 * r + j] * uy[r];
+                Ay[13 * 12 + j] = sb;
             }
-            cx.sync();
-            double pv = w.piv[k];
-            double dk = sqrt(pv > 0.0 ? pv : 1e-300);
-            LMH_FOR(i0, NC + 1 - k) {
-                int i = k + i0;
-                if (i == k) w.ldiag[k] = dk;
-                else if (i < NC) Q[LDQ * i + k] = Q[LDQ * i + k] / dk;
-                else w.zq[k] = w.zq[k] / dk;
-            }
-            cx.sync();
-        }
-        // back substitution L' cs = zq (column oriented)
-        for (int k = NC - 1; k >= 0; --k) {
-            double xk = w.zq[k] / w.ldiag[k];
-            LMH_FOR(i, k + 1) {
-                if (i == k) w.cs[k] = w.free_mask[k] ? xk : 0.0;
-                else w.zq[i] -= Q[LDQ * k + i] * xk;
-            }
-            cx.sync();
-        }
-        // gradient on the working set: mu = Q cs - pq
-        LMH_FOR(i, NC) {
-            double s = -w.pq[i];
-            for (int j = 0; j < NC; ++j) {
-                double qij = i == j ? w.qdiag[i] : (i < j ? Q[LDQ * i + j] : Q[LDQ * j + i]);
-                s += qij * w.cs[j];
-            }
-            w.mu[i] = s;
         }
         cx.sync();
-        // decisions are taken redundantly by every thread from the shared vectors
-        double cmin = 0.0, pmax = 1.0;
+        double pmin = 1e300, pmaxv = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 0; k < 12; ++k) {
+            LMH_FOR(i0, 13 - k) {
+                int i = k + i0;
+                double* ri = Ay + 13 * i;
+                const double* rk = Ay + 13 * k;
+                double s0 = ri[k];
+                for (int m = 0; m < k; ++m) s0 -= ri[m] * rk[m];
+                ri[k] = s0;
+            }
+            cx.sync();
+            double pv = Ay[13 * k + k];
+            pmin = fmin(pmin, pv); pmaxv = fmax(pmaxv, pv);
+            double dk = sqrt(pv > 0.0 ? pv : 1e-300);
+            LMH_FOR(i0, 13 - k) {
+                int i = k + i0;
+                if (i == k) w.piv[k] = dk;
+                else Ay[13 * i + k] = Ay[13 * i + k] / dk;
+            }
+            cx.sync();
+        }
+        if (!(pmin > 1e-7 * pmaxv)) { fallback = true; break; }     // P_F lost rank: the wrench-space system is unreliable
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 11; k >= 0; --k) {        // L' y = z (row 12 of Ay), column oriented
+            double xk = Ay[13 * 12 + k] / w.piv[k];
+            cx.sync();
+            LMH_FOR(i, k + 1) {
+                if (i == k) Ay[13 * 12 + k] = xk;
+                else Ay[13 * 12 + i] -= Ay[13 * k + i] * xk;
+            }
+            cx.sync();
+        }
+        LMH_FOR(i, NC) {
+            int foot = i / 16, gi = i % 16;
+            double sc = 0.0;
+            for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * Ay[13 * 12 + 6 * foot + k];
+            w.mu[i] = sc;                              // g_i'y : coefficient if free, -multiplier/eps if not
+            w.cs[i] = w.free_mask[i] ? sc : 0.0;
+        }
+        cx.sync();
+        // decisions, taken redundantly by every thread from the shared vectors
+        double cmin = 0.0, cmax = 1.0;
         for (int i = 0; i < NC; ++i) {
             if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
-            pmax = fmax(pmax, fabs(w.pq[i]));
+            cmax = fmax(cmax, fabs(w.cs[i]));
         }
         bool done = false;
         int change = -1, to_free = 0;
         double alpha = 1.0;
-        if (!have_feasible) {
-            if (cmin >= 0.0) {
-                have_feasible = true;     // unconstrained minimiser is feasible: check multipliers (none active) -> optimal
-                done = true;
-                for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < -1e-12 * pmax) done = false;
-                if (!done) { double worst = 0.0; for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; } to_free = 1; }
-                alpha = 1.0;
-            } else {
-                // first iterate: project onto the orthant, working set = the clipped coefficients
-                have_feasible = true;
-                alpha = -1.0;             // marker: projection step
-            }
+        if (!have_point) {
+            have_point = true;
+            if (cmin >= 0.0) done = true;              // the all-free minimiser is feasible: optimal
+            else alpha = -1.0;                         // project onto the orthant; working set = the clipped coefficients
         } else if (cmin >= 0.0) {
-            double worst = -1e-12 * pmax;
-            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
+            double worst = 1e-10 * cmax;
+            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] > worst) { worst = w.mu[i]; change = i; }
             if (change < 0) done = true; else to_free = 1;
-            alpha = 1.0;
         } else {
             double best = 2.0;
             for (int i = 0; i < NC; ++i)
@@ -1016,7 +1104,6 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                     if (r < best) { best = r; change = i; }
                 }
             alpha = best < 1.0 ? best : 1.0;
-            to_free = 0;
         }
         cx.sync();
         LMH_FOR(i, NC) {
@@ -1038,7 +1125,8 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         if (done) break;
         if (iters >= K.qp_max_iter) { status = 1; break; }
     }
-    }
+    w.qp_fallback = fallback ? 1 : 0;
+    if (fallback) qp_cspace_fallback(cx, w, K, Ls, gscratch, iters, status);
     w.qp_iters = iters;
     w.qp_status = status;
     // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12) ; a = -La^-T (wv + Y' lam)
@@ -1053,7 +1141,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         double l[6];
         for (int r = 0; r < 6; ++r) {
             double s = w.rhs[r];
-            for (int k = 0; k < 12; ++k) s -= w.JF[NQ * k + r] * w.f12[k];
+            for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
             l[r] = s;
         }
         for (int r = 0; r < 6; ++r) { double s = l[r]; for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m]; l[r] = s / Ls[7 * r]; }
@@ -1087,7 +1175,10 @@ LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
         for (int k = 0; k < 6; ++k) s += w.M6[NQ * k + 6 + j] * w.a[k];
         int c = joint_chain(j), j0 = chain_joint0(c), n = chain_nact(c);
         for (int b = 0; b < n; ++b) s += w.Hc[36 * c + 6 * (j - j0) + b] * w.a[6 + j0 + b];
-        for (int k = 0; k < 12; ++k) s -= w.JF[NQ * k + 6 + j] * w.f12[k];
+        if (j < 12) {
+            const int f = j / 6;
+            for (int k = 0; k < 6; ++k) s -= w.JFc[72 * f + 12 * k + 6 + (j - 6 * f)] * w.f12[6 * f + k];
+        }
         w.tau[j] = s;
     }
     LMH_FOR(i, NQ) {
@@ -1097,7 +1188,6 @@ LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
             x = rot_row(w.R0, i, w.a + 3) + cross_k(w.p0, ra, i);
         } else if (i < 6) x = rot_row(w.R0, i - 3, w.a);
         else x = w.a[i];
-        w.qpp[i] = x;
         w.xdot[NQ + i] = x;
         double qd;
         if (i < 3) qd = w.v[i] + cross_k(w.v + 3, w.q, i);       // v + w x p
@@ -1131,9 +1221,9 @@ LMH_HDN void dump_stage(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
         int i = it / NQ, j = it % NQ;
         d->M[it] = i < 6 ? w.M6[NQ * i + j] : j < 6 ? w.M6[NQ * j + i] : hjoint(w, i - 6, j - 6);
     }
-    LMH_FOR(i, NQ) { d->C[i] = w.C[i]; d->Cg[i] = w.Cg[i]; d->qppRef[i] = w.qppRef[i]; d->a[i] = w.a[i]; d->qpp[i] = w.qpp[i]; }
+    LMH_FOR(i, NQ) { d->C[i] = w.C[i]; d->Cg[i] = w.Cg[i]; d->qppRef[i] = w.qppRef[i]; d->a[i] = w.a[i]; d->qpp[i] = w.xdot[NQ + i]; }
     LMH_FOR(i, 6 * NQ) d->AG[i] = w.AG[i];
-    LMH_FOR(i, 12 * NQ) d->JFeet[i] = w.JF[i];
+    LMH_FOR(i, 12 * NQ) d->JFeet[i] = jf_full(w, i / NQ, i % NQ);
     LMH_FOR(i, 2 * NQ) d->xdot[i] = w.xdot[i];
     LMH_FOR(i, NC) d->c[i] = w.c[i];
     LMH_FOR(i, NJ) d->tau[i] = w.tau[i];
@@ -1154,7 +1244,8 @@ LMH_HDN void dump_stage(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
 // One dynamics(x,t) evaluation.  On entry w.q, w.v, w.vh, w.t are set; on exit w.xdot, w.tau, w.f12,
 // w.qpp (and every intermediate) are valid and w.vh has been advanced to this stage's velocity.
 template <class Cx>
-LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, LmhStageDump* dump = nullptr) {
+LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, double* gscratch,
+                        LmhStageDump* dump = nullptr) {
     fk_phase(cx, w, K);
     base_twist_phase(cx, w);
     rnea_phase(cx, w, K);
@@ -1163,7 +1254,7 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
     mpc_pd_phase(cx, w, K, P, plan_id);
     assemble_phase(cx, w, K);
     if (dump) dump_assembly(cx, w, dump);
-    qp_phase(cx, w, K);
+    qp_phase(cx, w, K, gscratch);
     output_phase(cx, w);
     if (dump) dump_stage(cx, w, dump);
     LMH_FOR(i, NQ) w.vh[i] = w.v[i];     // Robot::updateVelocityState (Robot.cpp:271-274)
@@ -1183,17 +1274,17 @@ LMH_HD double mul_then_add(double a, double b, double c) {
 // Running statistics of one environment (kept by thread 0 of the group).
 struct StatsAcc {
     double max_tau, max_err, max_qpp;
-    int32_t qp_iters, qp_fail, steps, alive;
+    int32_t qp_iters, qp_fail, steps, alive, qp_fallback;
 };
 
 // One RK4 step (rk4.hpp:5-18) + Clock::step (Clock.hpp:11).  x: [60] state in shared memory, kacc:
 // [60] scratch, t: the env clock (same value in every thread of the group).
 template <class Cx>
 LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t, const Consts& K, const Plan& P,
-                      int plan_id, LmhStepLog* log, StatsAcc* st) {
+                      int plan_id, double* gscratch, LmhStepLog* log, StatsAcc* st) {
     const double dt = K.dt;
     const double half = 0.5 * dt;
-    int iters = 0, fails = 0;
+    int iters = 0, fails = 0, nfall = 0;
     for (int stage = 0; stage < 4; ++stage) {
         const double cstage = stage == 0 ? 0.0 : stage == 3 ? dt : half;
         LMH_FOR(i, 2 * NQ) {
@@ -1202,13 +1293,14 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         }
         LMH_FOR(i, 1) w.t = stage == 0 ? t : mul_then_add(t, stage == 3 ? 1.0 : 0.5, dt);
         cx.sync();
-        stage_eval(cx, w, K, P, plan_id);
+        stage_eval(cx, w, K, P, plan_id, gscratch);
         LMH_FOR(i, 2 * NQ) {
             double k = w.xdot[i];
             kacc[i] = stage == 0 ? k : stage == 3 ? kacc[i] + k : mul_then_add(kacc[i], 2.0, k);
         }
         iters += w.qp_iters;
         fails += w.qp_status != 0;
+        nfall += w.qp_fallback;
         if (log) {
             LMH_FOR(i, 1) log->k_index[stage] = w.k_index;
             if (stage == 0) { LMH_FOR(i, NJ) log->tau_k1[i] = w.tau[i]; }
@@ -1217,7 +1309,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
             LMH_FOR(i, 1) {
                 double m = st->max_tau, a = st->max_qpp;
                 for (int j = 0; j < NJ; ++j) m = fmax(m, fabs(w.tau[j]));
-                for (int j = 0; j < NQ; ++j) a = fmax(a, fabs(w.qpp[j]));
+                for (int j = 0; j < NQ; ++j) a = fmax(a, fabs(w.xdot[NQ + j]));
                 st->max_tau = m; st->max_qpp = a;
             }
         }
@@ -1238,7 +1330,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
             double ex = w.com[0] - P.zmp_x[(size_t)plan_id * P.zmp_len + k0];
             double ey = w.com[1] - P.zmp_y[(size_t)plan_id * P.zmp_len + k0];
             st->max_err = fmax(st->max_err, sqrt(ex * ex + ey * ey));
-            st->qp_iters += iters; st->qp_fail += fails; st->steps += 1;
+            st->qp_iters += iters; st->qp_fail += fails; st->steps += 1; st->qp_fallback += nfall;
         }
     }
     cx.sync();

@@ -162,7 +162,7 @@ private:
         for (int i = 0; i < 28; ++i) {
             const NaoLinkRow& L = kNaoLinks[i];
             double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            if (i < NF) for (int k = 0; k < 9; ++k) R[k] = w.u.m.Tw[12 * i + k];
+            if (i < NF) for (int k = 0; k < 9; ++k) R[k] = w.u.m.p.Tw[12 * i + k];
             double cj[3], RtI[9], Ij[9];
             for (int r3 = 0; r3 < 3; ++r3) cj[r3] = R[r3] * L.c[0] + R[3 + r3] * L.c[1] + R[6 + r3] * L.c[2];
             for (int r3 = 0; r3 < 3; ++r3) for (int c = 0; c < 3; ++c) RtI[3 * r3 + c] = R[r3] * L.I[c] + R[3 + r3] * L.I[3 + c] + R[6 + r3] * L.I[6 + c];
@@ -325,7 +325,7 @@ private:
                         double row[NQ];
                         for (int c = 0; c < NQ; ++c) {
                             int src_c = c < 3 ? c + 3 : c < 6 ? c - 3 : c;
-                            row[c] = w.JF[NQ * (6 * s + (half == 0 ? 3 + r : r)) + src_c];
+                            row[c] = jf_full(w, 6 * s + (half == 0 ? 3 + r : r), src_c);
                         }
                         double att[3] = {row[3], row[4], row[5]};
                         for (int c = 0; c < 3; ++c) row[3 + c] = att[0] * Omi[c] + att[1] * Omi[3 + c] + att[2] * Omi[6 + c];
@@ -341,7 +341,9 @@ private:
             for (int k = 0; k < 3; ++k) J[(size_t)(24 + k) * NQ + 3 + k] = 1.0;
             // CoM Jacobian (invKinematics.cpp:208-245)
             {
-                const double* Tw = w.u.m.Tw;
+                Ctx<1> cx1{0, 0};
+                fk_phase(cx1, w, K);       // the world transforms were overlaid by the dynamics phases: redo the kinematics
+                const double* Tw = w.u.m.p.Tw;
                 double Jc[3 * NQ];
                 for (int k = 0; k < 3 * NQ; ++k) Jc[k] = 0.0;
                 for (int i = 0; i < NF; ++i) {

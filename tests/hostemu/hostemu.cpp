@@ -9,6 +9,7 @@ using namespace lmh;
 struct Emu {
     HostModel hm;
     Plan plan;
+    std::vector<double> scratch = std::vector<double>(QP_SCRATCH_DOUBLES);
     explicit Emu(const Scenario& s) : hm(s) {
         plan.zmp_x = hm.zmp_x.data();
         plan.zmp_y = hm.zmp_y.data();
@@ -46,7 +47,7 @@ void emu_stage(void* p, const double* x60, double* vheld30, double t, LmhStageDu
     for (int i = 0; i < NQ; ++i) { w.q[i] = x60[i]; w.v[i] = x60[NQ + i]; w.vh[i] = vheld30[i]; }
     w.t = t;
     Ctx<1> cx{0, 0};
-    stage_eval(cx, w, e->hm.K, e->plan, 0, dump);
+    stage_eval(cx, w, e->hm.K, e->plan, 0, e->scratch.data(), dump);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
 }
 void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps, LmhStepLog* logs, LmhStats* stats) {
@@ -54,13 +55,13 @@ void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps,
     EnvWS& w = e->hm.workspace();
     for (int i = 0; i < NQ; ++i) w.vh[i] = vheld30[i];
     double kacc[60];
-    StatsAcc st{0, 0, 0, 0, 0, 0, 1};
+    StatsAcc st{0, 0, 0, 0, 0, 0, 1, 0};
     Ctx<1> cx{0, 0};
-    for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, logs ? logs + s : nullptr, &st);
+    for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, e->scratch.data(), logs ? logs + s : nullptr, &st);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
     if (stats) {
         stats->max_abs_tau = st.max_tau; stats->max_com_err = st.max_err; stats->max_abs_qpp = st.max_qpp;
-        stats->qp_iters = st.qp_iters; stats->qp_fail = st.qp_fail; stats->steps = st.steps; stats->alive = st.alive;
+        stats->qp_iters = st.qp_iters; stats->qp_fail = st.qp_fail; stats->steps = st.steps; stats->alive = st.alive; stats->qp_fallback = st.qp_fallback; stats->pad = 0;
     }
 }
 }

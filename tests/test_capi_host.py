@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     n_dbl = sum(int(n) for n in re.findall(r"\w+\[(\d+)\]", body.split("int32_t")[0]))
     assert api.STAGE_DTYPE.itemsize == 8 * n_dbl + 16
     assert api.STEPLOG_DTYPE.itemsize == 8 * (3 + 3 + 3 + 24) + 4 * 6
-    assert api.STATS_DTYPE.itemsize == 8 * 3 + 4 * 4
+    assert api.STATS_DTYPE.itemsize == 8 * 3 + 4 * 6
     assert C.sizeof(api.LmhConfig) == 8 * (3 + 3 + 6 + 6 + 3) + 4 * 4
 
 
