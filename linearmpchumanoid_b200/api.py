@@ -49,7 +49,7 @@ SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", 
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... in-tree (cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "lmh_capi.cu")
-    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("lmh_model.cuh", "lmh_setup.hpp", "lmh_nao_table.inc")]
+    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("lmh_model.cuh", "lmh_warp.cuh", "lmh_setup.hpp", "lmh_nao_table.inc")]
     deps.append(os.path.join(_ROOT, "include", "lmh_capi.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH

@@ -130,6 +130,11 @@ struct EnvWS {
                     double Fb[2][NJ * 6];
                 } crba;
                 double Xn[2][2 * 18];  // running sole_X_j as (E, B) for both feet, double buffered
+                struct {               // exchange buffers of the one-warp-per-env versions (lmh_warp.cuh)
+                    double vbuf[2][32], abuf[2][32], hbuf[32], contrib[32], col2[32], accs[12];
+                    double frc[NF * 6];
+                    double Ybuf[NCH * 36], Ybuf2[NCH * 36];
+                } wr;
             } p;
         } m;
         struct {                       // assembly + QP phase
@@ -1241,6 +1246,10 @@ LMH_HDN void dump_stage(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
     cx.sync();
 }
 
+}  // namespace lmh
+#include "lmh_warp.cuh"
+namespace lmh {
+
 // One dynamics(x,t) evaluation.  On entry w.q, w.v, w.vh, w.t are set; on exit w.xdot, w.tau, w.f12,
 // w.qpp (and every intermediate) are valid and w.vh has been advanced to this stage's velocity.
 template <class Cx>
@@ -1248,8 +1257,17 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
                         LmhStageDump* dump = nullptr) {
     fk_phase(cx, w, K);
     base_twist_phase(cx, w);
-    rnea_phase(cx, w, K);
-    crba_phase(cx, w, K);
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) {
+        const LaneRole L = lane_role(cx.tid);
+        rnea_warp(w, K, L, cx.tid);
+        crba_warp(w, K, L, cx.tid);
+    } else
+#endif
+    {
+        rnea_phase(cx, w, K);
+        crba_phase(cx, w, K);
+    }
     centroidal_jacobian_phase(cx, w, K);
     mpc_pd_phase(cx, w, K, P, plan_id);
     assemble_phase(cx, w, K);

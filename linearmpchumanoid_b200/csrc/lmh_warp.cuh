@@ -1,0 +1,275 @@
+// lmh_warp.cuh -- one-warp-per-environment (NT = 32) device versions of the tree recursions (RNEA bias
+// forces, CRBA).  Same inputs and outputs in the workspace as rnea_phase / crba_phase of lmh_model.cuh (which
+// stay the reference implementation: host-testable, used for every other group size, and the thing these are
+// checked against on the GPU), but organised around fixed lane roles instead of a parallel-for over items:
+//
+//   lane = 6*c + r :  chain c (0 right leg, 1 left leg, 2 right arm, 3 left arm, 4 head), spatial component /
+//                     matrix row r.  Lanes 30, 31 idle in the chain phases.
+//
+// A lane keeps "its" row of the composite inertia and "its" joint's force vector in registers across tree
+// levels; what the other five lanes of a chain need travels through a few shared-memory words with one
+// __syncwarp per exchange.  No index arithmetic survives in the inner loops.
+#pragma once
+#if defined(__CUDACC__)
+
+namespace lmh {
+
+struct LaneRole {
+    int c, r;          // chain, component
+    int first, len, nact, j0;
+    bool on;           // lane < 30
+};
+
+__device__ __forceinline__ LaneRole lane_role(int lane) {
+    LaneRole L;
+    L.on = lane < 30;
+    L.c = L.on ? lane / 6 : 4;
+    L.r = L.on ? lane % 6 : 0;
+    L.first = chain_first(L.c);
+    L.len = chain_len(L.c);
+    L.nact = chain_nact(L.c);
+    L.j0 = chain_joint0(L.c);
+    return L;
+}
+
+__device__ __forceinline__ void load6(const double* p, double* o) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = p[k];
+}
+__device__ __forceinline__ void load12(const double* p, double* o) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) o[k] = p[k];
+}
+// row r of X m, X = [[E,0],[-E p^,E]], E = R'
+__device__ __forceinline__ double xm_row(const double* Rp, const double* m, int r) {
+    if (r < 3) return Rp[r] * m[0] + Rp[3 + r] * m[1] + Rp[6 + r] * m[2];
+    const int k = r - 3;
+    const double u0 = m[3] + (m[1] * Rp[11] - m[2] * Rp[10]);
+    const double u1 = m[4] + (m[2] * Rp[9] - m[0] * Rp[11]);
+    const double u2 = m[5] + (m[0] * Rp[10] - m[1] * Rp[9]);
+    return Rp[k] * u0 + Rp[3 + k] * u1 + Rp[6 + k] * u2;
+}
+// all six components of X' f : [R n + p x (R f); R f]
+__device__ __forceinline__ void xf_all(const double* Rp, const double* f, double* o) {
+    const double r0 = Rp[0] * f[3] + Rp[1] * f[4] + Rp[2] * f[5];
+    const double r1 = Rp[3] * f[3] + Rp[4] * f[4] + Rp[5] * f[5];
+    const double r2 = Rp[6] * f[3] + Rp[7] * f[4] + Rp[8] * f[5];
+    o[0] = Rp[0] * f[0] + Rp[1] * f[1] + Rp[2] * f[2] + (Rp[10] * r2 - Rp[11] * r1);
+    o[1] = Rp[3] * f[0] + Rp[4] * f[1] + Rp[5] * f[2] + (Rp[11] * r0 - Rp[9] * r2);
+    o[2] = Rp[6] * f[0] + Rp[7] * f[1] + Rp[8] * f[2] + (Rp[9] * r1 - Rp[10] * r0);
+    o[3] = r0; o[4] = r1; o[5] = r2;
+}
+__device__ __forceinline__ double xf_row(const double* Rp, const double* f, int r) {
+    double o[6];
+    xf_all(Rp, f, o);
+    return r == 0 ? o[0] : r == 1 ? o[1] : r == 2 ? o[2] : r == 3 ? o[3] : r == 4 ? o[4] : o[5];
+}
+__device__ __forceinline__ double cross3(const double* a, const double* b, int k) {
+    return k == 0 ? a[1] * b[2] - a[2] * b[1] : k == 1 ? a[2] * b[0] - a[0] * b[2] : a[0] * b[1] - a[1] * b[0];
+}
+
+// ---- RNEA with zero base acceleration on the held velocity (Dynamics.cpp:29-60,124-200) -> Cg, Jpqp
+__device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
+    auto& S = w.u.m.p.wr;
+    const double* Xl = w.u.m.Xl;
+    const int c6 = 6 * L.c, r = L.r;
+    // base: f0 = v0 x* (I0 v0), acc0 = 0
+    if (lane < 6) {
+        double v0[6];
+        load6(w.vhb6, v0);
+        const double* I = K.Isp + 6 * lane;
+        S.hbuf[lane] = I[0] * v0[0] + I[1] * v0[1] + I[2] * v0[2] + I[3] * v0[3] + I[4] * v0[4] + I[5] * v0[5];
+    }
+    __syncwarp();
+    if (lane < 6) {
+        double v0[6], h[6];
+        load6(w.vhb6, v0);
+        load6(S.hbuf, h);
+        S.frc[lane] = lane < 3 ? cross3(v0, h, lane) + cross3(v0 + 3, h + 3, lane) : cross3(v0, h + 3, lane - 3);
+    }
+    int cur = 0;
+#pragma unroll 1
+    for (int d = 1; d <= MAXDEPTH; ++d) {
+        const bool act = L.on && d <= L.len;
+        const int i = L.first + d - 1;
+        const bool joint = act && d <= L.nact;
+        double Rp[12], Irow[6], nv[6];
+        double qd = 0.0;
+        if (act) {
+            double pv[6];
+            load12(Xl + 12 * i, Rp);
+            if (d == 1) load6(w.vhb6, pv); else load6(S.vbuf[cur] + c6, pv);
+            double x = xm_row(Rp, pv, r);
+            if (joint) { qd = w.vh[6 + L.j0 + d - 1]; if (r == 2) x += qd; }
+            S.vbuf[cur ^ 1][c6 + r] = x;
+        }
+        __syncwarp();
+        if (act) {
+            double pa[6];
+            load6(S.vbuf[cur ^ 1] + c6, nv);
+            double x = 0.0;
+            if (d > 1) { load6(S.abuf[cur] + c6, pa); x = xm_row(Rp, pa, r); }
+            if (joint) {
+                const double col = r == 0 ? nv[1] : r == 1 ? -nv[0] : r == 3 ? nv[4] : r == 4 ? -nv[3] : 0.0;
+                x += col * qd;
+                load6(K.Isp + 36 * i + 6 * r, Irow);
+                S.hbuf[c6 + r] = Irow[0] * nv[0] + Irow[1] * nv[1] + Irow[2] * nv[2] + Irow[3] * nv[3] + Irow[4] * nv[4] + Irow[5] * nv[5];
+            }
+            S.abuf[cur ^ 1][c6 + r] = x;
+            if (d == 7) S.accs[c6 + r] = x;          // sole frames (legs only): spatial acceleration for Jdot*qdot
+        }
+        __syncwarp();
+        if (joint) {
+            double na[6], h[6];
+            load6(S.abuf[cur ^ 1] + c6, na);
+            load6(S.hbuf + c6, h);
+            double x = Irow[0] * na[0] + Irow[1] * na[1] + Irow[2] * na[2] + Irow[3] * na[3] + Irow[4] * na[4] + Irow[5] * na[5];
+            x += r < 3 ? cross3(nv, h, r) + cross3(nv + 3, h + 3, r) : cross3(nv, h + 3, r - 3);
+            S.frc[6 * i + r] = x;
+        }
+        cur ^= 1;
+    }
+    __syncwarp();
+    // backward pass: deepest actuated level first
+#pragma unroll 1
+    for (int d = MAXDEPTH - 1; d >= 2; --d) {
+        if (L.on && d <= L.nact) {
+            const int i = L.first + d - 1;
+            double Rp[12], f[6];
+            load12(Xl + 12 * i, Rp);
+            load6(S.frc + 6 * i, f);
+            S.frc[6 * (i - 1) + r] += xf_row(Rp, f, r);
+        }
+        __syncwarp();
+    }
+    if (L.on) {
+        double Rp[12], f[6];
+        load12(Xl + 12 * L.first, Rp);
+        load6(S.frc + 6 * L.first, f);
+        S.contrib[c6 + r] = xf_row(Rp, f, r);
+        if (r == 2)
+            for (int d = 1; d <= L.nact; ++d) w.Cg[6 + L.j0 + d - 1] = S.frc[6 * (L.first + d - 1) + 2];
+    }
+    __syncwarp();
+    if (lane < 6) {
+        double s = S.frc[lane];
+        for (int c = NCH - 1; c >= 0; --c) s += S.contrib[6 * c + lane];
+        w.Cg[lane] = s;
+    }
+    if (lane >= 6 && lane < 18) {       // Jpqp = world-rotated sole accelerations
+        const int it = lane - 6, s = it / 6, k = it % 6;
+        const double* ai = S.accs + 6 * s + (k < 3 ? 0 : 3);
+        w.Jpqp[it] = rot_row(w.Rs[s], k % 3, ai);
+    }
+    __syncwarp();
+}
+
+// ---- CRBA (Dynamics.cpp:62-101) -> M6 = [Ic0 | F2], Hc
+__device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
+    auto& S = w.u.m.p.wr;
+    const double* Xl = w.u.m.Xl;
+    const int c6 = 6 * L.c, r = L.r;
+    double icin[6] = {0, 0, 0, 0, 0, 0};     // row r of the composite inertia arriving from the level below
+    double F[6] = {0, 0, 0, 0, 0, 0};        // force vector of joint (c, r), expressed in the frame reached so far
+    if (lane < 30) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w.Hc[36 * L.c + 6 * r + k] = 0.0;
+    }
+#pragma unroll 1
+    for (int d = MAXDEPTH - 1; d >= 1; --d) {
+        const bool act = L.on && d <= L.nact;
+        const int i = L.first + d - 1;
+        double Rp[12];
+        if (act) {
+            load12(Xl + 12 * i, Rp);
+            double ic[6];
+            load6(K.Isp + 36 * i + 6 * r, ic);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ic[k] += icin[k];
+            S.col2[c6 + r] = ic[2];
+            // B = -E p^ (3x3), E = R'
+            double y[6];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                // E[k][cc] = R[cc][k] = Rp[3*cc + k]
+                const double e0 = Rp[3 * cc], e1 = Rp[3 * cc + 1], e2 = Rp[3 * cc + 2];
+                y[3 + cc] = ic[3] * e0 + ic[4] * e1 + ic[5] * e2;
+                y[cc] = ic[0] * e0 + ic[1] * e1 + ic[2] * e2;
+            }
+            // + ic[3:6] . B[:, cc],  B[k][cc] = -(E p^)[k][cc] ; (E p^)[k][:] = (E[k][1] p2 - E[k][2] p1, -E[k][0] p2 + E[k][2] p0, E[k][0] p1 - E[k][1] p0)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double ek0 = Rp[k], ek1 = Rp[3 + k], ek2 = Rp[6 + k];     // E[k][0..2]
+                const double b0 = -(ek1 * Rp[11] - ek2 * Rp[10]);
+                const double b1 = -(-ek0 * Rp[11] + ek2 * Rp[9]);
+                const double b2 = -(ek0 * Rp[10] - ek1 * Rp[9]);
+                y[0] += ic[3 + k] * b0; y[1] += ic[3 + k] * b1; y[2] += ic[3 + k] * b2;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) S.Ybuf[36 * L.c + 6 * r + k] = y[k];
+            if (r == 2) w.Hc[36 * L.c + 7 * (d - 1)] = ic[2];
+        }
+        __syncwarp();
+        if (act) {
+            // this lane's joint: pick up the new vector at its own depth, then cross frame i towards the root
+            if (r == d - 1) load6(S.col2 + c6, F);
+            if (r >= d - 1 && r < L.nact) {
+                double o[6];
+                xf_all(Rp, F, o);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) F[k] = o[k];
+                if (d > 1) {
+                    w.Hc[36 * L.c + 6 * (d - 2) + r] = F[2];
+                    w.Hc[36 * L.c + 6 * r + (d - 2)] = F[2];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w.M6[NQ * k + 6 + L.j0 + r] = F[k];
+                }
+            }
+            // row r of X' Y : sum_k X[k][r] Y[k][:]
+            double out[6] = {0, 0, 0, 0, 0, 0};
+            const double* Yc = S.Ybuf + 36 * L.c;
+            if (r < 3) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {           // X[k][r] = E[k][r] = R[r][k]
+                    const double x = Rp[3 * r + k];
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) out[cc] += x * Yc[6 * k + cc];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {           // X[3+k][r] = B[k][r]
+                    const double ek0 = Rp[k], ek1 = Rp[3 + k], ek2 = Rp[6 + k];
+                    const double x = r == 0 ? -(ek1 * Rp[11] - ek2 * Rp[10]) : r == 1 ? -(-ek0 * Rp[11] + ek2 * Rp[9]) : -(ek0 * Rp[10] - ek1 * Rp[9]);
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) out[cc] += x * Yc[6 * (3 + k) + cc];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {           // X[3+k][r] = E[k][r-3] = R[r-3][k]
+                    const double x = Rp[3 * (r - 3) + k];
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) out[cc] += x * Yc[6 * (3 + k) + cc];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) icin[k] = out[k];
+            if (d == 1) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) S.Ybuf2[36 * L.c + 6 * r + k] = out[k];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 6) {       // Ic0 = I0 + sum over the five chains
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+            double s = K.Isp[6 * lane + cc];
+            for (int c = NCH - 1; c >= 0; --c) s += S.Ybuf2[36 * c + 6 * lane + cc];
+            w.M6[NQ * lane + cc] = s;
+        }
+    }
+    __syncwarp();
+}
+
+}  // namespace lmh
+#endif

@@ -182,7 +182,9 @@ def test_thread_geometries_agree():
         b.set_pushes(step, dv)
         b.step(20)
         xs.append(b.get_state()[0])
-    assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[0], xs[2])
+    # 64 and 128 threads run the same generic code; one warp per env runs the lane-role versions of the tree
+    # recursions (lmh_warp.cuh): same results up to summation order
+    assert np.array_equal(xs[1], xs[2]) and np.abs(xs[0] - xs[1]).max() < 1e-10
 
 
 def test_plans_and_edge_cases():
