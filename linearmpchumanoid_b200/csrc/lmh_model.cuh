@@ -43,6 +43,9 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+constexpr int ND1 = 18;     // base + both legs: the block of H_a that the sole Jacobians couple
+constexpr int LD1 = 19;
+constexpr int NYR = 10;     // right-hand-side rows carried through the factorisation
 constexpr int QP_SCRATCH_DOUBLES = 6 * NC + NC * LDQ + 4 * NC;   // per-env global scratch of the rare c-space fallback
 
 // chain c: frames chain_first[c] .. chain_first[c]+chain_len[c]-1, depth 1..chain_len[c]
@@ -112,7 +115,7 @@ struct EnvWS {
     double qppRef[NQ], hGpRef[6], footAccRef[12];
     double ga[NQ], a[NQ], f12[12], tau[NJ], xdot[2 * NQ];
     double Sa[36], rhs[6], sv[6], lam[6];
-    double c[NC], cs[NC], mu[NC], piv[NC], ladiag[NQ];
+    double c[NC], cs[NC], mu[NC], piv[NC], ladiag[ND1];
     double red[32];                // reduction scratch
     int32_t free_mask[NC];
     int32_t k_index, qp_iters, qp_status, qp_fallback;
@@ -138,8 +141,10 @@ struct EnvWS {
             } p;
         } m;
         struct {                       // assembly + QP phase
-            double Ha[NQ * LDM];       // H_a, then its Cholesky factor (lower)
-            double Y[7 * NQ];          // rows 0..5: (La^-1 M6')', row 6: (La^-1 ga)'
+            double L1[ND1 * LD1];      // D1 = Wj + wFoot J'J on base+legs (18 x 18), then its Cholesky factor (lower)
+            double Yt[NYR * NQ];       // rows M6[0..5], ga, U[0..2] (U = sqrt(wCoML) AG[3..5]); cols 0..17: L1^-1 applied,
+                                       // cols 18..29: scaled by 1/sqrt(wJoints)
+            double Gm[NYR * NYR];      // Gram matrix Yt Yt'
             double Vy[6 * 12];         // Lz^-1 Jb'
             double Ay[13 * 13];        // wrench-space system: lower triangle factorised in place, row 12 = rhs / y
             double uy[6];              // Lz^-1 rhs
@@ -703,33 +708,9 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
     cx.sync();
 }
 
-// ================================================================================================
-// Phase 6: QP data.  H_a = AG' Wc AG + Wj + JF' Wf JF, g_a (controller.cpp:94-132).  Overwrites
-// the model scratch (union), so everything it needs was copied to the persistent part.
+// linear term of the QP (controller.cpp:125-132)
 template <class Cx>
-LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
-    double* Ha = w.u.s.Ha;
-    LMH_FOR(it, NQ * (NQ + 1) / 2) {
-        // unrank the lower-triangular index
-        int i = (int)((sqrt(8.0 * it + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= it) ++i;
-        while (i * (i + 1) / 2 > it) --i;
-        int j = it - i * (i + 1) / 2;
-        double s = 0.0;
-        for (int k = 0; k < 3; ++k) s += K.wCoMK * w.AG[NQ * k + i] * w.AG[NQ * k + j];
-        for (int k = 3; k < 6; ++k) s += K.wCoML * w.AG[NQ * k + i] * w.AG[NQ * k + j];
-        double sj = 0.0;
-        for (int f = 0; f < 2; ++f) {
-            int ci = jf_col(f, i), cj = jf_col(f, j);
-            if (ci >= 0 && cj >= 0) {
-                const double* Jf = w.JFc + 72 * f;
-                for (int k = 0; k < 6; ++k) sj += Jf[12 * k + ci] * Jf[12 * k + cj];
-            }
-        }
-        s += K.wFoot * sj;
-        if (i == j) s += i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
-        Ha[LDM * i + j] = s;
-    }
+LMH_HDN void assemble_ga_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     LMH_FOR(i, NQ) {
         double s = 0.0;
         for (int k = 0; k < 6; ++k) s += (k < 3 ? K.wCoMK : K.wCoML) * w.AG[NQ * k + i] * (w.AGpqp[k] - w.hGpRef[k]);
@@ -742,6 +723,54 @@ LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         double wj = i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
         w.ga[i] = s - wj * w.qppRef[i] + K.wFoot * sj;
     }
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 6: QP data (controller.cpp:94-132).  H_a = Wj + JF' Wf JF + AG' Wc AG is never formed: with the angular
+// momentum weight at zero (controller.hpp:119) the centroidal term is U'U with U = sqrt(wCoML) AG[3..5] (rank 3),
+// and the rest, D = Wj + wFoot JF'JF, only couples the 18 base+leg coordinates (D1); on the 12 arm/head joints it
+// is the constant wJoints.  Everything that needs H_a^-1 goes through
+//     H_a^-1 = D^-1 - D^-1 U' (I3 + U D^-1 U')^-1 U D^-1                       (Woodbury)
+// so only the 18 x 18 block is factorised.  Overwrites the model scratch (union).
+LMH_HD double ha_entry(const EnvWS& w, const Consts& K, int i, int j) {      // H_a(i,j), for dumps and tests
+    double s = 0.0;
+    for (int k = 0; k < 3; ++k) s += K.wCoMK * w.AG[NQ * k + i] * w.AG[NQ * k + j];
+    for (int k = 3; k < 6; ++k) s += K.wCoML * w.AG[NQ * k + i] * w.AG[NQ * k + j];
+    double sj = 0.0;
+    for (int f = 0; f < 2; ++f) {
+        int ci = jf_col(f, i), cj = jf_col(f, j);
+        if (ci >= 0 && cj >= 0)
+            for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + ci] * w.JFc[72 * f + 12 * k + cj];
+    }
+    s += K.wFoot * sj;
+    if (i == j) s += i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
+    return s;
+}
+// entry (r, j) of the right-hand-side block [M6; ga'; U] before the factorisation
+LMH_HD double yt_entry(const EnvWS& w, const Consts& K, int r, int j) {
+    double v = r < 6 ? w.M6[NQ * r + j] : r == 6 ? w.ga[j] : sqrt(K.wCoML) * w.AG[NQ * (r - 4) + j];
+    return j < ND1 ? v : v / sqrt(K.wJoints);
+}
+template <class Cx>
+LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
+    assemble_ga_phase(cx, w, K);        // (ends with a sync; the union is free from here on)
+    double* L1 = w.u.s.L1;
+    LMH_FOR(it, ND1 * ND1) {
+        int i = it / ND1, j = it % ND1;
+        if (j <= i) {
+            double sj = 0.0;
+            for (int f = 0; f < 2; ++f) {
+                int ci = jf_col(f, i), cj = jf_col(f, j);
+                if (ci >= 0 && cj >= 0)
+                    for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + ci] * w.JFc[72 * f + 12 * k + cj];
+            }
+            double v = K.wFoot * sj;
+            if (i == j) v += i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
+            L1[LD1 * i + j] = v;
+        }
+    }
+    LMH_FOR(it, NYR * NQ) w.u.s.Yt[it] = yt_entry(w, K, it / NQ, it % NQ);
     cx.sync();
 }
 
@@ -899,6 +928,11 @@ LMH_HDN void qp_cspace_fallback(const Cx& cx, EnvWS& w, const Consts& K, const d
     }
 }
 
+#if defined(__CUDACC__)
+__device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane);
+__device__ void qp_backsolve_warp(EnvWS& w, int lane);
+#endif
+
 // ================================================================================================
 // Phase 7: the WBC QP (controller.cpp:388-479) in reduced form.
 //   variables a (30), c (32);  f12 = G c eliminated (controller.cpp:156-294 rows 6..17)
@@ -907,48 +941,69 @@ LMH_HDN void qp_cspace_fallback(const Cx& cx, EnvWS& w, const Consts& K, const d
 // leaving   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I,
 // which a primal active-set method solves exactly (masked Cholesky of Q per working set).
 template <class Cx>
-LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch) {
-    double* Ha = w.u.s.Ha;
-    double* Y = w.u.s.Y;
-    // rows 30..36 of the augmented matrix: M6 and ga' ; left-looking Cholesky carries them along so
-    // that they come out as (La^-1 M6')' and (La^-1 ga)'.
-    LMH_FOR(it, 7 * NQ) Y[it] = it < 6 * NQ ? w.M6[it] : w.ga[it - 6 * NQ];
-    cx.sync();
-    for (int k = 0; k < NQ; ++k) {
-        // column k: s_i = A[i][k] - sum_{m<k} L[i][m] L[k][m]   (element (i,k) is touched by item i only)
-        LMH_FOR(i0, NQ + 7 - k) {
-            int i = k + i0;
-            double* ri = i < NQ ? Ha + LDM * i : Y + NQ * (i - NQ);
-            const double* rk = Ha + LDM * k;
-            double s0 = ri[k], s1 = 0.0;
-            int m = 0;
-            for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
-            if (m < k) s0 -= ri[m] * rk[m];
-            ri[k] = s0 + s1;
-        }
-        cx.sync();
-        double dk = sqrt(Ha[LDM * k + k]);     // nobody writes the pivot in the next loop
-        LMH_FOR(i0, NQ + 7 - k) {
-            int i = k + i0;
-            if (i == k) w.ladiag[k] = dk;
-            else {
-                double* ri = i < NQ ? Ha + LDM * i : Y + NQ * (i - NQ);
-                ri[k] = ri[k] / dk;
+LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch, bool factor_done) {
+    double* L1 = w.u.s.L1;
+    double* Yt = w.u.s.Yt;
+    double* Gm = w.u.s.Gm;
+    if (!factor_done) {
+        // left-looking Cholesky of D1 (18 columns); the 10 right-hand-side rows ride along and come out as L1^-1 [.]
+        for (int k = 0; k < ND1; ++k) {
+            LMH_FOR(i0, ND1 + NYR - k) {
+                int i = k + i0;
+                double* ri = i < ND1 ? L1 + LD1 * i : Yt + NQ * (i - ND1);
+                const double* rk = L1 + LD1 * k;
+                double s0 = ri[k], s1 = 0.0;
+                int m = 0;
+                for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
+                if (m < k) s0 -= ri[m] * rk[m];
+                ri[k] = s0 + s1;
             }
+            cx.sync();
+            double dk = sqrt(L1[LD1 * k + k]);     // nobody writes the pivot in the next loop
+            LMH_FOR(i0, ND1 + NYR - k) {
+                int i = k + i0;
+                if (i == k) w.ladiag[k] = dk;
+                else {
+                    double* ri = i < ND1 ? L1 + LD1 * i : Yt + NQ * (i - ND1);
+                    ri[k] = ri[k] / dk;
+                }
+            }
+            cx.sync();
         }
-        cx.sync();
     }
-    // Sa = Y Y' (6x6), rhs = C6 - Y w
-    LMH_FOR(it, 42) {
-        int r = it / 6, c = it % 6;
-        double s = 0.0;
-        if (r < 6) {
-            for (int m = 0; m < NQ; ++m) s += Y[NQ * r + m] * Y[NQ * c + m];
-            w.Sa[it] = s;
-        } else {
-            for (int m = 0; m < NQ; ++m) s += Y[NQ * c + m] * Y[NQ * 6 + m];
-            w.rhs[c] = w.C[c] - s;
+    // Gram matrix of the rows: Gm[r][c] = [.]_r D^-1 [.]_c'
+    LMH_FOR(it, NYR * NYR) {
+        int r = it / NYR, c = it % NYR;
+        if (c <= r) {
+            double s0 = 0.0, s1 = 0.0;
+            const double* yr = Yt + NQ * r;
+            const double* yc = Yt + NQ * c;
+            for (int m = 0; m < NQ; m += 2) { s0 += yr[m] * yc[m]; s1 += yr[m + 1] * yc[m + 1]; }
+            Gm[NYR * r + c] = s0 + s1;
+            Gm[NYR * c + r] = s0 + s1;
         }
+    }
+    cx.sync();
+    // Ci = (I3 + U D^-1 U')^-1 in every thread; Sa = M6 Ha^-1 M6', rhs = C6 - M6 Ha^-1 ga
+    double Ci[9];
+    {
+        double c00 = 1.0 + Gm[NYR * 7 + 7], c01 = Gm[NYR * 7 + 8], c02 = Gm[NYR * 7 + 9];
+        double c11 = 1.0 + Gm[NYR * 8 + 8], c12 = Gm[NYR * 8 + 9], c22 = 1.0 + Gm[NYR * 9 + 9];
+        double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
+        double a11 = c00 * c22 - c02 * c02, a12 = c01 * c02 - c00 * c12, a22 = c00 * c11 - c01 * c01;
+        double det = c00 * a00 + c01 * a01 + c02 * a02;
+        Ci[0] = a00 / det; Ci[1] = a01 / det; Ci[2] = a02 / det;
+        Ci[3] = Ci[1];     Ci[4] = a11 / det; Ci[5] = a12 / det;
+        Ci[6] = Ci[2];     Ci[7] = Ci[5];     Ci[8] = a22 / det;
+    }
+    LMH_FOR(it, 42) {
+        int r = it / 6, c = it % 6;          // r == 6: the ga row
+        const int rr = r < 6 ? r : c, cc = r < 6 ? c : 6;
+        double g0 = Gm[NYR * rr + 7], g1 = Gm[NYR * rr + 8], g2 = Gm[NYR * rr + 9];
+        double h0 = Gm[NYR * 7 + cc], h1 = Gm[NYR * 8 + cc], h2 = Gm[NYR * 9 + cc];
+        double t0 = Ci[0] * h0 + Ci[1] * h1 + Ci[2] * h2, t1 = Ci[3] * h0 + Ci[4] * h1 + Ci[5] * h2, t2 = Ci[6] * h0 + Ci[7] * h1 + Ci[8] * h2;
+        double v = Gm[NYR * rr + cc] - (g0 * t0 + g1 * t1 + g2 * t2);
+        if (r < 6) w.Sa[it] = v; else w.rhs[c] = w.C[c] - v;
     }
     cx.sync();
     // Ls = chol(Sa), sv = Ls^-1 rhs -- 6x6, every thread redundantly in registers
@@ -1134,7 +1189,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch)
     if (fallback) qp_cspace_fallback(cx, w, K, Ls, gscratch, iters, status);
     w.qp_iters = iters;
     w.qp_status = status;
-    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12) ; a = -La^-T (wv + Y' lam)
+    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12)
     LMH_FOR(r, 12) {
         int foot = r / 6, k = r % 6;
         double s = 0.0;
@@ -1151,20 +1206,30 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch)
         }
         for (int r = 0; r < 6; ++r) { double s = l[r]; for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m]; l[r] = s / Ls[7 * r]; }
         for (int r = 5; r >= 0; --r) { double s = l[r]; for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m]; l[r] = s / Ls[7 * r]; }
+        // a = -Ha^-1 (ga + M6' lam) through the same Woodbury pieces
+        double coef[7] = {l[0], l[1], l[2], l[3], l[4], l[5], 1.0};
+        double z[3] = {0, 0, 0};
+        for (int r = 0; r < 7; ++r) { z[0] += Gm[NYR * 7 + r] * coef[r]; z[1] += Gm[NYR * 8 + r] * coef[r]; z[2] += Gm[NYR * 9 + r] * coef[r]; }
+        double cu[3] = {-(Ci[0] * z[0] + Ci[1] * z[1] + Ci[2] * z[2]), -(Ci[3] * z[0] + Ci[4] * z[1] + Ci[5] * z[2]),
+                        -(Ci[6] * z[0] + Ci[7] * z[1] + Ci[8] * z[2])};
         LMH_FOR(i, NQ) {
-            double s = Y[NQ * 6 + i];
-            for (int r = 0; r < 6; ++r) s += Y[NQ * r + i] * l[r];
-            w.a[i] = -s;
+            double sy = 0.0;
+            for (int r = 0; r < 7; ++r) sy += Yt[NQ * r + i] * coef[r];
+            for (int u = 0; u < 3; ++u) sy += Yt[NQ * (7 + u) + i] * cu[u];
+            w.a[i] = i < ND1 ? -sy : -sy / sqrt(K.wJoints);
         }
         LMH_FOR(r, 6) w.lam[r] = l[r];
     }
     cx.sync();
-    for (int k = NQ - 1; k >= 0; --k) {     // La' a = rhs, column oriented
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) { qp_backsolve_warp(w, cx.tid); return; }
+#endif
+    for (int k = ND1 - 1; k >= 0; --k) {     // L1' a[0:18] = rhs, column oriented
         double xk = w.a[k] / w.ladiag[k];
         cx.sync();
         LMH_FOR(i, k + 1) {
             if (i == k) w.a[k] = xk;
-            else w.a[i] -= Ha[LDM * k + i] * xk;
+            else w.a[i] -= L1[LD1 * k + i] * xk;
         }
         cx.sync();
     }
@@ -1212,11 +1277,8 @@ LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
 
 // Debug/parity dump of one stage (global memory on the device).
 template <class Cx>
-LMH_HDN void dump_assembly(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
-    LMH_FOR(it, NQ * NQ) {
-        int i = it / NQ, j = it % NQ;
-        d->Ha[it] = i >= j ? w.u.s.Ha[LDM * i + j] : w.u.s.Ha[LDM * j + i];
-    }
+LMH_HDN void dump_assembly(const Cx& cx, const EnvWS& w, const Consts& K, LmhStageDump* d) {
+    LMH_FOR(it, NQ * NQ) d->Ha[it] = ha_entry(w, K, it / NQ, it % NQ);
     LMH_FOR(i, NQ) d->ga[i] = w.ga[i];
     cx.sync();
 }
@@ -1270,9 +1332,20 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
     }
     centroidal_jacobian_phase(cx, w, K);
     mpc_pd_phase(cx, w, K, P, plan_id);
-    assemble_phase(cx, w, K);
-    if (dump) dump_assembly(cx, w, dump);
-    qp_phase(cx, w, K, gscratch);
+    bool factor_done = false;
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32 && K.wCoMK == 0.0) {
+        assemble_ga_phase(cx, w, K);
+        if (dump) dump_assembly(cx, w, K, dump);
+        qp_factor_warp(w, K, cx.tid);
+        factor_done = true;
+    } else
+#endif
+    {
+        assemble_phase(cx, w, K);
+        if (dump) dump_assembly(cx, w, K, dump);
+    }
+    qp_phase(cx, w, K, gscratch, factor_done);
     output_phase(cx, w);
     if (dump) dump_stage(cx, w, dump);
     LMH_FOR(i, NQ) w.vh[i] = w.v[i];     // Robot::updateVelocityState (Robot.cpp:271-274)

@@ -271,5 +271,85 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
     __syncwarp();
 }
 
+
+// ---- QP front end for one warp (see assemble_phase / qp_phase of lmh_model.cuh for the algebra): lane i < 18 owns
+// row i of D1 = Wj + wFoot JF'JF, lanes 18..27 own the ten right-hand-side rows [M6; ga'; U]; rows are assembled
+// straight into registers and the left-looking Cholesky runs on them, reading the finished part of row k back from
+// shared memory as a broadcast.  Leaves L1, ladiag and Yt in shared memory where qp_phase expects them.
+__device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
+    double* L1 = w.u.s.L1;
+    double* Yt = w.u.s.Yt;
+    double h[ND1];
+    const bool mrow = lane < ND1;
+    const int yr = lane - ND1;                       // right-hand-side row of this lane (0..9) if >= 0
+    const bool yrow = yr >= 0 && yr < NYR;
+#pragma unroll
+    for (int j = 0; j < ND1; ++j) h[j] = 0.0;
+    if (mrow) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const int ci = jf_col(f, lane);
+            if (ci >= 0) {
+                const double* Jf = w.JFc + 72 * f;
+                double jc[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) jc[k] = K.wFoot * Jf[12 * k + ci];
+#pragma unroll
+                for (int cj = 0; cj < 12; ++cj) {
+                    double sj = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) sj += jc[k] * Jf[12 * k + cj];
+                    h[cj < 6 ? cj : 6 + 6 * f + (cj - 6)] += sj;
+                }
+            }
+        }
+        const double wj = lane < 3 ? K.wBasePos : lane < 6 ? K.wBaseAng : K.wJoints;
+#pragma unroll
+        for (int j = 0; j < ND1; ++j) if (j == lane) h[j] += wj;
+    } else if (yrow) {
+#pragma unroll
+        for (int j = 0; j < ND1; ++j) h[j] = yt_entry(w, K, yr, j);
+        for (int j = ND1; j < NQ; ++j) Yt[NQ * yr + j] = yt_entry(w, K, yr, j);     // the arm/head part needs no solve
+    }
+#pragma unroll
+    for (int k = 0; k < ND1; ++k) {
+        double s = h[k], t = 0.0;
+        const double* Lk = L1 + LD1 * k;
+#pragma unroll
+        for (int m = 0; m < k; ++m) {
+            const double l = Lk[m];
+            if (m & 1) t -= h[m] * l; else s -= h[m] * l;
+        }
+        s += t;
+        const double piv = __shfl_sync(0xffffffffu, s, k);
+        const double rs = rsqrt(piv);
+        const double lik = lane == k ? piv * rs : s * rs;
+        h[k] = lik;
+        if (lane > k && mrow) L1[LD1 * lane + k] = lik;
+        if (lane == k) w.ladiag[k] = lik;
+        __syncwarp();
+    }
+    if (yrow) {
+#pragma unroll
+        for (int j = 0; j < ND1; ++j) Yt[NQ * yr + j] = h[j];
+    }
+    __syncwarp();
+}
+
+// back substitution L1' a[0:18] = b with lane i holding a_i (w.a in, w.a out)
+__device__ void qp_backsolve_warp(EnvWS& w, int lane) {
+    const double* L1 = w.u.s.L1;
+    double ai = lane < ND1 ? w.a[lane] : 0.0;
+    const double invd = lane < ND1 ? 1.0 / w.ladiag[lane] : 0.0;
+#pragma unroll
+    for (int k = ND1 - 1; k >= 0; --k) {
+        const double xk = __shfl_sync(0xffffffffu, ai * invd, k);
+        if (lane == k) ai = xk;
+        else if (lane < k) ai -= L1[LD1 * k + lane] * xk;
+    }
+    if (lane < ND1) w.a[lane] = ai;
+    __syncwarp();
+}
+
 }  // namespace lmh
 #endif
