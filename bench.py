@@ -321,7 +321,7 @@ def run_ours(args):
             orc_py.build()
             lib = orc_py.oracle()
             cores = os.cpu_count() or 1
-            n_cpu, s_cpu = 2 * cores, 100
+            n_cpu, s_cpu = 16 * cores, S          # a bounded sample: the first 16*cores envs, full rollout length
             rate, dtc, x_cpu = cpu_rollout_rate(lib, "port", n_cpu, s_cpu, cores)
             # the same envs on the GPU for the same number of steps: a live parity check beside the timing
             b2 = lmh.Batch(n_cpu, device=local_rank, threads_per_env=args.threads_per_env)

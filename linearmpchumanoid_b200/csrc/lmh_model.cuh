@@ -76,6 +76,7 @@ struct Consts {
     double Gf[6 * 16];        // per-foot wrench generators: rows 0-2 moment, 3-5 force (controller.cpp:156-294)
     double GtG[16 * 16];      // Gf' Gf
     double GGt[36];           // Gf Gf' (6 x 6), the all-free wrench Gram matrix of one foot
+    double sq_wCoML, isq_wJoints;   // sqrt(wCoML), 1/sqrt(wJoints)
     double KpJ, KdJ, KpM, KdM, KpF, KdF;                                    // controller.hpp:100-111
     double wCoML, wCoMK, wBasePos, wBaseAng, wJoints, wForce, wFoot, epsC;   // controller.hpp:118-124, controller.cpp:109-123
     // LIPM MPC (mpcLinearPendulum.cpp:41-68,89-101): u0 = -(rPx . [pos,vel]) + sum_i r[i]*zmp[k+i]
@@ -114,7 +115,7 @@ struct EnvWS {
     double com[3], comVel[3], angMom[3], xRef[3], yRef[3];
     double qppRef[NQ], hGpRef[6], footAccRef[12];
     double ga[NQ], a[NQ], f12[12], tau[NJ], xdot[2 * NQ];
-    double Sa[36], rhs[6], sv[6], lam[6];
+    double Sa[36], Ls[36], rhs[6], sv[6], lam[6];
     double c[NC], cs[NC], mu[NC], piv[NC], ladiag[ND1];
     double red[32];                // reduction scratch
     int32_t free_mask[NC];
@@ -178,6 +179,44 @@ struct Ctx {
     }
 };
 #define LMH_FOR(i, n) for (int i = cx.tid; i < (n); i += Cx::NT)
+#if defined(__CUDACC__)
+#define LMH_UNROLL _Pragma("unroll")
+#else
+#define LMH_UNROLL
+#endif
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
+
+// in-place Cholesky of a 6x6 SPD matrix held in registers (lower triangle), fully unrolled
+LMH_HD void chol6(double* A) {
+    LMH_UNROLL
+    for (int k = 0; k < 6; ++k) {
+        double s = A[7 * k];
+        LMH_UNROLL
+        for (int m = 0; m < k; ++m) s -= A[6 * k + m] * A[6 * k + m];
+        const double dk = sqrt(s);
+        const double inv = 1.0 / dk;
+        A[7 * k] = dk;
+        LMH_UNROLL
+        for (int i = k + 1; i < 6; ++i) {
+            double t = A[6 * i + k];
+            LMH_UNROLL
+            for (int m = 0; m < k; ++m) t -= A[6 * i + m] * A[6 * k + m];
+            A[6 * i + k] = t * inv;
+        }
+    }
+}
 
 LMH_HD void lmh_sincos(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
@@ -543,6 +582,11 @@ LMH_HD double hjoint(const EnvWS& w, int a, int b) {
     return w.Hc[36 * c + 6 * (a - chain_joint0(c)) + (b - chain_joint0(c))];
 }
 
+#if defined(__CUDACC__)
+struct EnvWS;
+__device__ void jacobian_warp(EnvWS& w, int lane);
+#endif
+
 // ================================================================================================
 // Phase 4: gravity bias by linearity, centroidal matrix (Dynamics.cpp:103-121), sole Jacobians
 // (invKinematics.cpp:72-149), CoM velocity / angular momentum (Robot.cpp:300-310).
@@ -570,6 +614,11 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
             else { w.AGpqp[k] = a; w.AGpqp[3 + k] = b; }
         }
     }
+    bool jac_done = false;
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) { jacobian_warp(w, cx.tid); jac_done = true; }
+#endif
+    if (!jac_done) {
     // running sole_X_j = (E, B) for both feet, starting from the sole frame
     LMH_FOR(it, 36) {
         int s = it / 18, e = it % 18;
@@ -615,6 +664,7 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
         w.JFc[72 * s + 12 * k + b] = rot_row(w.Rs[s], k % 3, cv);
     }
     cx.sync();
+    }
     // h = AG vb (current velocity)
     LMH_FOR(k, 6) {
         double s = 0.0;
@@ -749,8 +799,8 @@ LMH_HD double ha_entry(const EnvWS& w, const Consts& K, int i, int j) {      // 
 }
 // entry (r, j) of the right-hand-side block [M6; ga'; U] before the factorisation
 LMH_HD double yt_entry(const EnvWS& w, const Consts& K, int r, int j) {
-    double v = r < 6 ? w.M6[NQ * r + j] : r == 6 ? w.ga[j] : sqrt(K.wCoML) * w.AG[NQ * (r - 4) + j];
-    return j < ND1 ? v : v / sqrt(K.wJoints);
+    double v = r < 6 ? w.M6[NQ * r + j] : r == 6 ? w.ga[j] : K.sq_wCoML * w.AG[NQ * (r - 4) + j];
+    return j < ND1 ? v : v * K.isq_wJoints;
 }
 template <class Cx>
 LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
@@ -930,6 +980,7 @@ LMH_HDN void qp_cspace_fallback(const Cx& cx, EnvWS& w, const Consts& K, const d
 
 #if defined(__CUDACC__)
 __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane);
+__device__ void jacobian_warp(EnvWS& w, int lane);
 __device__ void qp_backsolve_warp(EnvWS& w, int lane);
 #endif
 
@@ -1006,22 +1057,15 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         if (r < 6) w.Sa[it] = v; else w.rhs[c] = w.C[c] - v;
     }
     cx.sync();
-    // Ls = chol(Sa), sv = Ls^-1 rhs -- 6x6, every thread redundantly in registers
-    double Ls[36];
+    // Ls = chol(Sa): 6x6, every thread redundantly in registers, then parked in shared memory
     {
-        for (int e = 0; e < 36; ++e) Ls[e] = w.Sa[e];
-        for (int k = 0; k < 6; ++k) {
-            double s = Ls[7 * k];
-            for (int m = 0; m < k; ++m) s -= Ls[6 * k + m] * Ls[6 * k + m];
-            double dk = sqrt(s);
-            Ls[7 * k] = dk;
-            for (int i = k + 1; i < 6; ++i) {
-                double t = Ls[6 * i + k];
-                for (int m = 0; m < k; ++m) t -= Ls[6 * i + m] * Ls[6 * k + m];
-                Ls[6 * i + k] = t / dk;
-            }
-        }
+        double A[36];
+        LMH_UNROLL
+        for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
+        chol6(A);
+        LMH_FOR(e, 36) w.Ls[e] = A[e];
     }
+    const double* Ls = w.Ls;
     // ---- wrench-space solves.  With y = (Jb lam - wF f)/eps the stationarity in the free coefficients reads
     //   (P_F + (eps/wF)(I - Jb Z^-1 Jb')) y = Jb Z^-1 rhs,  Z = wF Sa + Jb'Jb,  P_F = sum_{i free} g_i g_i',
     // with c_F = G_F'y and multipliers -eps g_i'y on the working set.  12 x 12, and well conditioned as long
@@ -1031,32 +1075,35 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
     double* uy = w.u.s.uy;
     {
         double Lz[36];
-        for (int r = 0; r < 6; ++r)
-            for (int c = 0; c <= r; ++c) {
+        LMH_UNROLL
+        for (int r = 0; r < 6; ++r) {
+            LMH_UNROLL
+            for (int c = 0; c < 6; ++c) {
                 double sj = 0.0;
-                for (int f = 0; f < 2; ++f)
-                    for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + r] * w.JFc[72 * f + 12 * k + c];
-                Lz[6 * r + c] = K.wForce * w.Sa[6 * r + c] + sj;
-            }
-        for (int k = 0; k < 6; ++k) {
-            double sd = Lz[7 * k];
-            for (int m = 0; m < k; ++m) sd -= Lz[6 * k + m] * Lz[6 * k + m];
-            double dk = sqrt(sd);
-            Lz[7 * k] = dk;
-            for (int i = k + 1; i < 6; ++i) {
-                double t = Lz[6 * i + k];
-                for (int m = 0; m < k; ++m) t -= Lz[6 * i + m] * Lz[6 * k + m];
-                Lz[6 * i + k] = t / dk;
+                if (c <= r) {
+                    LMH_UNROLL
+                    for (int f = 0; f < 2; ++f) {
+                        LMH_UNROLL
+                        for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + r] * w.JFc[72 * f + 12 * k + c];
+                    }
+                    sj += K.wForce * w.Sa[6 * r + c];
+                }
+                Lz[6 * r + c] = sj;
             }
         }
+        chol6(Lz);
         LMH_FOR(j, 13) {
             double col[6];
+            LMH_UNROLL
             for (int r = 0; r < 6; ++r) col[r] = j < 12 ? w.JFc[72 * (j / 6) + 12 * (j % 6) + r] : w.rhs[r];
+            LMH_UNROLL
             for (int r = 0; r < 6; ++r) {
                 double sd = col[r];
+                LMH_UNROLL
                 for (int m = 0; m < r; ++m) sd -= Lz[6 * r + m] * col[m];
                 col[r] = sd / Lz[7 * r];
             }
+            LMH_UNROLL
             for (int r = 0; r < 6; ++r) { if (j < 12) Vy[12 * r + j] = col[r]; else uy[r] = col[r]; }
         }
     }
@@ -1138,15 +1185,43 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             w.cs[i] = w.free_mask[i] ? sc : 0.0;
         }
         cx.sync();
-        // decisions, taken redundantly by every thread from the shared vectors
+        // decisions: every thread reaches the same ones (warp reductions for one warp per env, else redundant loops)
+        bool done = false;
+        int change = -1, to_free = 0;
+        double alpha = 1.0;
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) {
+            const int i = cx.tid;
+            const bool fr = w.free_mask[i] != 0;
+            const double csi = w.cs[i], mui = w.mu[i], ci = w.c[i];
+            const double cmin = warp_min(fr && csi < 0.0 ? csi : 0.0);
+            const double cmax = warp_max(fmax(1.0, fabs(csi)));
+            if (!have_point) {
+                have_point = true;
+                if (cmin >= 0.0) done = true; else alpha = -1.0;
+            } else if (cmin >= 0.0) {
+                const double thr = 1e-10 * cmax;
+                const bool cand = !fr && mui > thr;
+                const double vmax = warp_max(cand ? mui : -1e300);
+                const unsigned hit = __ballot_sync(0xffffffffu, cand && mui == vmax);
+                if (hit == 0u) done = true; else { change = __ffs(hit) - 1; to_free = 1; }
+            } else {
+                const bool cand = fr && csi < 0.0;
+                const double dl = ci - csi;
+                const double ri = cand ? (dl > 0.0 ? ci / dl : 0.0) : 2.0;
+                const double best = warp_min(ri);
+                const unsigned hit = __ballot_sync(0xffffffffu, cand && ri == best);
+                if (hit != 0u) change = __ffs(hit) - 1;
+                alpha = best < 1.0 ? best : 1.0;
+            }
+        } else
+#endif
+        {
         double cmin = 0.0, cmax = 1.0;
         for (int i = 0; i < NC; ++i) {
             if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
             cmax = fmax(cmax, fabs(w.cs[i]));
         }
-        bool done = false;
-        int change = -1, to_free = 0;
-        double alpha = 1.0;
         if (!have_point) {
             have_point = true;
             if (cmin >= 0.0) done = true;              // the all-free minimiser is feasible: optimal
@@ -1164,6 +1239,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
                     if (r < best) { best = r; change = i; }
                 }
             alpha = best < 1.0 ? best : 1.0;
+        }
         }
         cx.sync();
         LMH_FOR(i, NC) {
@@ -1199,13 +1275,27 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
     cx.sync();
     {
         double l[6];
+        LMH_UNROLL
         for (int r = 0; r < 6; ++r) {
             double s = w.rhs[r];
+            LMH_UNROLL
             for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
             l[r] = s;
         }
-        for (int r = 0; r < 6; ++r) { double s = l[r]; for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m]; l[r] = s / Ls[7 * r]; }
-        for (int r = 5; r >= 0; --r) { double s = l[r]; for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m]; l[r] = s / Ls[7 * r]; }
+        LMH_UNROLL
+        for (int r = 0; r < 6; ++r) {
+            double s = l[r];
+            LMH_UNROLL
+            for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m];
+            l[r] = s / Ls[7 * r];
+        }
+        LMH_UNROLL
+        for (int r = 5; r >= 0; --r) {
+            double s = l[r];
+            LMH_UNROLL
+            for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m];
+            l[r] = s / Ls[7 * r];
+        }
         // a = -Ha^-1 (ga + M6' lam) through the same Woodbury pieces
         double coef[7] = {l[0], l[1], l[2], l[3], l[4], l[5], 1.0};
         double z[3] = {0, 0, 0};
@@ -1216,7 +1306,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             double sy = 0.0;
             for (int r = 0; r < 7; ++r) sy += Yt[NQ * r + i] * coef[r];
             for (int u = 0; u < 3; ++u) sy += Yt[NQ * (7 + u) + i] * cu[u];
-            w.a[i] = i < ND1 ? -sy : -sy / sqrt(K.wJoints);
+            w.a[i] = i < ND1 ? -sy : -sy * K.isq_wJoints;
         }
         LMH_FOR(r, 6) w.lam[r] = l[r];
     }

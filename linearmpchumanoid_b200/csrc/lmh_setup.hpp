@@ -192,7 +192,8 @@ private:
     void build_controller_tables() {
         K.KpJ = 300; K.KdJ = 34; K.KpM = 10; K.KdM = 6.32; K.KpF = 500; K.KdF = 44;        // controller.hpp:100-111
         K.wCoML = 4000; K.wCoMK = 0; K.wBasePos = 10; K.wBaseAng = 10; K.wJoints = 1;      // controller.hpp:118-124
-        K.wForce = 1; K.wFoot = 100000; K.epsC = 1e-8;                                      // controller.cpp:109-123
+        K.wForce = 1; K.wFoot = 100000; K.epsC = 1e-8;
+        K.sq_wCoML = std::sqrt(K.wCoML); K.isq_wJoints = 1.0 / std::sqrt(K.wJoints);                                      // controller.cpp:109-123
         K.qp_max_iter = sc.qp_max_iter;
         K.dt = sc.dt;
         // friction pyramid edges and contact vertices (controller.cpp:33-36, Robot.cpp:38-42)

@@ -272,6 +272,45 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
 }
 
 
+
+// ---- sole Jacobians (invKinematics.cpp:72-149), one column per lane: lane = 12*foot + col, col 0..5 the base twist
+// block (sole_X_base e_col), col 6+l the joint l of that leg (sole_X_(joint frame) S).  A column is a unit vector
+// pushed through the motion transforms of the frames between it and the sole; no cross-lane traffic.
+__device__ void jacobian_warp(EnvWS& w, int lane) {
+    if (lane < 24) {
+        const int s = lane / 12, col = lane % 12;
+        const int f0 = s == 0 ? 1 : 8;
+        const double* Xl = w.u.m.Xl;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        int start;
+        if (col < 6) { v[0] = col == 0; v[1] = col == 1; v[2] = col == 2; v[3] = col == 3; v[4] = col == 4; v[5] = col == 5; start = 0; }
+        else { v[2] = 1.0; start = col - 5; }
+#pragma unroll 1
+        for (int i = start; i <= 6; ++i) {
+            double Rp[12];
+            load12(Xl + 12 * (f0 + i), Rp);
+            const double u0 = v[3] + (v[1] * Rp[11] - v[2] * Rp[10]);
+            const double u1 = v[4] + (v[2] * Rp[9] - v[0] * Rp[11]);
+            const double u2 = v[5] + (v[0] * Rp[10] - v[1] * Rp[9]);
+            const double t0 = Rp[0] * v[0] + Rp[3] * v[1] + Rp[6] * v[2];
+            const double t1 = Rp[1] * v[0] + Rp[4] * v[1] + Rp[7] * v[2];
+            const double t2 = Rp[2] * v[0] + Rp[5] * v[1] + Rp[8] * v[2];
+            v[3] = Rp[0] * u0 + Rp[3] * u1 + Rp[6] * u2;
+            v[4] = Rp[1] * u0 + Rp[4] * u1 + Rp[7] * u2;
+            v[5] = Rp[2] * u0 + Rp[5] * u1 + Rp[8] * u2;
+            v[0] = t0; v[1] = t1; v[2] = t2;
+        }
+        const double* R = w.Rs[s];
+        double* J = w.JFc + 72 * s + col;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            J[12 * k] = R[3 * k] * v[0] + R[3 * k + 1] * v[1] + R[3 * k + 2] * v[2];
+            J[12 * (3 + k)] = R[3 * k] * v[3] + R[3 * k + 1] * v[4] + R[3 * k + 2] * v[5];
+        }
+    }
+    __syncwarp();
+}
+
 // ---- QP front end for one warp (see assemble_phase / qp_phase of lmh_model.cuh for the algebra): lane i < 18 owns
 // row i of D1 = Wj + wFoot JF'JF, lanes 18..27 own the ten right-hand-side rows [M6; ga'; U]; rows are assembled
 // straight into registers and the left-looking Cholesky runs on them, reading the finished part of row k back from
