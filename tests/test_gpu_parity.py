@@ -215,3 +215,21 @@ def test_plans_and_edge_cases():
     b.step(3)
     st = b.stats()
     assert np.isfinite(b.get_state()[0][[0, 1, 2, 4]]).all() and (st["steps"] == 3).all()
+
+
+def test_offline_app_on_the_facade_classes(golden, tmp_path):
+    """apps/offline/main.cpp rebuilt against include/linearMpcHumanoid_b200/facade.hpp (Robot,
+    Kinematics, Mpc3dLip, ZMP, Controller, rk4Step with the reference's names) prints the reference's stream."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "offline_b200")
+    libdir = os.path.join(root, "linearmpchumanoid_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "apps", "offline_b200", "main.cpp"), "-L" + libdir, "-llmh_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    cx = np.array([float(v) for v in out])
+    assert len(cx) == 500
+    assert np.abs(cx - golden["stand_comx"]).max() < 5e-8          # both streams carry 6 significant digits
+    fused = subprocess.run([exe, "--fused", "64"], check=True, capture_output=True, text=True).stdout.split()
+    assert abs(float(fused[0]) - golden["stand_comx"][-1]) < 5e-8   # the fused batched rollout ends in the same place
