@@ -44,7 +44,7 @@ struct Params {
 constexpr int kExtraDoubles = 2 * 60;   // x and the RK4 accumulator
 
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 32 ? 9 : 1) rollout_kernel(Params p) {
+__global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p) {
     extern __shared__ double smem[];
     EnvWS& w = *reinterpret_cast<EnvWS*>(smem);
     double* x = smem + (sizeof(EnvWS) + 7) / 8;

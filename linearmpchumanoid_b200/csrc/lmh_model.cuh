@@ -130,7 +130,7 @@ struct EnvWS {
                 struct {
                     double IcIn[NCH * 36];     // composite inertia arriving from the level below
                     double IcCur[NCH * 36];    // composite inertia of the level being processed
-                    double Xd[NCH * 36], Yt[NCH * 36];
+                    double Yt[NCH * 36];
                     double Fb[2][NJ * 6];
                 } crba;
                 double Xn[2][2 * 18];  // running sole_X_j as (E, B) for both feet, double buffered
@@ -262,6 +262,12 @@ LMH_HD double xdense(const double* Rp, int a, int b) {
     return bc == 0 ? -(e1 * p[2] - e2 * p[1]) : bc == 1 ? -(-e0 * p[2] + e2 * p[0]) : -(e0 * p[1] - e1 * p[0]);
 }
 
+#if defined(__CUDACC__)
+struct EnvWS;
+struct Consts;
+__device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane);
+#endif
+
 // ================================================================================================
 // Phase 1: forward kinematics, parent-relative transforms, CoM.
 template <class Cx>
@@ -307,6 +313,9 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         }
     }
     cx.sync();
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) { fk_chain_warp(w, K, cx.tid); return; }
+#endif
     // chained world transforms, one tree level per pass
     for (int d = 1; d <= MAXDEPTH; ++d) {
         LMH_FOR(it, NCH * 12) {
@@ -493,7 +502,6 @@ template <class Cx>
 LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     double* IcIn = w.u.m.p.crba.IcIn;
     double* IcCur = w.u.m.p.crba.IcCur;
-    double* Xd = w.u.m.p.crba.Xd;
     double* Yt = w.u.m.p.crba.Yt;
     const double* Xl = w.u.m.Xl;
     LMH_FOR(it, NCH * 36) { IcIn[it] = 0.0; w.Hc[it] = 0.0; }
@@ -511,7 +519,6 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                 int i = chain_first(c) + d - 1;
                 double v = K.Isp[36 * i + e] + IcIn[it];
                 IcCur[it] = v;
-                Xd[it] = xdense(Xl + 12 * i, e / 6, e % 6);
                 if (e % 6 == 2) {
                     int k = e / 6, a = chain_joint0(c) + d - 1;
                     w.u.m.p.crba.Fb[cur][6 * a + k] = v;
@@ -526,8 +533,10 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             if (d <= chain_nact(c)) {
                 int r = e / 6, cc = e % 6;
                 const double* I = IcCur + 36 * c + 6 * r;
-                const double* X = Xd + 36 * c + cc;
-                Yt[it] = I[0] * X[0] + I[1] * X[6] + I[2] * X[12] + I[3] * X[18] + I[4] * X[24] + I[5] * X[30];
+                const double* Rp = Xl + 12 * (chain_first(c) + d - 1);
+                double sy = 0.0;
+                for (int k = 0; k < 6; ++k) sy += I[k] * xdense(Rp, k, cc);
+                Yt[it] = sy;
             }
         }
         LMH_FOR(it, NJ * 6) {
@@ -553,9 +562,11 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                 int c = it / 36, e = it % 36;
                 if (d <= chain_nact(c)) {
                     int r = e / 6, cc = e % 6;
-                    const double* X = Xd + 36 * c + r;
+                    const double* Rp = Xl + 12 * (chain_first(c) + d - 1);
                     const double* Y = Yt + 36 * c + cc;
-                    IcIn[it] = X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
+                    double sx = 0.0;
+                    for (int k = 0; k < 6; ++k) sx += xdense(Rp, k, r) * Y[6 * k];
+                    IcIn[it] = sx;
                 }
             }
         } else {
@@ -563,9 +574,9 @@ LMH_HDN void crba_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                 int r = e / 6, cc = e % 6;
                 double sum = K.Isp[e];
                 for (int c = NCH - 1; c >= 0; --c) {
-                    const double* X = Xd + 36 * c + r;
+                    const double* Rp = Xl + 12 * chain_first(c);
                     const double* Y = Yt + 36 * c + cc;
-                    sum += X[0] * Y[0] + X[6] * Y[6] + X[12] * Y[12] + X[18] * Y[18] + X[24] * Y[24] + X[30] * Y[30];
+                    for (int k = 0; k < 6; ++k) sum += xdense(Rp, k, r) * Y[6 * k];
                 }
                 w.M6[NQ * r + cc] = sum;   // Ic0
             }

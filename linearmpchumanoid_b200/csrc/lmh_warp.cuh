@@ -68,6 +68,74 @@ __device__ __forceinline__ double cross3(const double* a, const double* b, int k
     return k == 0 ? a[1] * b[2] - a[2] * b[1] : k == 1 ? a[2] * b[0] - a[0] * b[2] : a[0] * b[1] - a[1] * b[0];
 }
 
+
+// ---- forward kinematics after the local transforms are in w.u.m.Xl (Robot.cpp:45-160,225-238,276-298):
+// lane 3c + r3 (< 15) carries row r3 of the world transform of chain c's current frame down the chain (a row-local
+// recurrence: no exchange between levels); then lane i (< 27) turns frame i's local transform into the
+// parent-relative one and adds its link to the centre of mass.
+__device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
+    double* Tw = w.u.m.p.Tw;
+    double* Xl = w.u.m.Xl;
+    if (lane < 15) {
+        const int c = lane / 3, r3 = lane % 3;
+        const int first = chain_first(c), len = chain_len(c);
+        double R0 = Tw[3 * r3], R1 = Tw[3 * r3 + 1], R2 = Tw[3 * r3 + 2], pp = Tw[9 + r3];   // torso row
+#pragma unroll 1
+        for (int d = 0; d < len; ++d) {
+            const double* L = Xl + 12 * (first + d);
+            double* O = Tw + 12 * (first + d);
+            const double n0 = R0 * L[0] + R1 * L[3] + R2 * L[6];
+            const double n1 = R0 * L[1] + R1 * L[4] + R2 * L[7];
+            const double n2 = R0 * L[2] + R1 * L[5] + R2 * L[8];
+            pp = R0 * L[9] + R1 * L[10] + R2 * L[11] + pp;
+            R0 = n0; R1 = n1; R2 = n2;
+            O[3 * r3] = R0; O[3 * r3 + 1] = R1; O[3 * r3 + 2] = R2; O[9 + r3] = pp;
+        }
+    }
+    __syncwarp();
+    double cm0 = 0.0, cm1 = 0.0, cm2 = 0.0;
+    if (lane < NF) {
+        double Ti[12];
+        load12(Tw + 12 * lane, Ti);
+        double* O = Xl + 12 * lane;
+        if (lane == 0) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) O[e] = Ti[e];
+        } else {
+            double P[12];
+            load12(Tw + 12 * frame_parent(lane), P);
+#pragma unroll
+            for (int r3 = 0; r3 < 3; ++r3) {
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) O[3 * r3 + cc] = P[r3] * Ti[cc] + P[3 + r3] * Ti[3 + cc] + P[6 + r3] * Ti[6 + cc];
+                const double pi = P[r3] * Ti[9] + P[3 + r3] * Ti[10] + P[6 + r3] * Ti[11];
+                const double pq = P[r3] * P[9] + P[3 + r3] * P[10] + P[6 + r3] * P[11];
+                O[9 + r3] = pi - pq;
+            }
+        }
+        const double* mc = K.mc + 4 * lane;
+        const double m = mc[3];
+        cm0 = m * (Ti[0] * mc[0] + Ti[1] * mc[1] + Ti[2] * mc[2] + Ti[9]);
+        cm1 = m * (Ti[3] * mc[0] + Ti[4] * mc[1] + Ti[5] * mc[2] + Ti[10]);
+        cm2 = m * (Ti[6] * mc[0] + Ti[7] * mc[1] + Ti[8] * mc[2] + Ti[11]);
+        if (lane == 7 || lane == 14) {
+            const int s = lane == 7 ? 0 : 1;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) w.Rs[s][e] = Ti[e];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) w.ps[s][e] = Ti[9 + e];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cm0 += __shfl_xor_sync(0xffffffffu, cm0, o);
+        cm1 += __shfl_xor_sync(0xffffffffu, cm1, o);
+        cm2 += __shfl_xor_sync(0xffffffffu, cm2, o);
+    }
+    if (lane == 0) { w.com[0] = cm0 / K.mass; w.com[1] = cm1 / K.mass; w.com[2] = cm2 / K.mass; }
+    __syncwarp();
+}
+
 // ---- RNEA with zero base acceleration on the held velocity (Dynamics.cpp:29-60,124-200) -> Cg, Jpqp
 __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
     auto& S = w.u.m.p.wr;
