@@ -43,10 +43,13 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+#ifndef LMH_WARP_WRENCH
+#define LMH_WARP_WRENCH 0
+#endif
 constexpr int ND1 = 18;     // base + both legs: the block of H_a that the sole Jacobians couple
 constexpr int LD1 = 19;
 constexpr int NYR = 10;     // right-hand-side rows carried through the factorisation
-constexpr int QP_SCRATCH_DOUBLES = 6 * NC + NC * LDQ + 4 * NC;   // per-env global scratch of the rare c-space fallback
+constexpr int QP_SCRATCH_DOUBLES = 8;   // (the c-space fallback that used a global scratch is gone)   // per-env global scratch of the rare c-space fallback
 
 // chain c: frames chain_first[c] .. chain_first[c]+chain_len[c]-1, depth 1..chain_len[c]
 LMH_HD int chain_first(int c) { return c == 0 ? 1 : c == 1 ? 8 : c == 2 ? 15 : c == 3 ? 20 : 25; }
@@ -76,6 +79,7 @@ struct Consts {
     double Gf[6 * 16];        // per-foot wrench generators: rows 0-2 moment, 3-5 force (controller.cpp:156-294)
     double GtG[16 * 16];      // Gf' Gf
     double GGt[36];           // Gf Gf' (6 x 6), the all-free wrench Gram matrix of one foot
+    double Ball[36], Tall[36], BTiall[36];    // its Cholesky factor B (GGt = B B'), B'B and B (B'B)^-1
     double sq_wCoML, isq_wJoints;   // sqrt(wCoML), 1/sqrt(wJoints)
     double KpJ, KdJ, KpM, KdM, KpF, KdF;                                    // controller.hpp:100-111
     double wCoML, wCoMK, wBasePos, wBaseAng, wJoints, wForce, wFoot, epsC;   // controller.hpp:118-124, controller.cpp:109-123
@@ -119,6 +123,7 @@ struct EnvWS {
     double c[NC], cs[NC], mu[NC], piv[NC], ladiag[ND1];
     double red[32];                // reduction scratch
     int32_t free_mask[NC];
+    int32_t pdone[12], ppiv[2];
     int32_t k_index, qp_iters, qp_status, qp_fallback;
     // ---- phase-overlaid scratch
     union {
@@ -146,9 +151,9 @@ struct EnvWS {
             double Yt[NYR * NQ];       // rows M6[0..5], ga, U[0..2] (U = sqrt(wCoML) AG[3..5]); cols 0..17: L1^-1 applied,
                                        // cols 18..29: scaled by 1/sqrt(wJoints)
             double Gm[NYR * NYR];      // Gram matrix Yt Yt'
-            double Vy[6 * 12];         // Lz^-1 Jb'
-            double Ay[13 * 13];        // wrench-space system: lower triangle factorised in place, row 12 = rhs / y
-            double uy[6];              // Lz^-1 rhs
+            double Bm[12 * 6], Pm[2 * 36], Wb[6 * 12];   // wrench-space basis, its Gram matrix, Ls^-1 Jb' B
+            double Ay[13 * 13];        // wrench-space system: lower triangle factorised in place, row 12 = rhs / zeta
+            double vv[36];
         } s;
     } u;
 };
@@ -596,6 +601,7 @@ LMH_HD double hjoint(const EnvWS& w, int a, int b) {
 #if defined(__CUDACC__)
 struct EnvWS;
 __device__ void jacobian_warp(EnvWS& w, int lane);
+__device__ void wrench_solve_warp(EnvWS& w, int lane);
 #endif
 
 // ================================================================================================
@@ -835,160 +841,6 @@ LMH_HDN void assemble_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     cx.sync();
 }
 
-// c-space fallback of the WBC QP for working sets on which the wrench Gram matrix P_F is (nearly) singular
-// (a foot left with too few free generators, e.g. tipping on an edge):
-//   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I   (32 x 32),
-// masked Cholesky of Q per working set.  Q lives in a per-environment GLOBAL scratch buffer: this path is rare
-// and keeping it out of shared memory doubles the number of resident environments.  Continues the primal
-// active-set iteration from the current feasible point (w.c, w.free_mask).
-template <class Cx>
-LMH_HDN void qp_cspace_fallback(const Cx& cx, EnvWS& w, const Consts& K, const double* Ls, double* gs, int& iters, int& status) {
-    double* Wm = gs;               // 6 x 32
-    double* Q = gs + 6 * NC;       // upper: Q ; lower: masked factor
-    double* pq = Q + NC * LDQ;
-    double* zq = pq + NC;
-    double* qdiag = zq + NC;
-    double* ldiag = qdiag + NC;
-    LMH_FOR(i, NC + 1) {
-        double col[6];
-        if (i < NC) {
-            int foot = i / 16, gi = i % 16;
-            for (int r = 0; r < 6; ++r) {
-                double s = 0.0;
-                for (int k = 0; k < 6; ++k) s += w.JFc[72 * foot + 12 * k + r] * K.Gf[16 * k + gi];
-                col[r] = s;
-            }
-        } else {
-            for (int r = 0; r < 6; ++r) col[r] = w.rhs[r];
-        }
-        for (int r = 0; r < 6; ++r) {
-            double s = col[r];
-            for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * col[m];
-            col[r] = s / Ls[7 * r];
-        }
-        if (i < NC) for (int r = 0; r < 6; ++r) Wm[NC * r + i] = col[r];
-        else for (int r = 0; r < 6; ++r) w.sv[r] = col[r];
-    }
-    cx.sync();
-    LMH_FOR(it, NC * (NC + 1) / 2) {
-        int i = (int)((sqrt(8.0 * it + 1.0) - 1.0) * 0.5);
-        while ((i + 1) * (i + 2) / 2 <= it) ++i;
-        while (i * (i + 1) / 2 > it) --i;
-        int j = it - i * (i + 1) / 2;     // j <= i ; store at the UPPER position (j,i)
-        double s = 0.0;
-        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * Wm[NC * r + j];
-        if (i / 16 == j / 16) s += K.wForce * K.GtG[16 * (i % 16) + (j % 16)];
-        if (i == j) qdiag[i] = s + K.epsC;
-        else Q[LDQ * j + i] = s;
-    }
-    LMH_FOR(i, NC) {
-        double s = 0.0;
-        for (int r = 0; r < 6; ++r) s += Wm[NC * r + i] * w.sv[r];
-        pq[i] = s;
-    }
-    cx.sync();
-    while (true) {
-        ++iters;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int k = 0; k < NC; ++k) {
-            const bool fk = w.free_mask[k] != 0;
-            LMH_FOR(i0, NC + 1 - k) {
-                int i = k + i0;   // i == NC : the rhs row
-                double s0 = 0.0;
-                if (fk) {
-                    if (i < NC) {
-                        if (w.free_mask[i]) {
-                            s0 = i == k ? qdiag[k] : Q[LDQ * k + i];
-                            const double* ri = Q + LDQ * i;
-                            const double* rk = Q + LDQ * k;
-                            double s1 = 0.0;
-                            int m = 0;
-                            for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
-                            if (m < k) s0 -= ri[m] * rk[m];
-                            s0 += s1;
-                        }
-                    } else {
-                        s0 = pq[k];
-                        const double* rk = Q + LDQ * k;
-                        for (int m = 0; m < k; ++m) s0 -= zq[m] * rk[m];
-                    }
-                }
-                if (i == k) w.piv[k] = fk ? s0 : 1.0;
-                else if (i < NC) Q[LDQ * i + k] = s0;
-                else zq[k] = s0;
-            }
-            cx.sync();
-            double pv = w.piv[k];
-            double dk = sqrt(pv > 0.0 ? pv : 1e-300);
-            LMH_FOR(i0, NC + 1 - k) {
-                int i = k + i0;
-                if (i == k) ldiag[k] = dk;
-                else if (i < NC) Q[LDQ * i + k] = Q[LDQ * i + k] / dk;
-                else zq[k] = zq[k] / dk;
-            }
-            cx.sync();
-        }
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int k = NC - 1; k >= 0; --k) {      // L' cs = zq, column oriented
-            double xk = zq[k] / ldiag[k];
-            cx.sync();
-            LMH_FOR(i, k + 1) {
-                if (i == k) w.cs[k] = w.free_mask[k] ? xk : 0.0;
-                else zq[i] -= Q[LDQ * k + i] * xk;
-            }
-            cx.sync();
-        }
-        LMH_FOR(i, NC) {                          // gradient on the working set: mu = Q cs - pq
-            double s = -pq[i];
-            for (int j = 0; j < NC; ++j) {
-                double qij = i == j ? qdiag[i] : (i < j ? Q[LDQ * i + j] : Q[LDQ * j + i]);
-                s += qij * w.cs[j];
-            }
-            w.mu[i] = s;
-        }
-        cx.sync();
-        double cmin = 0.0, pmax = 1.0;
-        for (int i = 0; i < NC; ++i) {
-            if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
-            pmax = fmax(pmax, fabs(pq[i]));
-        }
-        bool done = false;
-        int change = -1, to_free = 0;
-        double alpha = 1.0;
-        if (cmin >= 0.0) {
-            double worst = -1e-12 * pmax;
-            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
-            if (change < 0) done = true; else to_free = 1;
-        } else {
-            double best = 2.0;
-            for (int i = 0; i < NC; ++i)
-                if (w.free_mask[i] && w.cs[i] < 0.0) {
-                    double dl = w.c[i] - w.cs[i];
-                    double r = dl > 0.0 ? w.c[i] / dl : 0.0;
-                    if (r < best) { best = r; change = i; }
-                }
-            alpha = best < 1.0 ? best : 1.0;
-        }
-        cx.sync();
-        LMH_FOR(i, NC) {
-            double x = w.c[i] + alpha * (w.cs[i] - w.c[i]);
-            if (!w.free_mask[i]) x = 0.0;
-            if (i == change) {
-                if (to_free) w.free_mask[i] = 1;
-                else { w.free_mask[i] = 0; x = 0.0; }
-            }
-            w.c[i] = x > 0.0 ? x : 0.0;
-        }
-        cx.sync();
-        if (done) { status = 0; break; }
-        if (iters >= K.qp_max_iter) { status = 1; break; }
-    }
-}
-
 #if defined(__CUDACC__)
 __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane);
 __device__ void jacobian_warp(EnvWS& w, int lane);
@@ -1004,6 +856,7 @@ __device__ void qp_backsolve_warp(EnvWS& w, int lane);
 // which a primal active-set method solves exactly (masked Cholesky of Q per working set).
 template <class Cx>
 LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch, bool factor_done) {
+    (void)gscratch;
     double* L1 = w.u.s.L1;
     double* Yt = w.u.s.Yt;
     double* Gm = w.u.s.Gm;
@@ -1077,81 +930,119 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         LMH_FOR(e, 36) w.Ls[e] = A[e];
     }
     const double* Ls = w.Ls;
-    // ---- wrench-space solves.  With y = (Jb lam - wF f)/eps the stationarity in the free coefficients reads
-    //   (P_F + (eps/wF)(I - Jb Z^-1 Jb')) y = Jb Z^-1 rhs,  Z = wF Sa + Jb'Jb,  P_F = sum_{i free} g_i g_i',
-    // with c_F = G_F'y and multipliers -eps g_i'y on the working set.  12 x 12, and well conditioned as long
-    // as P_F keeps full rank (always in the all-free case; checked through the Cholesky pivots otherwise).
-    double* Vy = w.u.s.Vy;
-    double* Ay = w.u.s.Ay;
-    double* uy = w.u.s.uy;
-    {
-        double Lz[36];
-        LMH_UNROLL
-        for (int r = 0; r < 6; ++r) {
-            LMH_UNROLL
-            for (int c = 0; c < 6; ++c) {
-                double sj = 0.0;
-                if (c <= r) {
-                    LMH_UNROLL
-                    for (int f = 0; f < 2; ++f) {
-                        LMH_UNROLL
-                        for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + r] * w.JFc[72 * f + 12 * k + c];
-                    }
-                    sj += K.wForce * w.Sa[6 * r + c];
-                }
-                Lz[6 * r + c] = sj;
-            }
-        }
-        chol6(Lz);
-        LMH_FOR(j, 13) {
-            double col[6];
-            LMH_UNROLL
-            for (int r = 0; r < 6; ++r) col[r] = j < 12 ? w.JFc[72 * (j / 6) + 12 * (j % 6) + r] : w.rhs[r];
-            LMH_UNROLL
-            for (int r = 0; r < 6; ++r) {
-                double sd = col[r];
-                LMH_UNROLL
-                for (int m = 0; m < r; ++m) sd -= Lz[6 * r + m] * col[m];
-                col[r] = sd / Lz[7 * r];
-            }
-            LMH_UNROLL
-            for (int r = 0; r < 6; ++r) { if (j < 12) Vy[12 * r + j] = col[r]; else uy[r] = col[r]; }
-        }
-    }
+    // ---- primal active set on c >= 0, every working set solved in the wrench space of the feet.
+    // For a free set F let P_F = G_F G_F' = B B' (B: 12 x 12, block diagonal per foot, from a diagonally pivoted
+    // Cholesky that stops at the numerical rank: columns beyond the rank are zero).  With f = B zeta the
+    // equality-constrained problem on F is
+    //     (B'K B + eps I) zeta = B'd,   K = wF I + Jb Sa^-1 Jb',  d = Jb Sa^-1 rhs,
+    // c_F = G_F' B (B'B)^-1 zeta, and the multipliers of the clipped coefficients are mu_i = g_i'(wF f - Jb lam),
+    // lam = Sa^-1 (rhs - Jb'f).  Well conditioned for ANY contact pattern (a foot on an edge, on one vertex, or
+    // unloaded only shortens B), which a c-space or a full 12 x 12 wrench-space system is not.
+    double* Bm = w.u.s.Bm;            // [12][6] : row 6f+i, basis column k of foot f
+    double* Pm = w.u.s.Pm;            // [2][36] : residual of the pivoted Cholesky, then T = B'B
+    double* Wb = w.u.s.Wb;            // [6][12] : Ls^-1 Jb' B
+    double* Ay = w.u.s.Ay;            // 13 x 13 : lower triangle factorised in place, row 12 = rhs / zeta
+    double* vv = w.u.s.vv;            // [36]   : u = T^-1 zeta (12), y = B u (12), r = wF f - Jb lam (12)
     LMH_FOR(i, NC) { w.free_mask[i] = 1; w.c[i] = 0.0; }
     cx.sync();
     int iters = 0, status = 0;
-    bool have_point = false, fallback = false;
+    bool have_point = false;
     while (true) {
         ++iters;
-        // A = P_F + (eps/wF)(I - V'V), rhs row = V'u
-        LMH_FOR(it, 13 * 12) {
-            int i = it / 12, j = it % 12;
-            if (i < 12) {
-                if (j <= i) {
-                    double sv_ = 0.0;
-                    for (int r = 0; r < 6; ++r) sv_ += Vy[12 * r + i] * Vy[12 * r + j];
-                    double kt = (i == j ? 1.0 : 0.0) - sv_;
-                    double pij = 0.0;
-                    if (i / 6 == j / 6) {
-                        if (!have_point) pij = K.GGt[6 * (i % 6) + (j % 6)];
-                        else {
-                            const int foot = i / 6;
-                            const double* gi = K.Gf + 16 * (i % 6);
-                            const double* gj = K.Gf + 16 * (j % 6);
-                            for (int g = 0; g < 16; ++g) if (w.free_mask[16 * foot + g]) pij += gi[g] * gj[g];
-                        }
-                    }
-                    Ay[13 * i + j] = pij + (K.epsC / K.wForce) * kt;
+        if (!have_point) {            // all free: B and T are constants of the foot geometry
+            LMH_FOR(it, 72) { Bm[it] = K.Ball[it % 36]; Pm[it] = K.Tall[it % 36]; }
+            cx.sync();
+        } else {
+            LMH_FOR(it, 72) {         // P_F per foot
+                const int f = it / 36, i = (it % 36) / 6, j = it % 6;
+                const double* gi = K.Gf + 16 * i;
+                const double* gj = K.Gf + 16 * j;
+                double pij = 0.0;
+                for (int g = 0; g < 16; ++g) if (w.free_mask[16 * f + g]) pij += gi[g] * gj[g];
+                Pm[it] = pij;
+                Bm[it] = 0.0;
+            }
+            LMH_FOR(i, 12) w.pdone[i] = 0;
+            cx.sync();
+            double dmax0[2] = {0.0, 0.0};
+            for (int f = 0; f < 2; ++f) for (int i = 0; i < 6; ++i) dmax0[f] = fmax(dmax0[f], Pm[36 * f + 7 * i]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < 6; ++k) {      // one pivot per foot and step; rows 6f+i are the work items
+                LMH_FOR(it, 12) {
+                    const int f = it / 6, i = it % 6;
+                    const double* S = Pm + 36 * f;
+                    int p = -1;
+                    double best = 1e-10 * dmax0[f];
+                    for (int j = 0; j < 6; ++j) if (!w.pdone[6 * f + j] && S[7 * j] > best) { best = S[7 * j]; p = j; }
+                    double colv = 0.0;
+                    if (p >= 0 && !w.pdone[it]) colv = p == i ? sqrt(best) : S[6 * i + p] / sqrt(best);
+                    Bm[6 * it + k] = colv;
+                    if (i == 0) w.ppiv[f] = p;
                 }
-            } else {
-                double sb = 0.0;
-                for (int r = 0; r < 6; ++r) sb += Vy[12 * r + j] * uy[r];
-                Ay[13 * 12 + j] = sb;
+                cx.sync();
+                LMH_FOR(it, 12) {
+                    const int f = it / 6, i = it % 6;
+                    double* S = Pm + 36 * f;
+                    const int p = w.ppiv[f];
+                    if (p >= 0) {
+                        const double colv = Bm[6 * it + k];
+                        for (int j = 0; j < 6; ++j) S[6 * i + j] -= colv * Bm[6 * (6 * f + j) + k];
+                    }
+                }
+                cx.sync();
+                LMH_FOR(f, 2) { if (w.ppiv[f] >= 0) w.pdone[6 * f + w.ppiv[f]] = 1; }
+                cx.sync();
+            }
+            LMH_FOR(it, 72) {         // T = B'B per foot (into Pm)
+                const int f = it / 36, k = (it % 36) / 6, l = it % 6;
+                double t = 0.0;
+                for (int i = 0; i < 6; ++i) t += Bm[6 * (6 * f + i) + k] * Bm[6 * (6 * f + i) + l];
+                Pm[it] = t;
+            }
+            cx.sync();
+        }
+        LMH_FOR(col, 13) {            // W[:, col] = Ls^-1 Jb' B[:, col] ; column 12: sv = Ls^-1 rhs (first pass only)
+            if (col < 12 || !have_point) {
+                const int f = col / 6, k = col % 6;
+                double t[6];
+                for (int m = 0; m < 6; ++m) {
+                    double sd = 0.0;
+                    if (col < 12) { for (int i = 0; i < 6; ++i) sd += w.JFc[72 * f + 12 * i + m] * Bm[6 * (6 * f + i) + k]; }
+                    else sd = w.rhs[m];
+                    t[m] = sd;
+                }
+                for (int m = 0; m < 6; ++m) {
+                    double sd = t[m];
+                    for (int n = 0; n < m; ++n) sd -= Ls[6 * m + n] * t[n];
+                    t[m] = sd / Ls[7 * m];
+                    if (col < 12) Wb[12 * m + col] = t[m]; else w.sv[m] = t[m];
+                }
             }
         }
         cx.sync();
-        double pmin = 1e300, pmaxv = 0.0;
+        LMH_FOR(it, 13 * 12) {        // A = wF T + W'W + eps I ; rhs row = W' sv
+            const int i = it / 12, j = it % 12;
+            double sd = 0.0;
+            if (i < 12) {
+                if (j <= i) {
+                    for (int m = 0; m < 6; ++m) sd += Wb[12 * m + i] * Wb[12 * m + j];
+                    if (i / 6 == j / 6) sd += K.wForce * Pm[36 * (i / 6) + 6 * (i % 6) + (j % 6)];
+                    if (i == j) sd += K.epsC;
+                    Ay[13 * i + j] = sd;
+                }
+            } else {
+                for (int m = 0; m < 6; ++m) sd += Wb[12 * m + j] * w.sv[m];
+                Ay[13 * 12 + j] = sd;
+            }
+        }
+        cx.sync();
+        bool solved = false;
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32 && LMH_WARP_WRENCH) { wrench_solve_warp(w, cx.tid); solved = true; }
+#endif
+        if (!solved) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -1166,7 +1057,6 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             }
             cx.sync();
             double pv = Ay[13 * k + k];
-            pmin = fmin(pmin, pv); pmaxv = fmax(pmaxv, pv);
             double dk = sqrt(pv > 0.0 ? pv : 1e-300);
             LMH_FOR(i0, 13 - k) {
                 int i = k + i0;
@@ -1175,11 +1065,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             }
             cx.sync();
         }
-        if (!(pmin > 1e-7 * pmaxv)) { fallback = true; break; }     // P_F lost rank: the wrench-space system is unreliable
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        for (int k = 11; k >= 0; --k) {        // L' y = z (row 12 of Ay), column oriented
+        for (int k = 11; k >= 0; --k) {        // L' zeta = z (row 12 of Ay), column oriented
             double xk = Ay[13 * 12 + k] / w.piv[k];
             cx.sync();
             LMH_FOR(i, k + 1) {
@@ -1188,33 +1077,117 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             }
             cx.sync();
         }
+        }
+        const double* zeta = Ay + 13 * 12;
+        if (!have_point) {
+            // all free: y = B T^-1 zeta with the constant matrix B T^-1; no working set, so no multipliers to look at
+            LMH_FOR(it, 12) {
+                const int f = it / 6, i = it % 6;
+                double sy = 0.0;
+                for (int k = 0; k < 6; ++k) sy += K.BTiall[6 * i + k] * zeta[6 * f + k];
+                vv[12 + it] = sy;
+                vv[24 + it] = 0.0;
+            }
+            cx.sync();
+        } else {
+        LMH_FOR(it, 14) {
+            if (it < 12) {            // f = B zeta
+                const int f = it / 6;
+                double sd = 0.0;
+                for (int k = 0; k < 6; ++k) sd += Bm[6 * it + k] * zeta[6 * f + k];
+                w.f12[it] = sd;
+            } else {                  // u = T^-1 zeta per foot (unit diagonal on the columns beyond the rank)
+                const int f = it - 12;
+                double A6[36], u[6];
+                LMH_UNROLL
+                for (int e = 0; e < 36; ++e) A6[e] = Pm[36 * f + e];
+                LMH_UNROLL
+                for (int k = 0; k < 6; ++k) if (A6[7 * k] == 0.0) A6[7 * k] = 1.0;
+                chol6(A6);
+                LMH_UNROLL
+                for (int r = 0; r < 6; ++r) {
+                    double sd = zeta[6 * f + r];
+                    LMH_UNROLL
+                    for (int m = 0; m < r; ++m) sd -= A6[6 * r + m] * u[m];
+                    u[r] = sd / A6[7 * r];
+                }
+                LMH_UNROLL
+                for (int r = 5; r >= 0; --r) {
+                    double sd = u[r];
+                    LMH_UNROLL
+                    for (int m = r + 1; m < 6; ++m) sd -= A6[6 * m + r] * u[m];
+                    u[r] = sd / A6[7 * r];
+                }
+                LMH_UNROLL
+                for (int r = 0; r < 6; ++r) vv[6 * f + r] = u[r];
+            }
+        }
+        cx.sync();
+        {
+            // lam = Sa^-1 (rhs - Jb'f) in every thread; y = B u; r = wF f - Jb lam
+            double l[6];
+            LMH_UNROLL
+            for (int r = 0; r < 6; ++r) {
+                double sd = w.rhs[r];
+                LMH_UNROLL
+                for (int k = 0; k < 12; ++k) sd -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
+                l[r] = sd;
+            }
+            LMH_UNROLL
+            for (int r = 0; r < 6; ++r) {
+                double sd = l[r];
+                LMH_UNROLL
+                for (int m = 0; m < r; ++m) sd -= Ls[6 * r + m] * l[m];
+                l[r] = sd / Ls[7 * r];
+            }
+            LMH_UNROLL
+            for (int r = 5; r >= 0; --r) {
+                double sd = l[r];
+                LMH_UNROLL
+                for (int m = r + 1; m < 6; ++m) sd -= Ls[6 * m + r] * l[m];
+                l[r] = sd / Ls[7 * r];
+            }
+            LMH_FOR(it, 12) {
+                const int f = it / 6;
+                double sy = 0.0, sj = 0.0;
+                for (int k = 0; k < 6; ++k) sy += Bm[6 * it + k] * vv[6 * f + k];
+                for (int r = 0; r < 6; ++r) sj += w.JFc[72 * f + 12 * (it % 6) + r] * l[r];
+                vv[12 + it] = sy;
+                vv[24 + it] = K.wForce * w.f12[it] - sj;
+            }
+        }
+        cx.sync();
+        }
         LMH_FOR(i, NC) {
-            int foot = i / 16, gi = i % 16;
-            double sc = 0.0;
-            for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * Ay[13 * 12 + 6 * foot + k];
-            w.mu[i] = sc;                              // g_i'y : coefficient if free, -multiplier/eps if not
+            const int foot = i / 16, gi = i % 16;
+            double sc = 0.0, sm = 0.0;
+            for (int k = 0; k < 6; ++k) { sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k]; sm += K.Gf[16 * k + gi] * vv[24 + 6 * foot + k]; }
             w.cs[i] = w.free_mask[i] ? sc : 0.0;
+            w.mu[i] = sm;                              // multiplier of c_i >= 0 (meaningful on the working set)
         }
         cx.sync();
         // decisions: every thread reaches the same ones (warp reductions for one warp per env, else redundant loops)
         bool done = false;
         int change = -1, to_free = 0;
         double alpha = 1.0;
+        // multipliers come out of the cancellation wF f - Jb lam: anything below the round-off of those two terms is
+        // zero (such coefficients only move c inside the null space of G, which no output depends on)
+        double rmax = 1.0;
+        for (int k = 0; k < 12; ++k) rmax = fmax(rmax, fabs(K.wForce * w.f12[k]) + fabs(vv[24 + k]));
+        const double mu_tol = -2e-10 * rmax;
 #if defined(__CUDA_ARCH__)
         if (Cx::NT == 32) {
             const int i = cx.tid;
             const bool fr = w.free_mask[i] != 0;
             const double csi = w.cs[i], mui = w.mu[i], ci = w.c[i];
             const double cmin = warp_min(fr && csi < 0.0 ? csi : 0.0);
-            const double cmax = warp_max(fmax(1.0, fabs(csi)));
             if (!have_point) {
                 have_point = true;
                 if (cmin >= 0.0) done = true; else alpha = -1.0;
             } else if (cmin >= 0.0) {
-                const double thr = 1e-10 * cmax;
-                const bool cand = !fr && mui > thr;
-                const double vmax = warp_max(cand ? mui : -1e300);
-                const unsigned hit = __ballot_sync(0xffffffffu, cand && mui == vmax);
+                const bool cand = !fr && mui < mu_tol;
+                const double vmin = warp_min(cand ? mui : 1e300);
+                const unsigned hit = __ballot_sync(0xffffffffu, cand && mui == vmin);
                 if (hit == 0u) done = true; else { change = __ffs(hit) - 1; to_free = 1; }
             } else {
                 const bool cand = fr && csi < 0.0;
@@ -1228,18 +1201,15 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         } else
 #endif
         {
-        double cmin = 0.0, cmax = 1.0;
-        for (int i = 0; i < NC; ++i) {
-            if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
-            cmax = fmax(cmax, fabs(w.cs[i]));
-        }
+        double cmin = 0.0;
+        for (int i = 0; i < NC; ++i) if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
         if (!have_point) {
             have_point = true;
             if (cmin >= 0.0) done = true;              // the all-free minimiser is feasible: optimal
             else alpha = -1.0;                         // project onto the orthant; working set = the clipped coefficients
         } else if (cmin >= 0.0) {
-            double worst = 1e-10 * cmax;
-            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] > worst) { worst = w.mu[i]; change = i; }
+            double worst = mu_tol;
+            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
             if (change < 0) done = true; else to_free = 1;
         } else {
             double best = 2.0;
@@ -1252,6 +1222,12 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             alpha = best < 1.0 ? best : 1.0;
         }
         }
+#if defined(LMH_DEBUG_QP) && !defined(__CUDA_ARCH__)
+        if (iters < 8) {
+            int nf = 0; double cm = 0; for (int i = 0; i < NC; ++i) { nf += w.free_mask[i]; if (w.free_mask[i] && w.cs[i] < cm) cm = w.cs[i]; }
+            printf("it %d nfree %d cmin %.3e alpha %.3e change %d to_free %d done %d mu_tol %.2e mu[change] %.3e\n", iters, nf, cm, alpha, change, to_free, (int)done, mu_tol, change >= 0 ? w.mu[change] : 0.0);
+        }
+#endif
         cx.sync();
         LMH_FOR(i, NC) {
             if (alpha < 0.0) {
@@ -1272,8 +1248,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         if (done) break;
         if (iters >= K.qp_max_iter) { status = 1; break; }
     }
-    w.qp_fallback = fallback ? 1 : 0;
-    if (fallback) qp_cspace_fallback(cx, w, K, Ls, gscratch, iters, status);
+    w.qp_fallback = iters > 1 ? 1 : 0;     // stages whose all-free solution was infeasible (contact-limited)
     w.qp_iters = iters;
     w.qp_status = status;
     // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12)

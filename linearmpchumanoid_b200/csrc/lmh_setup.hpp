@@ -219,6 +219,26 @@ private:
                 for (int k = 0; k < 16; ++k) s += K.Gf[16 * i + k] * K.Gf[16 * j + k];
                 K.GGt[6 * i + j] = s;
             }
+        {   // all-free wrench basis: GGt = B B' (plain Cholesky: full rank), T = B'B
+            double B[36];
+            for (int e = 0; e < 36; ++e) B[e] = K.GGt[e];
+            chol6(B);
+            for (int i = 0; i < 6; ++i) for (int j = i + 1; j < 6; ++j) B[6 * i + j] = 0.0;
+            for (int e = 0; e < 36; ++e) K.Ball[e] = B[e];
+            for (int k = 0; k < 6; ++k)
+                for (int l = 0; l < 6; ++l) {
+                    double t = 0;
+                    for (int i = 0; i < 6; ++i) t += B[6 * i + k] * B[6 * i + l];
+                    K.Tall[6 * k + l] = t;
+                }
+            // B T^-1 : solve T X' = B' column by column
+            for (int i = 0; i < 6; ++i) {
+                std::vector<double> Tm(K.Tall, K.Tall + 36), rhs(6), x(6);
+                for (int k = 0; k < 6; ++k) rhs[k] = B[6 * i + k];
+                dense_solve(6, Tm, rhs, x.data());
+                for (int k = 0; k < 6; ++k) K.BTiall[6 * i + k] = x[k];
+            }
+        }
     }
 
     // u0 = -e0' H^-1 beta Pu' (Px x - z)  with H = alpha I + beta Pu'Pu constant  =>  gain vector r = beta Pu H^-1 e0

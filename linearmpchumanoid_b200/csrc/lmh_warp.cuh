@@ -379,6 +379,43 @@ __device__ void jacobian_warp(EnvWS& w, int lane) {
     __syncwarp();
 }
 
+
+// ---- 12 x 12 wrench-space system for one warp: lane i < 12 owns row i of A (w.u.s.Ay, lower triangle), lane 12 the
+// right-hand-side row; left-looking Cholesky with the forward substitution riding along, then the back
+// substitution with lane i holding zeta_i.  Result in row 12 of Ay, as the generic loops leave it.
+__device__ void wrench_solve_warp(EnvWS& w, int lane) {
+    double* Ay = w.u.s.Ay;
+    double h[12];
+    const bool row = lane < 13;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) h[j] = (row && (j <= lane)) ? Ay[13 * lane + j] : 0.0;
+    double myinv = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        double s = h[k];
+        const double* Lk = Ay + 13 * k;
+#pragma unroll
+        for (int m = 0; m < k; ++m) s -= h[m] * Lk[m];
+        const double piv = __shfl_sync(0xffffffffu, s, k);
+        const double rs = rsqrt(piv > 0.0 ? piv : 1e-300);
+        const double lik = lane == k ? piv * rs : s * rs;
+        h[k] = lik;
+        if (lane == k) myinv = rs;
+        if (lane > k && row) Ay[13 * lane + k] = lik;
+        __syncwarp();
+    }
+    double zi = lane < 12 ? Ay[13 * 12 + lane] : 0.0;
+#pragma unroll
+    for (int k = 11; k >= 0; --k) {
+        const double xk = __shfl_sync(0xffffffffu, zi * myinv, k);
+        if (lane == k) zi = xk;
+        else if (lane < k) zi -= Ay[13 * k + lane] * xk;
+    }
+    __syncwarp();
+    if (lane < 12) Ay[13 * 12 + lane] = zi;
+    __syncwarp();
+}
+
 // ---- QP front end for one warp (see assemble_phase / qp_phase of lmh_model.cuh for the algebra): lane i < 18 owns
 // row i of D1 = Wj + wFoot JF'JF, lanes 18..27 own the ten right-hand-side rows [M6; ga'; U]; rows are assembled
 // straight into registers and the left-looking Cholesky runs on them, reading the finished part of row k back from
