@@ -36,7 +36,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_ENV_STEP = 0.51e6          # SURVEY.md 8(d) / App. C, active-set changes k = 0 (conservative)
-STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 40 + 24   # state read+write, stats, CoM per launch
+STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 48 + 24   # state read+write, stats, CoM per launch
+# dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel from the committed ncu --set full capture (E = 4096;
+# the traffic of a launch does not depend on the number of steps it fuses: the state stays on chip)
+NCU_DRAM_BYTES_PER_LAUNCH = None
+NCU_TRAFFIC_SOURCE = None
 
 
 # ---------------------------------------------------------------- distributed helpers (also unit-tested with gloo)
@@ -169,7 +173,7 @@ def run_reference_arm(args):
                              "sample": f"first {n_env} envs x {S} RK4 steps per bench step, {cores} host threads", "note": note},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -276,6 +280,11 @@ def run_ours(args):
     gather_ms = 1e3 * (time.perf_counter() - tg)
 
     if rank == 0:
+        # batch-1 step latency (BASELINE metric, config 1): one environment, fused rollout, device time per RK4 step
+        b1 = lmh.Batch(1, device=local_rank, threads_per_env=args.threads_per_env)
+        b1.step(20)
+        lat_us = min(b1.step_timed(200) for _ in range(3)) / 200 * 1e3
+        b1.close()
         fp64_tf, sm_mhz_attr, sms = lmh.measure_fp64_peak(local_rank)
         peaks = {}
         try:
@@ -301,10 +310,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": launches,
+            "batch1_step_latency_us": lat_us,
             "wall_ms_timed_region": wall_ms,
             "gather_ms": gather_ms,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,
-                         "traffic": None, "kernel": "rollout_kernel", "kernel_ms_per_launch": kern,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE, "kernel": "rollout_kernel", "kernel_ms_per_launch": kern,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
                          "peak_source": "FP64 FMA micro-kernel measured in this run (lmh_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
@@ -334,7 +344,7 @@ def run_ours(args):
                                     "sample": f"first {n_cpu} envs of the workload x {s_cpu} RK4 steps, {cores} host threads, {dtc:.1f} s",
                                     "note": "oracle port: one WBC solve per stage, cached MPC factor, -O2, no sanitizers",
                                     "max_abs_state_diff_vs_gpu": float(np.abs(xg - x_cpu).max())}
-        print(json.dumps(line))
+        _emit(line)
     b.close()
     if world > 1:
         dist.barrier()
@@ -342,7 +352,18 @@ def run_ours(args):
     return 0
 
 
+def _emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                   # libraries that print to stdout (NCCL version banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
