@@ -35,6 +35,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOADS = {"push": "NAO balance under random push perturbations (BASELINE configs[1])",
+             "walk": "NAO LIPM-MPC walking, random footstep plans, 1.6 s horizon (BASELINE configs[2]; extension: upstream has no walking)",
+             "sweep": "NAO walking robustness Monte Carlo: footstep plans + pushes (BASELINE configs[3]; extension)"}
 FLOP_PER_ENV_STEP = 0.51e6          # SURVEY.md 8(d) / App. C, active-set changes k = 0 (conservative)
 STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 48 + 24   # state read+write, stats, CoM per launch
 # dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel from the committed ncu --set full capture (E = 4096;
@@ -196,9 +199,16 @@ def run_ours(args):
 
     E, S, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 0)
     lo = rank * E                                             # weak scaling: E envs per GPU, global ids lo..lo+E
-    b = lmh.Batch(E, device=local_rank, threads_per_env=args.threads_per_env)
+    walk = args.workload in ("walk", "sweep")
+    b = lmh.Batch(E, device=local_rank, threads_per_env=args.threads_per_env, **({"time_horizon": 1.6} if walk else {}))
     q0, zcom, mass, _ = b.nominal()
-    push_step, push_dv = lmh.push_plan(range(lo, lo + E))
+    if walk:      # configs 3-4 (EXTENSION: the reference has no walking): per-env footstep plans, 1.6 s MPC horizon
+        wp = lmh.walk_plan(range(lo, lo + E))
+        b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"], plan_ids=np.arange(E))
+    if args.workload in ("push", "sweep"):
+        push_step, push_dv = lmh.push_plan(range(lo, lo + E), seed=0x5EED0002 if args.workload == "push" else 0x5EED0004)
+    else:
+        push_step, push_dv = np.full(E, -1, np.int32), np.zeros((E, 6))
     b.set_pushes(push_step, push_dv)
 
     # initial state: pinned host copy (e2e leg) and device-resident template (value leg)
@@ -302,9 +312,10 @@ def run_ours(args):
             "metric": "closed-loop env-steps/sec (NAO, FP64)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": max(W, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "NAO balance under random push perturbations (BASELINE configs[1])",
+            "config": {"workload": WORKLOADS[args.workload],
                        "envs_per_gpu": E, "rk4_steps_per_rollout": S, "stage_evals_per_env_step": 4, "seed": "0x5EED0002",
-                       "push": "U(0,0.25) m/s on base v_xy at step U{0..50}", "mpc_horizon": 50, "dt": 0.01,
+                       "push": "U(0,0.25) m/s on base v_xy at step U{0..50}" if args.workload != "walk" else "none",
+                       "mpc_horizon": 160 if walk else 50, "dt": 0.01,
                        "threads_per_env": info["threads_per_env"], "smem_bytes_per_env": info["smem_bytes"],
                        "l2": "flushed (256 MiB write) before every timed rollout; working set is on-chip"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -325,7 +336,7 @@ def run_ours(args):
                               "qp_iters_per_stage": float(all_stats[:, 3].sum() / (all_stats[:, 5].sum() * 4.0)),
                               "max_abs_tau": float(all_stats[:, 0].max()), "max_com_err": float(all_stats[:, 1].max())},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "push":
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import orc_py
             orc_py.build()
@@ -372,6 +383,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--rollout", type=int, default=200, help="RK4 steps per rollout (= per bench step)")
     ap.add_argument("--threads-per-env", type=int, default=0)
+    ap.add_argument("--workload", default="push", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     return run_reference_arm(args) if args.impl == "reference" else run_ours(args)

@@ -59,7 +59,8 @@ typedef struct {
     double xdot[60];
     int32_t k_index;       /* (int)(t/dt), mpcLinearPendulum.cpp:92 */
     int32_t qp_status;     /* 0 ok, 1 iteration limit */
-    int32_t qp_iters, pad;
+    int32_t qp_iters;
+    int32_t phase;         /* walking extension: min((int)(t/phase_T), n_phases-1) */
 } LmhStageDump;
 
 /* One record per environment and step when logging is on. */
@@ -103,6 +104,13 @@ int32_t lmh_get_link_tables(const LmhBatch* h, double* mass28, double* com28x3, 
  * x(6) y(6) z(8) per foot, ascending powers.  plan_ids (or NULL = 0) selects one per env. */
 int32_t lmh_set_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zmp_x, const double* zmp_y,
                       const double* foot_coef, const int32_t* plan_ids);
+/* EXTENSION (walking; upstream declares walkZMP but never defines it, zmpGeneration.hpp:15-22): plans with phases.
+ * Phase p = min((int)(t/phase_T), n_phases-1) selects foot_coef [n_plans][n_phases][2][20] (polynomials in the
+ * phase-local time t - p*phase_T) and contact [n_plans][n_phases] (bit 0 right foot, bit 1 left foot may carry
+ * force; a swing foot's 16 contact coefficients are held at zero).  lmh_set_plans == one phase, both feet. */
+int32_t lmh_set_walk_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zmp_x, const double* zmp_y,
+                           int32_t n_phases, double phase_T, const double* foot_coef, const int32_t* contact,
+                           const int32_t* plan_ids);
 int32_t lmh_get_plan(const LmhBatch* h, int32_t plan, double* zmp_x, double* zmp_y, int32_t cap, int32_t* zmp_len, double* foot_coef40);
 
 /* State: x [n_env][60] = [q; v]; v_held [n_env][30] = velocity the Robot object still holds from the

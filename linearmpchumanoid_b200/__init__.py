@@ -3,4 +3,4 @@ Ema158/linearMpcHumanoid).  The compute path is liblmh_b200.so (hand-written sm_
 C ABI in include/lmh_capi.h); this package is the Python binding plus the scenario generators."""
 from .api import (Batch, LmhError, load_library, build_library, measure_fp64_peak,  # noqa: F401
                   STAGE_DTYPE, STEPLOG_DTYPE, STATS_DTYPE, SYMBOLS, LIB_PATH)
-from .scenarios import push_plan, shard_range  # noqa: F401
+from .scenarios import push_plan, shard_range, walk_plan, foot_coefficients  # noqa: F401

@@ -31,7 +31,7 @@ STAGE_DTYPE = np.dtype([("M", "f8", (30, 30)), ("C", "f8", 30), ("Cg", "f8", 30)
                         ("qppRef", "f8", 30), ("hGpRef", "f8", 6), ("footAccRef", "f8", 12), ("Ha", "f8", (30, 30)),
                         ("ga", "f8", 30), ("a", "f8", 30), ("f", "f8", 12), ("c", "f8", 32), ("lam", "f8", 6),
                         ("qpp", "f8", 30), ("tau", "f8", 24), ("T7", "f8", 12), ("T14", "f8", 12), ("xdot", "f8", 60),
-                        ("k_index", "i4"), ("qp_status", "i4"), ("qp_iters", "i4"), ("pad", "i4")])
+                        ("k_index", "i4"), ("qp_status", "i4"), ("qp_iters", "i4"), ("phase", "i4")])
 STEPLOG_DTYPE = np.dtype([("com_k4", "f8", 3), ("rfoot", "f8", 3), ("lfoot", "f8", 3), ("tau_k1", "f8", 24),
                           ("k_index", "i4", 4), ("qp_iters", "i4"), ("qp_fail", "i4")])
 STATS_DTYPE = np.dtype([("max_abs_tau", "f8"), ("max_com_err", "f8"), ("max_abs_qpp", "f8"), ("qp_iters", "i4"),
@@ -39,7 +39,7 @@ STATS_DTYPE = np.dtype([("max_abs_tau", "f8"), ("max_com_err", "f8"), ("max_abs_
 
 # every symbol include/lmh_capi.h declares (checked by the CPU test-suite against the built library)
 SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", "lmh_n_env", "lmh_get_nominal",
-           "lmh_get_mpc_gain", "lmh_get_link_tables", "lmh_set_plans", "lmh_get_plan", "lmh_set_state",
+           "lmh_get_mpc_gain", "lmh_get_link_tables", "lmh_set_plans", "lmh_set_walk_plans", "lmh_get_plan", "lmh_set_state",
            "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
            "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
            "lmh_stats_dev", "lmh_set_state_dev", "lmh_reset_stats", "lmh_timer_start", "lmh_timer_stop",
@@ -83,6 +83,7 @@ def load_library():
     L.lmh_get_mpc_gain.argtypes = [vp, vp, _i32, vp, vp]
     L.lmh_get_link_tables.argtypes = [vp, vp, vp, vp]
     L.lmh_set_plans.argtypes = [vp, _i32, _i32, vp, vp, vp, vp]
+    L.lmh_set_walk_plans.argtypes = [vp, _i32, _i32, vp, vp, _i32, _f64, vp, vp, vp]
     L.lmh_get_plan.argtypes = [vp, _i32, vp, vp, _i32, vp, vp]
     L.lmh_set_state.argtypes = [vp, vp, vp, vp]
     L.lmh_get_state.argtypes = [vp, vp, vp, vp]
@@ -189,6 +190,16 @@ class Batch:
         fc = np.ascontiguousarray(foot_coef, np.float64).reshape(zx.shape[0], 40)
         ids = None if plan_ids is None else np.ascontiguousarray(plan_ids, np.int32)
         _chk(self.L, self.L.lmh_set_plans(self.h, zx.shape[0], zx.shape[1], _p(zx), _p(zy), _p(fc), _p(ids)))
+
+    def set_walk_plans(self, zmp_x, zmp_y, phase_T, foot_coef, contact, plan_ids=None):
+        """EXTENSION (walking): zmp_x/zmp_y [n_plans][len]; foot_coef [n_plans][n_phases][2][20]; contact [n_plans][n_phases]"""
+        zx = np.ascontiguousarray(np.atleast_2d(zmp_x), np.float64)
+        zy = np.ascontiguousarray(np.atleast_2d(zmp_y), np.float64)
+        ct = np.ascontiguousarray(contact, np.int32).reshape(zx.shape[0], -1)
+        fc = np.ascontiguousarray(foot_coef, np.float64).reshape(zx.shape[0], ct.shape[1], 40)
+        ids = None if plan_ids is None else np.ascontiguousarray(plan_ids, np.int32)
+        _chk(self.L, self.L.lmh_set_walk_plans(self.h, zx.shape[0], zx.shape[1], _p(zx), _p(zy), ct.shape[1], float(phase_T),
+                                               _p(fc), _p(ct), _p(ids)))
 
     # ---- state
     def reset(self):

@@ -137,8 +137,11 @@ struct LmhBatch {
     std::vector<LmhStats> h_stats0;
     LmhStepLog* d_log = nullptr;
     LmhStageDump* d_dump = nullptr;
-    int32_t n_plans = 1, zmp_len = 0, step_counter = 0, launches = 0;
+    int32_t n_plans = 1, zmp_len = 0, step_counter = 0, launches = 0, n_phases = 1;
+    double phase_T = 1e30;
+    int32_t* d_contact = nullptr;
     std::vector<double> h_zmp_x, h_zmp_y, h_foot;
+    std::vector<int32_t> h_contact;
     bool has_pushes = false, has_plan_ids = false;
 };
 
@@ -148,6 +151,7 @@ Params make_params(LmhBatch* h) {
     Params p;
     p.K = h->dK;
     p.plan.zmp_x = h->d_zmp_x; p.plan.zmp_y = h->d_zmp_y; p.plan.foot_coef = h->d_foot; p.plan.zmp_len = h->zmp_len;
+    p.plan.contact = h->d_contact; p.plan.n_phases = h->n_phases; p.plan.phase_T = h->phase_T;
     p.plan_id = h->has_plan_ids ? h->d_plan_id : nullptr;
     p.x = h->d_x; p.vh = h->d_vh; p.t = h->d_t;
     p.push_step = h->has_pushes ? h->d_push_step : nullptr;
@@ -165,10 +169,12 @@ int32_t configure_kernels(int smem) {
 }
 
 int32_t upload_plans(LmhBatch* h) {
-    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot);
-    h->d_zmp_x = h->d_zmp_y = h->d_foot = nullptr;
-    size_t nz = (size_t)h->n_plans * h->zmp_len * sizeof(double), nf = (size_t)h->n_plans * 40 * sizeof(double);
-    CU(cudaMalloc(&h->d_zmp_x, nz)); CU(cudaMalloc(&h->d_zmp_y, nz)); CU(cudaMalloc(&h->d_foot, nf));
+    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact);
+    h->d_zmp_x = h->d_zmp_y = h->d_foot = nullptr; h->d_contact = nullptr;
+    size_t nz = (size_t)h->n_plans * h->zmp_len * sizeof(double), nf = (size_t)h->n_plans * h->n_phases * 40 * sizeof(double);
+    size_t nc = (size_t)h->n_plans * h->n_phases * sizeof(int32_t);
+    CU(cudaMalloc(&h->d_zmp_x, nz)); CU(cudaMalloc(&h->d_zmp_y, nz)); CU(cudaMalloc(&h->d_foot, nf)); CU(cudaMalloc(&h->d_contact, nc));
+    CU(cudaMemcpyAsync(h->d_contact, h->h_contact.data(), nc, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_zmp_x, h->h_zmp_x.data(), nz, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_zmp_y, h->h_zmp_y.data(), nz, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_foot, h->h_foot.data(), nf, cudaMemcpyHostToDevice, h->stream));
@@ -251,6 +257,7 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     h->n_plans = 1;
     h->zmp_len = (int32_t)h->hm->zmp_x.size();
     h->h_zmp_x = h->hm->zmp_x; h->h_zmp_y = h->hm->zmp_y; h->h_foot = h->hm->foot_coef;
+    h->h_contact.assign(1, 3);
     rc = upload_plans(h);
     if (rc != LMH_OK) return rc;
     *out = h;
@@ -263,7 +270,7 @@ void lmh_destroy(LmhBatch* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com); cudaFree(h->d_qp_scratch);
     cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
-    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot);
+    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -302,18 +309,23 @@ int32_t lmh_get_link_tables(const LmhBatch* h, double* mass, double* com, double
     return LMH_OK;
 }
 
-int32_t lmh_set_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zx, const double* zy,
-                      const double* foot, const int32_t* plan_ids) {
-    if (!h || n_plans <= 0 || zmp_len < h->hm->K.mpc_n1 || !zx || !zy || !foot)
-        return fail(LMH_EINVAL, "lmh_set_plans: bad arguments (zmp_len must cover horizon+1 samples)");
+int32_t lmh_set_walk_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zx, const double* zy,
+                           int32_t n_phases, double phase_T, const double* foot, const int32_t* contact,
+                           const int32_t* plan_ids) {
+    if (!h || n_plans <= 0 || zmp_len < h->hm->K.mpc_n1 || !zx || !zy || !foot || n_phases <= 0 || !(phase_T > 0) || !contact)
+        return fail(LMH_EINVAL, "lmh_set_walk_plans: bad arguments (zmp_len must cover horizon+1 samples)");
     CU(cudaSetDevice(h->cfg.device));
     if (plan_ids)
         for (int e = 0; e < h->n_env; ++e)
-            if (plan_ids[e] < 0 || plan_ids[e] >= n_plans) return fail(LMH_EINVAL, "lmh_set_plans: plan id out of range");
-    h->n_plans = n_plans; h->zmp_len = zmp_len;
+            if (plan_ids[e] < 0 || plan_ids[e] >= n_plans) return fail(LMH_EINVAL, "lmh_set_walk_plans: plan id out of range");
+    for (int i = 0; i < n_plans * n_phases; ++i)
+        if (contact[i] < 0 || contact[i] > 3) return fail(LMH_EINVAL, "lmh_set_walk_plans: contact masks are 0..3");
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_plans = n_plans; h->zmp_len = zmp_len; h->n_phases = n_phases; h->phase_T = phase_T;
     h->h_zmp_x.assign(zx, zx + (size_t)n_plans * zmp_len);
     h->h_zmp_y.assign(zy, zy + (size_t)n_plans * zmp_len);
-    h->h_foot.assign(foot, foot + (size_t)n_plans * 40);
+    h->h_foot.assign(foot, foot + (size_t)n_plans * n_phases * 40);
+    h->h_contact.assign(contact, contact + (size_t)n_plans * n_phases);
     int32_t rc = upload_plans(h);
     if (rc != LMH_OK) return rc;
     h->has_plan_ids = plan_ids != nullptr;
@@ -324,6 +336,13 @@ int32_t lmh_set_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const doubl
     return LMH_OK;
 }
 
+int32_t lmh_set_plans(LmhBatch* h, int32_t n_plans, int32_t zmp_len, const double* zx, const double* zy,
+                      const double* foot, const int32_t* plan_ids) {
+    if (n_plans <= 0) return fail(LMH_EINVAL, "lmh_set_plans: bad arguments");
+    std::vector<int32_t> both((size_t)n_plans, 3);
+    return lmh_set_walk_plans(h, n_plans, zmp_len, zx, zy, 1, 1e30, foot, both.data(), plan_ids);
+}
+
 int32_t lmh_get_plan(const LmhBatch* h, int32_t plan, double* zx, double* zy, int32_t cap, int32_t* zmp_len, double* foot40) {
     if (!h || plan < 0 || plan >= h->n_plans) return fail(LMH_EINVAL, "lmh_get_plan: bad arguments");
     if (zmp_len) *zmp_len = h->zmp_len;
@@ -331,7 +350,7 @@ int32_t lmh_get_plan(const LmhBatch* h, int32_t plan, double* zx, double* zy, in
         if (zx) zx[i] = h->h_zmp_x[(size_t)plan * h->zmp_len + i];
         if (zy) zy[i] = h->h_zmp_y[(size_t)plan * h->zmp_len + i];
     }
-    if (foot40) std::memcpy(foot40, h->h_foot.data() + (size_t)plan * 40, 40 * sizeof(double));
+    if (foot40) std::memcpy(foot40, h->h_foot.data() + (size_t)plan * h->n_phases * 40, 40 * sizeof(double));   // phase 0
     return LMH_OK;
 }
 

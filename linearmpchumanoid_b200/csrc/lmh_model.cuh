@@ -95,8 +95,11 @@ struct Consts {
 struct Plan {
     const double* zmp_x;      // [n_plans][zmp_len]
     const double* zmp_y;
-    const double* foot_coef;  // [n_plans][2 feet][20] : x(6) y(6) z(8), ascending powers (footRefTrajectory.cpp:4-47)
-    int32_t zmp_len;
+    const double* foot_coef;  // [n_plans][n_phases][2 feet][20] : x(6) y(6) z(8), ascending powers of the phase-local
+                              // time (footRefTrajectory.cpp:4-47)
+    const int32_t* contact;   // [n_plans][n_phases] : bit 0 right foot, bit 1 left foot may carry force
+    double phase_T;           // phase p = min((int)(t/phase_T), n_phases-1).  EXTENSION: upstream has one phase (stand).
+    int32_t zmp_len, n_phases;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -125,6 +128,7 @@ struct EnvWS {
     int32_t free_mask[NC];
     int32_t pdone[12], ppiv[2];
     int32_t k_index, qp_iters, qp_status, qp_fallback;
+    int32_t phase, contact;        // walking extension: phase index and contact mask of this stage
     // ---- phase-overlaid scratch
     union {
         struct {                       // model phase
@@ -202,6 +206,16 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 #endif
+
+// a + b*c with the product rounded before the sum, as the reference's (unfused) CPU arithmetic does
+LMH_HD double mul_then_add(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, __dmul_rn(b, c));
+#else
+    volatile double p = b * c;
+    return a + p;
+#endif
+}
 
 // in-place Cholesky of a 6x6 SPD matrix held in registers (lower triangle), fully unrolled
 LMH_HD void chol6(double* A) {
@@ -737,6 +751,11 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
             w.hGpRef[k] = K.mass * (K.KpM * (pr - w.com[j]) + K.KdM * (vr - w.comVel[j]) + ar);
         }
     }
+    // walking extension: phase of this stage (integer work, same FP64 expression as the oracle)
+    int ph = (int)(w.t / P.phase_T);
+    ph = ph < 0 ? 0 : (ph >= P.n_phases ? P.n_phases - 1 : ph);
+    const double tl = mul_then_add(w.t, -(double)ph, P.phase_T);
+    LMH_FOR(i, 1) { w.phase = ph; w.contact = P.contact[(size_t)plan_id * P.n_phases + ph]; }
     // feet (controller.cpp:329-386)
     LMH_FOR(it, 12) {
         int s = it / 6, k = it % 6;
@@ -762,12 +781,12 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
             out = K.KpF * eo + K.KdF * (0.0 - velk) + 0.0;
         } else {
             int j = k - 3;
-            const double* cf = P.foot_coef + ((size_t)plan_id * 2 + s) * 20 + (j == 0 ? 0 : j == 1 ? 6 : 12);
+            const double* cf = P.foot_coef + (((size_t)plan_id * P.n_phases + ph) * 2 + s) * 20 + (j == 0 ? 0 : j == 1 ? 6 : 12);
             int nc = j == 2 ? 8 : 6;
             double pos = 0.0, vr = 0.0, ar = 0.0, tp = 1.0, tv = 1.0, ta = 1.0;
-            for (int i = 0; i < nc; ++i) { pos += cf[i] * tp; tp *= w.t; }
-            for (int i = 1; i < nc; ++i) { vr += (double)i * cf[i] * tv; tv *= w.t; }
-            for (int i = 2; i < nc; ++i) { ar += (double)(i - 1) * ((double)i * cf[i]) * ta; ta *= w.t; }
+            for (int i = 0; i < nc; ++i) { pos += cf[i] * tp; tp *= tl; }
+            for (int i = 1; i < nc; ++i) { vr += (double)i * cf[i] * tv; tv *= tl; }
+            for (int i = 2; i < nc; ++i) { ar += (double)(i - 1) * ((double)i * cf[i]) * ta; ta *= tl; }
             out = K.KpF * (pos - w.ps[s][j]) + K.KdF * (vr - velk) + ar;
         }
         w.footAccRef[it] = out;
@@ -943,13 +962,15 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
     double* Wb = w.u.s.Wb;            // [6][12] : Ls^-1 Jb' B
     double* Ay = w.u.s.Ay;            // 13 x 13 : lower triangle factorised in place, row 12 = rhs / zeta
     double* vv = w.u.s.vv;            // [36]   : u = T^-1 zeta (12), y = B u (12), r = wF f - Jb lam (12)
-    LMH_FOR(i, NC) { w.free_mask[i] = 1; w.c[i] = 0.0; }
+    const int contact = w.contact;     // bit f: foot f may carry force (both set in the reference's stand task)
+    LMH_FOR(i, NC) { w.free_mask[i] = (contact >> (i / 16)) & 1; w.c[i] = 0.0; }
     cx.sync();
     int iters = 0, status = 0;
     bool have_point = false;
     while (true) {
         ++iters;
-        if (!have_point) {            // all free: B and T are constants of the foot geometry
+        const bool const_basis = !have_point && contact == 3;
+        if (const_basis) {            // all free: B and T are constants of the foot geometry
             LMH_FOR(it, 72) { Bm[it] = K.Ball[it % 36]; Pm[it] = K.Tall[it % 36]; }
             cx.sync();
         } else {
@@ -1079,7 +1100,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         }
         }
         const double* zeta = Ay + 13 * 12;
-        if (!have_point) {
+        if (const_basis) {
             // all free: y = B T^-1 zeta with the constant matrix B T^-1; no working set, so no multipliers to look at
             LMH_FOR(it, 12) {
                 const int f = it / 6, i = it % 6;
@@ -1185,7 +1206,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
                 have_point = true;
                 if (cmin >= 0.0) done = true; else alpha = -1.0;
             } else if (cmin >= 0.0) {
-                const bool cand = !fr && mui < mu_tol;
+                const bool cand = !fr && ((contact >> (i / 16)) & 1) && mui < mu_tol;
                 const double vmin = warp_min(cand ? mui : 1e300);
                 const unsigned hit = __ballot_sync(0xffffffffu, cand && mui == vmin);
                 if (hit == 0u) done = true; else { change = __ffs(hit) - 1; to_free = 1; }
@@ -1209,7 +1230,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             else alpha = -1.0;                         // project onto the orthant; working set = the clipped coefficients
         } else if (cmin >= 0.0) {
             double worst = mu_tol;
-            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
+            for (int i = 0; i < NC; ++i) if (!w.free_mask[i] && ((contact >> (i / 16)) & 1) && w.mu[i] < worst) { worst = w.mu[i]; change = i; }
             if (change < 0) done = true; else to_free = 1;
         } else {
             double best = 2.0;
@@ -1232,8 +1253,8 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         LMH_FOR(i, NC) {
             if (alpha < 0.0) {
                 double x = w.cs[i];
-                w.c[i] = x > 0.0 ? x : 0.0;
-                w.free_mask[i] = x > 0.0 ? 1 : 0;
+                w.c[i] = (x > 0.0 && ((contact >> (i / 16)) & 1)) ? x : 0.0;
+                w.free_mask[i] = (x > 0.0 && ((contact >> (i / 16)) & 1)) ? 1 : 0;
             } else {
                 double x = w.c[i] + alpha * (w.cs[i] - w.c[i]);
                 if (!w.free_mask[i]) x = 0.0;
@@ -1380,7 +1401,7 @@ LMH_HDN void dump_stage(const Cx& cx, const EnvWS& w, LmhStageDump* d) {
         d->CoM[i] = w.com[i]; d->comVel[i] = w.comVel[i]; d->comAngMom[i] = w.angMom[i];
         d->xRef[i] = w.xRef[i]; d->yRef[i] = w.yRef[i];
     }
-    LMH_FOR(i, 1) { d->k_index = w.k_index; d->qp_status = w.qp_status; d->qp_iters = w.qp_iters; d->pad = 0; }
+    LMH_FOR(i, 1) { d->k_index = w.k_index; d->qp_status = w.qp_status; d->qp_iters = w.qp_iters; d->phase = w.phase; }
     cx.sync();
 }
 
@@ -1426,16 +1447,6 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
     if (dump) dump_stage(cx, w, dump);
     LMH_FOR(i, NQ) w.vh[i] = w.v[i];     // Robot::updateVelocityState (Robot.cpp:271-274)
     cx.sync();
-}
-
-// a + b*c with the product rounded before the sum, as the reference's (unfused) CPU arithmetic does
-LMH_HD double mul_then_add(double a, double b, double c) {
-#if defined(__CUDA_ARCH__)
-    return __dadd_rn(a, __dmul_rn(b, c));
-#else
-    volatile double p = b * c;
-    return a + p;
-#endif
 }
 
 // Running statistics of one environment (kept by thread 0 of the group).

@@ -42,3 +42,64 @@ def shard_range(n_total, rank, world):
     lo = rank * per
     hi = n_total if rank == world - 1 else lo + per
     return lo, hi
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# EXTENSION: walking plans (BASELINE configs 3-4).  The reference declares ZMP::walkZMP but never defines it
+# (zmpGeneration.hpp:15-22) and has no contact switching; this is our definition.
+def _poly_fit(pt, pv, vt, vv, at, av):
+    """boundary-value polynomial, ascending powers (generalizedFunctions.cpp:103-163)"""
+    n = len(pt) + len(vt) + len(at)
+    A, b = np.zeros((n, n)), np.zeros(n)
+    row = 0
+    for t, v in zip(pt, pv):
+        A[row] = [t ** j for j in range(n)]; b[row] = v; row += 1
+    for t, v in zip(vt, vv):
+        A[row] = [0.0] + [j * t ** (j - 1) for j in range(1, n)]; b[row] = v; row += 1
+    for t, v in zip(at, av):
+        A[row] = [0.0, 0.0] + [j * (j - 1) * t ** (j - 2) for j in range(2, n)]; b[row] = v; row += 1
+    return np.linalg.solve(A, b)
+
+
+def foot_coefficients(cur, des, step_height, T):
+    """x(6) y(6) z(8) of one foot over one phase (footRefTrajectory.cpp:4-47)"""
+    t2, z2, t3, z3 = [0.0, T], [0.0, 0.0], [0.0, T / 2, T], [0.0, 0.0, 0.0]
+    x = _poly_fit(t2, [cur[0], des[0]], t2, z2, t2, z2)
+    y = _poly_fit(t2, [cur[1], des[1]], t2, z2, t2, z2)
+    z = _poly_fit(t3, [cur[2], step_height, des[2]], t3, z3, t2, z2)
+    return np.concatenate([x, y, z])
+
+
+def walk_plan(env_ids, seed=0x5EED0003, n_footsteps=4, time_per_step=0.4, dt=0.01, horizon_steps=160,
+              step_height=0.02, lateral=0.05, min_len=0.02, max_len=0.05, tail_steps=40):
+    """Config 3: per env a plan of n_footsteps steps (right foot first) of length ~U(min_len,max_len), one phase of
+    double support before and after.  Returns dict(zmp_x, zmp_y [E][len], phase_T, foot_coef [E][P][2][20],
+    contact [E][P] int32 (bit 0 right, bit 1 left), step_len [E])."""
+    env_ids = np.asarray(env_ids, dtype=np.int64)
+    P = n_footsteps + 2
+    per = int(round(time_per_step / dt))
+    zlen = P * per + tail_steps + horizon_steps + 2
+    E = env_ids.size
+    zx, zy = np.zeros((E, zlen)), np.zeros((E, zlen))
+    fc, ct = np.zeros((E, P, 2, 20)), np.zeros((E, P), np.int32)
+    lens = np.zeros(E)
+    for i, e in enumerate(env_ids.tolist()):
+        L = min_len + (max_len - min_len) * _u01(seed, e, 0)
+        lens[i] = L
+        foot = [np.array([0.0, -lateral, 0.0]), np.array([0.0, lateral, 0.0])]     # right, left
+        for p in range(P):
+            swing = -1 if p == 0 or p == P - 1 else (p - 1) % 2                      # right foot swings first
+            ct[i, p] = 3 if swing < 0 else (2 if swing == 0 else 1)
+            target = [f.copy() for f in foot]
+            if swing >= 0:
+                target[swing][0] = foot[1 - swing][0] + L
+            for s in range(2):
+                fc[i, p, s] = foot_coefficients(foot[s], target[s], step_height if s == swing else 0.0, time_per_step)
+            if swing < 0:
+                z = 0.5 * (foot[0][:2] + foot[1][:2])
+            else:
+                z = foot[1 - swing][:2]
+            k0, k1 = p * per, (p + 1) * per if p < P - 1 else zlen
+            zx[i, k0:k1], zy[i, k0:k1] = z[0], z[1]
+            foot = target
+    return dict(zmp_x=zx, zmp_y=zy, phase_T=time_per_step, foot_coef=fc, contact=ct, step_len=lens)

@@ -200,6 +200,24 @@ void orc_sim_link_table(void* sp, double* mass, double* com, double* inertia) {
     }
 }
 
+void orc_sim_set_walk_plan(void* sp, int32_t zmp_len, const double* zx, const double* zy, int32_t n_phases, double phase_T,
+                           const double* fc, const int32_t* contact) {
+    Sim* s = static_cast<Sim*>(sp);
+    Controller& c = *s->ctrl;
+    c.zmp.zmpXRef.assign(zx, zx + zmp_len);
+    c.zmp.zmpYRef.assign(zy, zy + zmp_len);
+    c.phase_T = phase_T;
+    c.contact.assign(contact, contact + n_phases);
+    c.rFp.resize(n_phases); c.lFp.resize(n_phases);
+    for (int p = 0; p < n_phases; ++p)
+        for (int f = 0; f < 2; ++f) {
+            const double* k = fc + ((size_t)p * 2 + f) * 20;
+            FootCoeff& d = f == 0 ? c.rFp[p] : c.lFp[p];
+            d.x.assign(k, k + 6); d.y.assign(k + 6, k + 12); d.z.assign(k + 12, k + 20);
+        }
+}
+int32_t orc_sim_last_phase(void* sp) { return static_cast<Sim*>(sp)->ctrl->last_phase; }
+
 int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t E, const double* x0, const int32_t* push_step,
                           const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
                           double* com_out, double* stats) {

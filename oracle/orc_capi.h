@@ -77,6 +77,13 @@ int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t n_env, const double* x0,
                           const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
                           double* com_out, double* stats);
 
+/* EXTENSION (walking, not in the reference): replaces the ZMP reference and installs per-phase foot polynomials
+ * (foot_coef: [n_phases][2][20] = x(6) y(6) z(8), ascending powers of the phase-local time) and contact masks
+ * (contact[n_phases]: bit 0 right foot, bit 1 left foot). */
+void orc_sim_set_walk_plan(void* sim, int32_t zmp_len, const double* zx, const double* zy, int32_t n_phases,
+                           double phase_T, const double* foot_coef, const int32_t* contact);
+int32_t orc_sim_last_phase(void* sim);
+
 /* Generic QP entry (config 5 microbenchmark, solver self-tests). */
 int32_t orc_qp_solve(int32_t n, const double* H, const double* g, int32_t m, const double* A,
                      const double* lbA, const double* ubA, double* x, double* y, int32_t long_double,

@@ -665,13 +665,22 @@ Vec<6> Controller::PDMomentumAcc() const {
     return h;
 }
 
-Vec<12> Controller::PDFeetAcc(double t) const {
+int Controller::phase_of(double t) const {
+    if (contact.empty()) return 0;
+    int p = static_cast<int>(t / phase_T);
+    int n = (int)contact.size();
+    return p < 0 ? 0 : (p >= n ? n - 1 : p);
+}
+
+Vec<12> Controller::PDFeetAcc(double t_abs) const {
+    const int ph = phase_of(t_abs);
+    const double t = contact.empty() ? t_abs : t_abs - ph * phase_T;
     Vec<30> v = robot.v;
     swapBaseVelocityAndRefToWorldFrame(robot.X[0], v);
     Vec<12> out;
     const int soles[2] = {7, 14};
     for (int s = 0; s < 2; ++s) {
-        const FootCoeff& c = s == 0 ? rF : lF;
+        const FootCoeff& c = contact.empty() ? (s == 0 ? rF : lF) : (s == 0 ? rFp[ph] : lFp[ph]);
         const Mat<6, 30>& J = s == 0 ? kin.JR : kin.JL;
         const Mat<3, 3>& Rdes = s == 0 ? robot.Rf_q0 : robot.Lf_q0;
         Vec<3> pos = robot.T[soles[s]].block<3, 1>(0, 3);
@@ -730,6 +739,12 @@ Vec<74> Controller::solveQP(const Mat<74, 74>& H, const Vec<74>& g) {
     Aqp.set(18, 0, Ain);
     for (int r = 0; r < 12; ++r) lbA[6 + r] = ubA[6 + r] = beq[r];
     for (int r = 0; r < 32; ++r) { lbA[18 + r] = bin[r]; ubA[18 + r] = QP_INFTY; }
+    if (!contact.empty()) {   // extension: a foot that is not in contact carries no force
+        int mask = contact[last_phase];
+        for (int foot = 0; foot < 2; ++foot)
+            if (!((mask >> foot) & 1))
+                for (int r = 0; r < 16; ++r) ubA[18 + 16 * foot + r] = 0.0;
+    }
     if (!all_finite(Hqp) || !all_finite(gqp) || !all_finite(Aqp) || !all_finite(lbA)) {
         std::fprintf(stderr, "orc::Controller::solveQP: NaN or Inf in QP data\n");
         std::abort();  // :448-466
@@ -747,6 +762,7 @@ Vec<74> Controller::solveQP(const Mat<74, 74>& H, const Vec<74>& g) {
 
 WBCOutput Controller::WBC(double t) {
     const int n = 30;
+    last_phase = phase_of(t);
     qppRef = PDJointsAcc();
     hGpRef = PDMomentumAcc();
     footAccRef = PDFeetAcc(t);

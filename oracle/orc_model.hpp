@@ -170,6 +170,15 @@ struct Controller {
     Vec<12> footAccRef;
     QpInfo qpInfo;
     bool qp_long_double = false;
+    // EXTENSION (not in the reference): walking plans.  Time is cut into n phases of length
+    // phase_T; phase p = min((int)(t/phase_T), n-1) selects the foot polynomials (evaluated at t - p*phase_T) and
+    // which feet may carry force (bit 0 right, bit 1 left; a swing foot's 16 coefficients get bounds [0,0]).
+    // The stand scenario is one phase of infinite length with both feet in contact: identical to upstream.
+    std::vector<FootCoeff> rFp, lFp;
+    std::vector<int> contact;
+    double phase_T = 1e30;
+    int last_phase = 0;
+    int phase_of(double t) const;
     long qp_solves = 0, qp_iterations = 0, qp_failures = 0;
 
     Controller(Robot& r, Mpc3dLip& m, const ZMP& z, const FootCoeff& rFc, const FootCoeff& lFc);  // :5-46

@@ -79,6 +79,9 @@ class Lib:
         L.orc_sim_link_table.argtypes = [C.c_void_p] * 4
         L.orc_batch_rollout.argtypes = [C.POINTER(OrcConfig), i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        if hasattr(L, "orc_sim_set_walk_plan"):
+            L.orc_sim_set_walk_plan.argtypes = [C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, f64, C.c_void_p, C.c_void_p]
+            L.orc_sim_last_phase.argtypes = [C.c_void_p]
         if hasattr(L, "orc_qp_solve"):
             L.orc_qp_solve.argtypes = [i32, C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p]
@@ -178,6 +181,12 @@ class Sim:
         out = np.zeros(max_steps)
         n = self.lib.L.orc_sim_run_stand(self.h, _p(out), max_steps)
         return out[:n]
+
+    def set_walk_plan(self, zx, zy, phase_T, foot_coef, contact):
+        """EXTENSION (walking): foot_coef [n_phases][2][20], contact [n_phases] (bit 0 right, bit 1 left)"""
+        zx = np.ascontiguousarray(zx, np.float64); zy = np.ascontiguousarray(zy, np.float64)
+        fc = np.ascontiguousarray(foot_coef, np.float64); ct = np.ascontiguousarray(contact, np.int32)
+        self.lib.L.orc_sim_set_walk_plan(self.h, len(zx), _p(zx), _p(zy), len(ct), float(phase_T), _p(fc), _p(ct))
 
     def mpc_tables(self):
         hz = np.zeros(1, np.int32)

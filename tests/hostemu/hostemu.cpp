@@ -9,12 +9,16 @@ using namespace lmh;
 struct Emu {
     HostModel hm;
     Plan plan;
+    int32_t contact_both = 3;
+    std::vector<double> wzx, wzy, wfc;
+    std::vector<int32_t> wct;
     std::vector<double> scratch = std::vector<double>(QP_SCRATCH_DOUBLES);
     explicit Emu(const Scenario& s) : hm(s) {
         plan.zmp_x = hm.zmp_x.data();
         plan.zmp_y = hm.zmp_y.data();
         plan.foot_coef = hm.foot_coef.data();
         plan.zmp_len = (int32_t)hm.zmp_x.size();
+        plan.contact = &contact_both; plan.n_phases = 1; plan.phase_T = 1e30;
     }
 };
 
@@ -26,6 +30,14 @@ void* emu_create(double dt, double sim_time, double horizon, const double* com3)
     return new Emu(s);
 }
 void emu_destroy(void* p) { delete static_cast<Emu*>(p); }
+void emu_set_walk_plan(void* p, int32_t zmp_len, const double* zx, const double* zy, int32_t n_phases, double phase_T,
+                       const double* fc, const int32_t* contact) {
+    Emu* e = static_cast<Emu*>(p);
+    e->wzx.assign(zx, zx + zmp_len); e->wzy.assign(zy, zy + zmp_len);
+    e->wfc.assign(fc, fc + (size_t)n_phases * 40); e->wct.assign(contact, contact + n_phases);
+    e->plan.zmp_x = e->wzx.data(); e->plan.zmp_y = e->wzy.data(); e->plan.foot_coef = e->wfc.data();
+    e->plan.contact = e->wct.data(); e->plan.zmp_len = zmp_len; e->plan.n_phases = n_phases; e->plan.phase_T = phase_T;
+}
 void emu_nominal(void* p, double* q0, double* zcom, double* mass, int32_t* ik_iters) {
     Emu* e = static_cast<Emu*>(p);
     for (int i = 0; i < NQ; ++i) q0[i] = e->hm.q0[i];

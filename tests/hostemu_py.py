@@ -14,6 +14,7 @@ _L.emu_destroy.argtypes = [_vp]
 _L.emu_nominal.argtypes = [_vp] * 5
 _L.emu_tables.argtypes = [_vp] * 8
 _L.emu_stage.argtypes = [_vp, _vp, _vp, _f64, _vp]
+_L.emu_set_walk_plan.argtypes = [_vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp]
 _L.emu_step.argtypes = [_vp, _vp, _vp, _vp, _i32, _vp, _vp]
 
 
@@ -40,6 +41,11 @@ class Emu:
                                    np.zeros(1, np.int32), np.zeros(2), np.zeros(40))
         _L.emu_tables(self.h, _p(m), _p(c), _p(i), _p(r), _p(n1), _p(rpx), _p(fc))
         return dict(mass=m, com=c, isp=i, mpc_r=r[:int(n1[0])].copy(), rPx=rpx, foot_coef=fc)
+
+    def set_walk_plan(self, zx, zy, phase_T, foot_coef, contact):
+        zx = np.ascontiguousarray(zx, np.float64); zy = np.ascontiguousarray(zy, np.float64)
+        fc = np.ascontiguousarray(foot_coef, np.float64); ct = np.ascontiguousarray(contact, np.int32)
+        _L.emu_set_walk_plan(self.h, len(zx), _p(zx), _p(zy), len(ct), float(phase_T), _p(fc), _p(ct))
 
     def stage(self, x, v_held, t):
         d = np.zeros(1, STAGE_DTYPE)

@@ -233,3 +233,31 @@ def test_offline_app_on_the_facade_classes(golden, tmp_path):
     assert np.abs(cx - golden["stand_comx"]).max() < 5e-8          # both streams carry 6 significant digits
     fused = subprocess.run([exe, "--fused", "64"], check=True, capture_output=True, text=True).stdout.split()
     assert abs(float(fused[0]) - golden["stand_comx"][-1]) < 5e-8   # the fused batched rollout ends in the same place
+
+
+def test_walking_extension_against_oracle(oracle):
+    """EXTENSION (BASELINE configs 3-4): per-environment walking plans, 1.6 s MPC horizon, contact
+    switching.  Defined in the oracle first; the GPU must agree env by env."""
+    E, n = 6, 70
+    wp = lmh.walk_plan(range(E))
+    b = lmh.Batch(E, time_horizon=1.6, log_steps=n)
+    b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"], plan_ids=np.arange(E))
+    b.step(n)
+    lg = b.log(0, n)
+    x, vh, t = b.get_state()
+    for e in range(E):
+        so = oracle.sim(time_horizon=1.6)
+        so.set_walk_plan(wp["zmp_x"][e], wp["zmp_y"][e], wp["phase_T"], wp["foot_coef"][e], wp["contact"][e])
+        lo = so.step(n)
+        assert np.abs(lg["com_k4"][:, e] - lo["com_k4"]).max() < 1e-9, e      # north star: 1e-4 m
+        assert np.abs(lg["rfoot"][:, e] - lo["rfoot"]).max() < 1e-9 and np.abs(lg["lfoot"][:, e] - lo["lfoot"]).max() < 1e-9
+        assert np.abs(x[e] - lo["x"][-1]).max() < 1e-8
+        assert np.array_equal(lg["k_index"][:, e], lo["k_index"])              # bit exact
+    st = b.stats()
+    assert (st["qp_fail"] == 0).all() and (st["alive"] == 1).all()
+    assert lg["rfoot"][:, :, 2].max() > 0.015
+    b.set_state(x, vh, np.full(E, 0.6))
+    d = b.stage()
+    assert (d["phase"] == 1).all() and np.abs(d["f"][:, :6]).max() == 0.0     # integer phase index; swing foot force-free
+    with pytest.raises(lmh.LmhError):
+        b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"] + 4, plan_ids=np.arange(E))

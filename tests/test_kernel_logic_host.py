@@ -88,3 +88,24 @@ def test_random_states_against_oracle(hostemu, oracle):
             assert relerr(d[k], do[k]) < 1e-12, (i, k)
         for k in ("qpp", "tau", "f"):
             assert relerr(d[k], do[k]) < 1e-7, (i, k, sc)
+
+
+def test_walking_extension_against_oracle(hostemu, oracle):
+    """EXTENSION (configs 3-4): phase plans with contact switching; kernel logic vs the oracle's definition."""
+    import linearmpchumanoid_b200 as lmh
+    wp = lmh.walk_plan(range(3, 4))
+    so = oracle.sim(time_horizon=1.6)
+    so.set_walk_plan(wp["zmp_x"][0], wp["zmp_y"][0], wp["phase_T"], wp["foot_coef"][0], wp["contact"][0])
+    e = hostemu.Emu(horizon=1.6)
+    e.set_walk_plan(wp["zmp_x"][0], wp["zmp_y"][0], wp["phase_T"], wp["foot_coef"][0], wp["contact"][0])
+    x0, _, _ = so.get_state()
+    n = 90                                                       # through the first swing phase and into the second
+    lo = so.step(n)
+    x, vh, t, lg, st = e.step(x0, np.zeros(30), 0.0, n)
+    assert np.abs(lg["com_k4"] - lo["com_k4"]).max() < 1e-9 and np.abs(lg["rfoot"] - lo["rfoot"]).max() < 1e-9
+    assert np.abs(x - lo["x"][-1]).max() < 1e-8 and relerr(lg["tau_k1"], lo["tau_k1"]) < 1e-7
+    assert np.array_equal(lg["k_index"], lo["k_index"])
+    assert st["qp_fail"] == 0 and st["alive"] == 1
+    assert lo["rfoot"][:, 2].max() > 0.015                       # the right foot really left the ground ...
+    d, _ = e.stage(lo["x"][59], lo["x"][59][30:], 0.6)          # ... and carries no force while it swings (phase 1)
+    assert d["phase"] == 1 and np.abs(d["f"][:6]).max() == 0.0 and d["f"][11] > 40.0
