@@ -112,6 +112,7 @@ struct EnvWS {
     double t;
     // ---- persistent through a stage
     double R0[9], p0[3];           // torso pose
+    double esc[4];                 // sin, cos of pitch and yaw (kept for the Euler-rate map of the state derivative)
     double Rs[2][9], ps[2][3];     // sole poses (frames 7, 14)
     double M6[6 * NQ];             // rows 0..5 of the mass matrix [Ic0 | F2]
     double Hc[NCH * 36];           // joint-space inertia, one 6x6 block per chain (chains do not couple)
@@ -122,7 +123,7 @@ struct EnvWS {
     double com[3], comVel[3], angMom[3], xRef[3], yRef[3];
     double qppRef[NQ], hGpRef[6], footAccRef[12];
     double ga[NQ], a[NQ], f12[12], tau[NJ], xdot[2 * NQ];
-    double Sa[36], Ls[36], rhs[6], sv[6], lam[6];
+    double Sa[36], Ls[36], Lsi[6], rhs[6], sv[6], lam[6];     // Lsi: 1 / diag(Ls)
     double c[NC], cs[NC], mu[NC], piv[NC], ladiag[ND1];
     double red[32];                // reduction scratch
     int32_t free_mask[NC];
@@ -217,6 +218,14 @@ LMH_HD double mul_then_add(double a, double b, double c) {
 #endif
 }
 
+LMH_HD double lmh_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 // in-place Cholesky of a 6x6 SPD matrix held in registers (lower triangle), fully unrolled
 LMH_HD void chol6(double* A) {
     LMH_UNROLL
@@ -224,9 +233,8 @@ LMH_HD void chol6(double* A) {
         double s = A[7 * k];
         LMH_UNROLL
         for (int m = 0; m < k; ++m) s -= A[6 * k + m] * A[6 * k + m];
-        const double dk = sqrt(s);
-        const double inv = 1.0 / dk;
-        A[7 * k] = dk;
+        const double inv = lmh_rsqrt(s);
+        A[7 * k] = s * inv;
         LMH_UNROLL
         for (int i = k + 1; i < 6; ++i) {
             double t = A[6 * i + k];
@@ -305,6 +313,7 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
             R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
             R[9] = w.q[0]; R[10] = w.q[1]; R[11] = w.q[2];
+            w.esc[0] = sp; w.esc[1] = cp; w.esc[2] = sy; w.esc[3] = cy;
             for (int k = 0; k < 9; ++k) w.R0[k] = R[k];
             for (int k = 0; k < 3; ++k) w.p0[k] = R[9 + k];
         } else if (i == 7 || i == 14) {
@@ -947,8 +956,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
         chol6(A);
         LMH_FOR(e, 36) w.Ls[e] = A[e];
+        LMH_FOR(e, 6) w.Lsi[e] = 1.0 / A[7 * e];
     }
     const double* Ls = w.Ls;
+    const double* Lsi = w.Lsi;
     // ---- primal active set on c >= 0, every working set solved in the wrench space of the feet.
     // For a free set F let P_F = G_F G_F' = B B' (B: 12 x 12, block diagonal per foot, from a diagonally pivoted
     // Cholesky that stops at the numerical rank: columns beyond the rank are zero).  With f = B zeta the
@@ -1037,7 +1048,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
                 for (int m = 0; m < 6; ++m) {
                     double sd = t[m];
                     for (int n = 0; n < m; ++n) sd -= Ls[6 * m + n] * t[n];
-                    t[m] = sd / Ls[7 * m];
+                    t[m] = sd * Lsi[m];
                     if (col < 12) Wb[12 * m + col] = t[m]; else w.sv[m] = t[m];
                 }
             }
@@ -1159,14 +1170,14 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
                 double sd = l[r];
                 LMH_UNROLL
                 for (int m = 0; m < r; ++m) sd -= Ls[6 * r + m] * l[m];
-                l[r] = sd / Ls[7 * r];
+                l[r] = sd * Lsi[r];
             }
             LMH_UNROLL
             for (int r = 5; r >= 0; --r) {
                 double sd = l[r];
                 LMH_UNROLL
                 for (int m = r + 1; m < 6; ++m) sd -= Ls[6 * m + r] * l[m];
-                l[r] = sd / Ls[7 * r];
+                l[r] = sd * Lsi[r];
             }
             LMH_FOR(it, 12) {
                 const int f = it / 6;
@@ -1294,14 +1305,14 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             double s = l[r];
             LMH_UNROLL
             for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m];
-            l[r] = s / Ls[7 * r];
+            l[r] = s * Lsi[r];
         }
         LMH_UNROLL
         for (int r = 5; r >= 0; --r) {
             double s = l[r];
             LMH_UNROLL
             for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m];
-            l[r] = s / Ls[7 * r];
+            l[r] = s * Lsi[r];
         }
         // a = -Ha^-1 (ga + M6' lam) through the same Woodbury pieces
         double coef[7] = {l[0], l[1], l[2], l[3], l[4], l[5], 1.0};
@@ -1359,9 +1370,7 @@ LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
         double qd;
         if (i < 3) qd = w.v[i] + cross_k(w.v + 3, w.q, i);       // v + w x p
         else if (i < 6) {    // Euler rates (generalizedFunctions.cpp:43-50)
-            double s2, c2;
-            lmh_sincos(w.q[5], &s2, &c2);
-            double c1 = cos(w.q[4]), t1 = tan(w.q[4]);
+            const double s2 = w.esc[2], c2 = w.esc[3], c1 = w.esc[1], t1 = w.esc[0] / w.esc[1];   // tan = sin/cos
             const double* om = w.v + 3;
             qd = i == 3 ? (c2 / c1) * om[0] + (s2 / c1) * om[1]
                : i == 4 ? -s2 * om[0] + c2 * om[1]
@@ -1484,11 +1493,20 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
             if (stage == 0) { LMH_FOR(i, NJ) log->tau_k1[i] = w.tau[i]; }
         }
         if (st && stage == 0) {
+#if defined(__CUDA_ARCH__)
+            if (Cx::NT == 32) {
+                const int i = cx.tid;
+                const double m = warp_max(i < NJ ? fabs(w.tau[i]) : 0.0), a = warp_max(i < NQ ? fabs(w.xdot[NQ + i]) : 0.0);
+                st->max_tau = fmax(st->max_tau, m); st->max_qpp = fmax(st->max_qpp, a);
+            } else
+#endif
+            {
             LMH_FOR(i, 1) {
                 double m = st->max_tau, a = st->max_qpp;
                 for (int j = 0; j < NJ; ++j) m = fmax(m, fabs(w.tau[j]));
                 for (int j = 0; j < NQ; ++j) a = fmax(a, fabs(w.xdot[NQ + j]));
                 st->max_tau = m; st->max_qpp = a;
+            }
             }
         }
         cx.sync();
@@ -1513,10 +1531,19 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
     }
     cx.sync();
     if (st) {
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) {
+            const int i = cx.tid;
+            const bool bad = !(fabs(x[i]) < 1e6) || (i < 28 && !(fabs(x[32 + i]) < 1e6)) || !(x[2] > 0.15);
+            if (__any_sync(0xffffffffu, bad)) st->alive = 0;
+        } else
+#endif
+        {
         LMH_FOR(i, 1) {
             bool ok = x[2] > 0.15;
             for (int j = 0; j < 2 * NQ; ++j) ok = ok && (fabs(x[j]) < 1e6);
             if (!ok) st->alive = 0;
+        }
         }
     }
     cx.sync();

@@ -451,9 +451,14 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
 #pragma unroll
         for (int j = 0; j < ND1; ++j) if (j == lane) h[j] += wj;
     } else if (yrow) {
+        // row yr of [M6; ga'; U]: a pointer and a scale per lane, no per-entry branching
+        const double* src = yr < 6 ? w.M6 + NQ * yr : yr == 6 ? w.ga : w.AG + NQ * (yr - 4);
+        const double sc = yr < 7 ? 1.0 : K.sq_wCoML;
+        const double sc2 = sc * K.isq_wJoints;
 #pragma unroll
-        for (int j = 0; j < ND1; ++j) h[j] = yt_entry(w, K, yr, j);
-        for (int j = ND1; j < NQ; ++j) Yt[NQ * yr + j] = yt_entry(w, K, yr, j);     // the arm/head part needs no solve
+        for (int j = 0; j < ND1; ++j) h[j] = sc * src[j];
+#pragma unroll
+        for (int j = ND1; j < NQ; ++j) Yt[NQ * yr + j] = sc2 * src[j];     // the arm/head part needs no solve
     }
 #pragma unroll
     for (int k = 0; k < ND1; ++k) {
