@@ -44,7 +44,7 @@ constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
 #ifndef LMH_WARP_WRENCH
-#define LMH_WARP_WRENCH 0
+#define LMH_WARP_WRENCH 1
 #endif
 constexpr int ND1 = 18;     // base + both legs: the block of H_a that the sole Jacobians couple
 constexpr int LD1 = 19;
@@ -915,9 +915,11 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
         }
     }
     // Gram matrix of the rows: Gm[r][c] = [.]_r D^-1 [.]_c'
-    LMH_FOR(it, NYR * NYR) {
-        int r = it / NYR, c = it % NYR;
-        if (c <= r) {
+    LMH_FOR(it, NYR * (NYR + 1) / 2) {
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= it) ++r;      // unrank the lower-triangular index (55 entries)
+        const int c = it - r * (r + 1) / 2;
+        {
             double s0 = 0.0, s1 = 0.0;
             const double* yr = Yt + NQ * r;
             const double* yc = Yt + NQ * c;
