@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
     if (env >= p.n_env) return;
     Ctx<NT> cx{(int)threadIdx.x, 0};
     const Consts& K = *p.K;
+    ws_reset(cx, w);
     for (int i = threadIdx.x; i < 60; i += NT) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = threadIdx.x; i < 30; i += NT) w.vh[i] = p.vh[(size_t)env * 30 + i];
     double t = p.t[env];
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(NT) stage_kernel(Params p) {
         w.vh[i] = p.vh[(size_t)env * 30 + i];
     }
     if (threadIdx.x == 0) w.t = p.t[env];
-    cx.sync();
+    ws_reset(cx, w);
     stage_eval(cx, w, *p.K, p.plan, p.plan_id ? p.plan_id[env] : 0, p.qp_scratch + (size_t)env * QP_SCRATCH_DOUBLES,
                p.dump ? p.dump + env : nullptr);
     for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];

@@ -130,6 +130,7 @@ struct EnvWS {
     int32_t pdone[12], ppiv[2];
     int32_t k_index, qp_iters, qp_status, qp_fallback;
     int32_t phase, contact;        // walking extension: phase index and contact mask of this stage
+    int32_t warm_contact, pad1_;   // contact mask the stored working set (free_mask, c) belongs to; -1 = none
     // ---- phase-overlaid scratch
     union {
         struct {                       // model phase
@@ -294,6 +295,14 @@ struct EnvWS;
 struct Consts;
 __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane);
 #endif
+
+// state that survives from one stage evaluation to the next besides vh: the QP working set (warm start)
+template <class Cx>
+LMH_HDN void ws_reset(const Cx& cx, EnvWS& w) {
+    LMH_FOR(i, NC) { w.free_mask[i] = 1; w.c[i] = 0.0; }
+    LMH_FOR(i, 1) w.warm_contact = -1;
+    cx.sync();
+}
 
 // ================================================================================================
 // Phase 1: forward kinematics, parent-relative transforms, CoM.
@@ -976,10 +985,22 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
     double* Ay = w.u.s.Ay;            // 13 x 13 : lower triangle factorised in place, row 12 = rhs / zeta
     double* vv = w.u.s.vv;            // [36]   : u = T^-1 zeta (12), y = B u (12), r = wF f - Jb lam (12)
     const int contact = w.contact;     // bit f: foot f may carry force (both set in the reference's stand task)
-    LMH_FOR(i, NC) { w.free_mask[i] = (contact >> (i / 16)) & 1; w.c[i] = 0.0; }
+    // Warm start: consecutive stage evaluations of an environment nearly always share their working set, and any
+    // c >= 0 is a feasible starting point, so the previous solution (w.c, w.free_mask) seeds the iteration when it
+    // has clipped coefficients and the contact phase is the same.  The minimiser is unique: only the path changes.
+    bool have_point = false;
+    if (w.warm_contact == contact) {
+        int nclip = 0;
+        for (int i = 0; i < NC; ++i) nclip += (((contact >> (i / 16)) & 1) && !w.free_mask[i]) ? 1 : 0;
+        have_point = nclip > 0;
+    }
+    cx.sync();
+    if (!have_point) {
+        LMH_FOR(i, NC) { w.free_mask[i] = (contact >> (i / 16)) & 1; w.c[i] = 0.0; }
+    }
+    LMH_FOR(i, 1) w.warm_contact = contact;
     cx.sync();
     int iters = 0, status = 0;
-    bool have_point = false;
     while (true) {
         ++iters;
         const bool const_basis = !have_point && contact == 3;
@@ -1037,8 +1058,8 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch,
             }
             cx.sync();
         }
-        LMH_FOR(col, 13) {            // W[:, col] = Ls^-1 Jb' B[:, col] ; column 12: sv = Ls^-1 rhs (first pass only)
-            if (col < 12 || !have_point) {
+        LMH_FOR(col, 13) {            // W[:, col] = Ls^-1 Jb' B[:, col] ; column 12: sv = Ls^-1 rhs (first pass of a stage only)
+            if (col < 12 || iters == 1) {
                 const int f = col / 6, k = col % 6;
                 double t[6];
                 for (int m = 0; m < 6; ++m) {

@@ -59,6 +59,7 @@ void emu_stage(void* p, const double* x60, double* vheld30, double t, LmhStageDu
     for (int i = 0; i < NQ; ++i) { w.q[i] = x60[i]; w.v[i] = x60[NQ + i]; w.vh[i] = vheld30[i]; }
     w.t = t;
     Ctx<1> cx{0, 0};
+    ws_reset(cx, w);
     stage_eval(cx, w, e->hm.K, e->plan, 0, e->scratch.data(), dump);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
 }
@@ -69,6 +70,7 @@ void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps,
     double kacc[60];
     StatsAcc st{0, 0, 0, 0, 0, 0, 1, 0};
     Ctx<1> cx{0, 0};
+    ws_reset(cx, w);
     for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, e->scratch.data(), logs ? logs + s : nullptr, &st);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
     if (stats) {
