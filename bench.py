@@ -35,7 +35,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {"push": "NAO balance under random push perturbations (BASELINE configs[1])",
+WORKLOADS = {"qp": "QP microbenchmark on frozen states (BASELINE configs[4])",
+             "push": "NAO balance under random push perturbations (BASELINE configs[1])",
              "walk": "NAO LIPM-MPC walking, random footstep plans, 1.6 s horizon (BASELINE configs[2]; extension: upstream has no walking)",
              "sweep": "NAO walking robustness Monte Carlo: footstep plans + pushes (BASELINE configs[3]; extension)"}
 FLOP_PER_ENV_STEP = 0.51e6          # SURVEY.md 8(d) / App. C, active-set changes k = 0 (conservative)
@@ -178,6 +179,55 @@ def run_reference_arm(args):
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
+    return 0
+
+
+# ---------------------------------------------------------------- config 5: QP micro-benchmark
+def run_qp_microbench(args):
+    """BASELINE configs[4]: frozen states taken at step 50 of config 2; cold-started WBC QPs (74 var / 18 eq / 32 ineq in
+    the reference's form) and LIPM-MPC evaluations on the GPU vs the oracle's solvers on the host cores."""
+    import torch
+    import linearmpchumanoid_b200 as lmh
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    E, R = args.envs, 50
+    b = lmh.Batch(E, threads_per_env=args.threads_per_env)
+    step, dv = lmh.push_plan(range(E))
+    b.set_pushes(step, dv)
+    b.step(50)                                      # frozen states = config 2 at step 50
+    X, VH, T = b.get_state()
+    b.qp_bench(0, 2)
+    ms_qp, a, f = b.qp_bench(0, R)
+    ms_model, _, _ = b.qp_bench(0, 1)
+    ms_mpc, _, _ = b.qp_bench(1, 4 * R)
+    qps = E * (R - 1) / ((ms_qp - ms_model) * 1e-3)
+    mpcs = E * 4 * R / ((ms_mpc - ms_model) * 1e-3) if ms_mpc > ms_model else float("nan")
+    # oracle on the host: the same QPs through its own solver, bounded sample
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc_py
+    orc_py.build()
+    O = orc_py.oracle()
+    so = O.sim()
+    n = min(E, 200)
+    t0, worst = time.perf_counter(), 0.0
+    for e in range(n):
+        so.set_state(X[e], float(T[e]), VH[e])
+        d = so.stage(X[e], float(T[e]))
+        xa, xf = d["x"][:30], d["x"][30:42]
+        worst = max(worst, float(np.abs(a[e] - xa).max() / max(1.0, np.abs(xa).max())),
+                    float(np.abs(f[e] - xf).max() / max(1.0, np.abs(xf).max())))
+    cpu_stage_rate = n / (time.perf_counter() - t0)
+    line = {"metric": "WBC QP solves/sec (74 var, 18 eq, 32 ineq; cold start, frozen states)", "value": qps, "unit": "QPs/s",
+            "n_gpus": 1, "steps": R, "warmup": 2, "ms_per_step": (ms_qp - ms_model) / (R - 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "QP microbenchmark on frozen states (BASELINE configs[4])", "envs": E,
+                       "states": "config 2 at step 50", "repeats": R},
+            "mpc_evaluations_per_s": mpcs, "max_rel_err_a_f_vs_oracle": worst, "oracle_sample_envs": n,
+            "cpu_baseline": {"value": cpu_stage_rate, "unit": "stage evaluations/s (model + MPC + QP)", "cores": 1, "kind": "port",
+                             "sample": f"{n} frozen states, oracle stage evaluation (its QP is ~85% of a stage)"},
+            "gpu_launches": 4}
+    _emit(line)
+    b.close()
     return 0
 
 
@@ -387,7 +437,9 @@ def main():
     ap.add_argument("--workload", default="push", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    return run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_qp_microbench(args) if args.workload == "qp" else run_ours(args)
 
 
 if __name__ == "__main__":

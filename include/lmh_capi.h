@@ -150,6 +150,13 @@ int32_t lmh_reset_stats(LmhBatch* h);
 int32_t lmh_timer_start(LmhBatch* h);
 int32_t lmh_timer_stop(LmhBatch* h, double* elapsed_ms);
 
+/* Config 5 micro-benchmark on the CURRENT (frozen) states: mode 0 = `repeats` cold-started WBC QP solves per
+ * environment (data + factorisation + active set, i.e. what Controller::solveQP + qpOASES do per call,
+ * controller.cpp:388-479); mode 1 = `repeats` LIPM-MPC evaluations (mpcLinearPendulum.cpp:78-133).  a_f_out
+ * (or NULL): [n_env][42] = joint accelerations a (30, base twist in the torso frame) and contact wrenches f (12) of
+ * the last solve.  elapsed_ms: device time of the launch (includes one evaluation of the model phases). */
+int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out, double* elapsed_ms);
+
 /* Launch geometry actually used. */
 int32_t lmh_launch_info(const LmhBatch* h, int32_t* threads_per_env, int32_t* envs_per_block, int32_t* smem_bytes,
                         int32_t* blocks, int32_t* kernel_launches_total);

@@ -43,7 +43,7 @@ SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", 
            "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
            "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
            "lmh_stats_dev", "lmh_set_state_dev", "lmh_reset_stats", "lmh_timer_start", "lmh_timer_stop",
-           "lmh_launch_info", "lmh_measure_fp64_peak"]
+           "lmh_qp_bench", "lmh_launch_info", "lmh_measure_fp64_peak"]
 
 
 def build_library(force=False, verbose=False):
@@ -103,6 +103,7 @@ def load_library():
     L.lmh_reset_stats.argtypes = [vp]
     L.lmh_timer_start.argtypes = [vp]
     L.lmh_timer_stop.argtypes = [vp, vp]
+    L.lmh_qp_bench.argtypes = [vp, _i32, _i32, vp, vp]
     L.lmh_launch_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.lmh_measure_fp64_peak.argtypes = [_i32, vp, vp, vp]
     _lib = L
@@ -260,6 +261,12 @@ class Batch:
         c = np.zeros((self.n_env, 3))
         _chk(self.L, self.L.lmh_get_com(self.h, _p(c)))
         return c
+
+    def qp_bench(self, mode, repeats):
+        """config 5: (ms, a[n_env][30], f[n_env][12]) of `repeats` WBC QP solves (mode 0) / MPC evaluations (mode 1)"""
+        out, ms = np.zeros((self.n_env, 42)), np.zeros(1)
+        _chk(self.L, self.L.lmh_qp_bench(self.h, int(mode), int(repeats), _p(out), _p(ms)))
+        return float(ms[0]), out[:, :30], out[:, 30:]
 
     def launch_info(self):
         v = [np.zeros(1, np.int32) for _ in range(5)]

@@ -37,7 +37,6 @@ struct Params {
     LmhStepLog* log;    // [log_cap][E] or null
     LmhStageDump* dump; // [E] or null
     double* com;        // [E][3]
-    double* qp_scratch; // [E][QP_SCRATCH_DOUBLES] global scratch of the rare c-space QP fallback
     int32_t n_env, n_steps, step0, log_cap;
 };
 
@@ -59,7 +58,6 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
     double t = p.t[env];
     const int plan_id = p.plan_id ? p.plan_id[env] : 0;
     const int push_at = p.push_step ? p.push_step[env] : -1;
-    double* gscratch = p.qp_scratch + (size_t)env * QP_SCRATCH_DOUBLES;
     StatsAcc st;
     {
         const LmhStats& s0 = p.stats[env];
@@ -74,7 +72,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
             cx.sync();
         }
         LmhStepLog* lg = (p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
-        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, gscratch, lg, &st);
+        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, lg, &st);
     }
     for (int i = threadIdx.x; i < 60; i += NT) p.x[(size_t)env * 60 + i] = x[i];
     for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];
@@ -101,10 +99,38 @@ __global__ void __launch_bounds__(NT) stage_kernel(Params p) {
     }
     if (threadIdx.x == 0) w.t = p.t[env];
     ws_reset(cx, w);
-    stage_eval(cx, w, *p.K, p.plan, p.plan_id ? p.plan_id[env] : 0, p.qp_scratch + (size_t)env * QP_SCRATCH_DOUBLES,
-               p.dump ? p.dump + env : nullptr);
+    stage_eval(cx, w, *p.K, p.plan, p.plan_id ? p.plan_id[env] : 0, p.dump ? p.dump + env : nullptr);
     for (int i = threadIdx.x; i < 30; i += NT) p.vh[(size_t)env * 30 + i] = w.vh[i];
     for (int i = threadIdx.x; i < 3; i += NT) p.com[(size_t)env * 3 + i] = w.com[i];
+}
+
+// Config 5 micro-benchmark: the model phases once at the frozen state, then `repeats` cold-started solves of the
+// WBC QP (mode 0; H/g data, factorisation, active set, back-substitution: everything controller.cpp:388-479 +
+// qpOASES do per call) or `repeats` evaluations of the LIPM-MPC (mode 1).  out: [E][42] = a (30), f (12).
+template <int NT>
+__global__ void __launch_bounds__(NT) qp_bench_kernel(Params p, int repeats, int mode, double* out) {
+    extern __shared__ double smem[];
+    EnvWS& w = *reinterpret_cast<EnvWS*>(smem);
+    const int env = blockIdx.x;
+    if (env >= p.n_env) return;
+    Ctx<NT> cx{(int)threadIdx.x, 0};
+    const Consts& K = *p.K;
+    for (int i = threadIdx.x; i < 30; i += NT) {
+        w.q[i] = p.x[(size_t)env * 60 + i];
+        w.v[i] = p.x[(size_t)env * 60 + 30 + i];
+        w.vh[i] = p.vh[(size_t)env * 30 + i];
+    }
+    if (threadIdx.x == 0) w.t = p.t[env];
+    ws_reset(cx, w);
+    const int plan_id = p.plan_id ? p.plan_id[env] : 0;
+    model_phases(cx, w, K);
+    mpc_pd_phase(cx, w, K, p.plan, plan_id);
+    for (int r = 0; r < repeats; ++r) {
+        if (mode == 1) { mpc_pd_phase(cx, w, K, p.plan, plan_id); continue; }
+        ws_reset(cx, w);                  // cold start, like the reference's SQProblem::init every call
+        qp_stage(cx, w, K, nullptr);
+    }
+    for (int i = threadIdx.x; i < 42; i += NT) out[(size_t)env * 42 + i] = i < 30 ? w.a[i] : w.f12[i - 30];
 }
 
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -131,7 +157,7 @@ struct LmhBatch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
     double *d_x = nullptr, *d_vh = nullptr, *d_t = nullptr, *d_push_dv = nullptr, *d_com = nullptr;
-    double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr, *d_qp_scratch = nullptr;
+    double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr;
     int32_t *d_plan_id = nullptr, *d_push_step = nullptr;
     LmhStats* d_stats = nullptr;
     LmhStats* d_stats0 = nullptr;
@@ -157,7 +183,7 @@ Params make_params(LmhBatch* h) {
     p.x = h->d_x; p.vh = h->d_vh; p.t = h->d_t;
     p.push_step = h->has_pushes ? h->d_push_step : nullptr;
     p.push_dv = h->d_push_dv;
-    p.stats = h->d_stats; p.log = h->d_log; p.dump = nullptr; p.com = h->d_com; p.qp_scratch = h->d_qp_scratch;
+    p.stats = h->d_stats; p.log = h->d_log; p.dump = nullptr; p.com = h->d_com;
     p.n_env = h->n_env; p.n_steps = 0; p.step0 = h->step_counter; p.log_cap = h->cfg.log_steps;
     return p;
 }
@@ -250,7 +276,6 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     CU(cudaMalloc(&h->d_x, E * 60 * sizeof(double))); CU(cudaMalloc(&h->d_vh, E * 30 * sizeof(double)));
     CU(cudaMalloc(&h->d_t, E * sizeof(double))); CU(cudaMalloc(&h->d_push_dv, E * 6 * sizeof(double)));
     CU(cudaMalloc(&h->d_com, E * 3 * sizeof(double)));
-    CU(cudaMalloc(&h->d_qp_scratch, E * QP_SCRATCH_DOUBLES * sizeof(double)));
     CU(cudaMalloc(&h->d_plan_id, E * sizeof(int32_t))); CU(cudaMalloc(&h->d_push_step, E * sizeof(int32_t)));
     CU(cudaMalloc(&h->d_stats, E * sizeof(LmhStats)));
     CU(cudaMalloc(&h->d_dump, E * sizeof(LmhStageDump)));
@@ -269,7 +294,7 @@ void lmh_destroy(LmhBatch* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com); cudaFree(h->d_qp_scratch);
+    cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
     cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
     cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -537,6 +562,32 @@ int32_t lmh_timer_stop(LmhBatch* h, double* ms) {
     float f = 0;
     CU(cudaEventElapsedTime(&f, h->ev0, h->ev1));
     if (ms) *ms = f;
+    return LMH_OK;
+}
+
+int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out, double* elapsed_ms) {
+    if (!h || repeats <= 0 || mode < 0 || mode > 1) return fail(LMH_EINVAL, "lmh_qp_bench: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    double* d_out = nullptr;
+    CU(cudaMalloc(&d_out, (size_t)h->n_env * 42 * sizeof(double)));
+    Params p = make_params(h);
+    dim3 grid(h->n_env), block(h->nt);
+    CU(cudaFuncSetAttribute(qp_bench_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+    CU(cudaFuncSetAttribute(qp_bench_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+    CU(cudaFuncSetAttribute(qp_bench_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    if (h->nt == 32) qp_bench_kernel<32><<<grid, block, h->smem, h->stream>>>(p, repeats, mode, d_out);
+    else if (h->nt == 64) qp_bench_kernel<64><<<grid, block, h->smem, h->stream>>>(p, repeats, mode, d_out);
+    else qp_bench_kernel<128><<<grid, block, h->smem, h->stream>>>(p, repeats, mode, d_out);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    if (elapsed_ms) *elapsed_ms = f;
+    if (a_f_out) CU(cudaMemcpy(a_f_out, d_out, (size_t)h->n_env * 42 * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_out);
+    h->launches += 1;
     return LMH_OK;
 }
 

@@ -49,7 +49,6 @@ constexpr int LDQ = 33;
 constexpr int ND1 = 18;     // base + both legs: the block of H_a that the sole Jacobians couple
 constexpr int LD1 = 19;
 constexpr int NYR = 10;     // right-hand-side rows carried through the factorisation
-constexpr int QP_SCRATCH_DOUBLES = 8;   // (the c-space fallback that used a global scratch is gone)   // per-env global scratch of the rare c-space fallback
 
 // chain c: frames chain_first[c] .. chain_first[c]+chain_len[c]-1, depth 1..chain_len[c]
 LMH_HD int chain_first(int c) { return c == 0 ? 1 : c == 1 ? 8 : c == 2 ? 15 : c == 3 ? 20 : 25; }
@@ -892,8 +891,7 @@ __device__ void qp_backsolve_warp(EnvWS& w, int lane);
 // leaving   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I,
 // which a primal active-set method solves exactly (masked Cholesky of Q per working set).
 template <class Cx>
-LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, double* gscratch, bool factor_done) {
-    (void)gscratch;
+LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done) {
     double* L1 = w.u.s.L1;
     double* Yt = w.u.s.Yt;
     double* Gm = w.u.s.Gm;
@@ -1443,9 +1441,9 @@ namespace lmh {
 
 // One dynamics(x,t) evaluation.  On entry w.q, w.v, w.vh, w.t are set; on exit w.xdot, w.tau, w.f12,
 // w.qpp (and every intermediate) are valid and w.vh has been advanced to this stage's velocity.
+// model part of a stage: kinematics, dynamics, Jacobians (everything up to the controller)
 template <class Cx>
-LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, double* gscratch,
-                        LmhStageDump* dump = nullptr) {
+LMH_HDN void model_phases(const Cx& cx, EnvWS& w, const Consts& K) {
     fk_phase(cx, w, K);
     base_twist_phase(cx, w);
 #if defined(__CUDA_ARCH__)
@@ -1460,7 +1458,11 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
         crba_phase(cx, w, K);
     }
     centroidal_jacobian_phase(cx, w, K);
-    mpc_pd_phase(cx, w, K, P, plan_id);
+}
+
+// QP data + solve of a stage (controller.cpp:94-132, 388-479)
+template <class Cx>
+LMH_HDN void qp_stage(const Cx& cx, EnvWS& w, const Consts& K, LmhStageDump* dump) {
     bool factor_done = false;
 #if defined(__CUDA_ARCH__)
     if (Cx::NT == 32 && K.wCoMK == 0.0) {
@@ -1474,7 +1476,14 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
         assemble_phase(cx, w, K);
         if (dump) dump_assembly(cx, w, K, dump);
     }
-    qp_phase(cx, w, K, gscratch, factor_done);
+    qp_phase(cx, w, K, factor_done);
+}
+
+template <class Cx>
+LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, LmhStageDump* dump = nullptr) {
+    model_phases(cx, w, K);
+    mpc_pd_phase(cx, w, K, P, plan_id);
+    qp_stage(cx, w, K, dump);
     output_phase(cx, w);
     if (dump) dump_stage(cx, w, dump);
     LMH_FOR(i, NQ) w.vh[i] = w.v[i];     // Robot::updateVelocityState (Robot.cpp:271-274)
@@ -1491,7 +1500,7 @@ struct StatsAcc {
 // [60] scratch, t: the env clock (same value in every thread of the group).
 template <class Cx>
 LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t, const Consts& K, const Plan& P,
-                      int plan_id, double* gscratch, LmhStepLog* log, StatsAcc* st) {
+                      int plan_id, LmhStepLog* log, StatsAcc* st) {
     const double dt = K.dt;
     const double half = 0.5 * dt;
     int iters = 0, fails = 0, nfall = 0;
@@ -1503,7 +1512,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         }
         LMH_FOR(i, 1) w.t = stage == 0 ? t : mul_then_add(t, stage == 3 ? 1.0 : 0.5, dt);
         cx.sync();
-        stage_eval(cx, w, K, P, plan_id, gscratch);
+        stage_eval(cx, w, K, P, plan_id);
         LMH_FOR(i, 2 * NQ) {
             double k = w.xdot[i];
             kacc[i] = stage == 0 ? k : stage == 3 ? kacc[i] + k : mul_then_add(kacc[i], 2.0, k);

@@ -12,7 +12,6 @@ struct Emu {
     int32_t contact_both = 3;
     std::vector<double> wzx, wzy, wfc;
     std::vector<int32_t> wct;
-    std::vector<double> scratch = std::vector<double>(QP_SCRATCH_DOUBLES);
     explicit Emu(const Scenario& s) : hm(s) {
         plan.zmp_x = hm.zmp_x.data();
         plan.zmp_y = hm.zmp_y.data();
@@ -60,7 +59,7 @@ void emu_stage(void* p, const double* x60, double* vheld30, double t, LmhStageDu
     w.t = t;
     Ctx<1> cx{0, 0};
     ws_reset(cx, w);
-    stage_eval(cx, w, e->hm.K, e->plan, 0, e->scratch.data(), dump);
+    stage_eval(cx, w, e->hm.K, e->plan, 0, dump);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
 }
 void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps, LmhStepLog* logs, LmhStats* stats) {
@@ -71,7 +70,7 @@ void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps,
     StatsAcc st{0, 0, 0, 0, 0, 0, 1, 0};
     Ctx<1> cx{0, 0};
     ws_reset(cx, w);
-    for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, e->scratch.data(), logs ? logs + s : nullptr, &st);
+    for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, logs ? logs + s : nullptr, &st);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
     if (stats) {
         stats->max_abs_tau = st.max_tau; stats->max_com_err = st.max_err; stats->max_abs_qpp = st.max_qpp;

@@ -261,3 +261,25 @@ def test_walking_extension_against_oracle(oracle):
     assert (d["phase"] == 1).all() and np.abs(d["f"][:, :6]).max() == 0.0     # integer phase index; swing foot force-free
     with pytest.raises(lmh.LmhError):
         b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"] + 4, plan_ids=np.arange(E))
+
+
+def test_qp_microbenchmark_entry(oracle):
+    """config 5: cold-started WBC QPs on frozen states through lmh_qp_bench, against the oracle's solver"""
+    E = 32
+    step, dv = lmh.push_plan(range(E), max_step=10)
+    b = lmh.Batch(E)
+    b.set_pushes(step, dv)
+    b.step(15)
+    X, VH, T = b.get_state()
+    ms, a, f = b.qp_bench(0, 3)
+    ms2, a2, f2 = b.qp_bench(0, 1)
+    assert np.array_equal(a, a2) and np.array_equal(f, f2) and ms > 0        # repeats are cold starts: same answer
+    so = oracle.sim()
+    for e in range(E):
+        so.set_state(X[e], T[e], VH[e])
+        d = so.stage(X[e], T[e])
+        assert relerr(a[e], d["x"][:30]) < 1e-7 and relerr(f[e], d["x"][30:42]) < 1e-7
+    msm, _, _ = b.qp_bench(1, 5)
+    assert msm > 0
+    with pytest.raises(lmh.LmhError):
+        b.qp_bench(2, 1)
