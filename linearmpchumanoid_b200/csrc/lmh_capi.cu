@@ -8,6 +8,7 @@
 #include "lmh_setup.hpp"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 using namespace lmh;
@@ -85,6 +86,54 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
     }
 }
 
+// One warp per environment, EPB environments per block (warp w of block b owns environment b*EPB + w and its own
+// slice of shared memory); the warps of a block are re-aligned at every stage so that they share instruction fetches.
+__global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes) {
+    extern __shared__ double smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    char* base = reinterpret_cast<char*>(smem) + (size_t)wid * env_bytes;
+    EnvWS& w = *reinterpret_cast<EnvWS*>(base);
+    double* x = reinterpret_cast<double*>(base) + (sizeof(EnvWS) + 7) / 8;
+    double* kacc = x + 60;
+    const int env_raw = blockIdx.x * epb + wid;
+    const bool live = env_raw < p.n_env;
+    const int env = live ? env_raw : p.n_env - 1;          // idle warps shadow the last environment and write nothing
+    Ctx<32> cx{lane, 1};
+    const Consts& K = *p.K;
+    ws_reset(cx, w);
+    for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
+    for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
+    double t = p.t[env];
+    const int plan_id = p.plan_id ? p.plan_id[env] : 0;
+    const int push_at = p.push_step ? p.push_step[env] : -1;
+    StatsAcc st;
+    {
+        const LmhStats& s0 = p.stats[env];
+        st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
+        st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
+    }
+    cx.sync();
+    for (int s = 0; s < p.n_steps; ++s) {
+        const int gstep = p.step0 + s;
+        if (gstep == push_at) {
+            for (int k = lane; k < 6; k += 32) x[30 + k] += p.push_dv[(size_t)env * 6 + k];
+            cx.sync();
+        }
+        LmhStepLog* lg = (live && p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
+        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, lg, &st);
+    }
+    if (!live) return;
+    for (int i = lane; i < 60; i += 32) p.x[(size_t)env * 60 + i] = x[i];
+    for (int i = lane; i < 30; i += 32) p.vh[(size_t)env * 30 + i] = w.vh[i];
+    for (int i = lane; i < 3; i += 32) p.com[(size_t)env * 3 + i] = w.com[i];
+    if (lane == 0) {
+        p.t[env] = t;
+        LmhStats& s1 = p.stats[env];
+        s1.max_abs_tau = st.max_tau; s1.max_com_err = st.max_err; s1.max_abs_qpp = st.max_qpp;
+        s1.qp_iters = st.qp_iters; s1.qp_fail = st.qp_fail; s1.steps = st.steps; s1.alive = st.alive; s1.qp_fallback = st.qp_fallback; s1.pad = 0;
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) stage_kernel(Params p) {
     extern __shared__ double smem[];
@@ -152,7 +201,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 struct LmhBatch {
     LmhConfig cfg;
     HostModel* hm = nullptr;
-    int32_t n_env = 0, nt = 64, smem = 0;
+    int32_t n_env = 0, nt = 64, smem = 0, epb = 5;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
@@ -213,6 +262,10 @@ int32_t launch_rollout(LmhBatch* h, int32_t n_steps) {
     Params p = make_params(h);
     p.n_steps = n_steps;
     dim3 grid(h->n_env), block(h->nt);
+    if (h->nt == 32 && h->epb > 1) {
+        const int nblk = (h->n_env + h->epb - 1) / h->epb;
+        rollout_kernel_multi<<<nblk, 32 * h->epb, (size_t)h->smem * h->epb, h->stream>>>(p, h->epb, h->smem);
+    } else
     if (h->nt == 32) rollout_kernel<32><<<grid, block, h->smem, h->stream>>>(p);
     else if (h->nt == 64) rollout_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
     else rollout_kernel<128><<<grid, block, h->smem, h->stream>>>(p);
@@ -266,6 +319,12 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
         return fail(LMH_EINVAL, std::string("lmh_create: setup failed: ") + ex.what());
     }
     h->smem = (int32_t)(((sizeof(EnvWS) + 7) / 8 + kExtraDoubles) * sizeof(double));
+    if (const char* extra = std::getenv("LMH_EXTRA_SMEM")) h->smem += std::atoi(extra);   // occupancy experiments only
+    h->smem = (h->smem + 15) / 16 * 16;
+    if (const char* e2 = std::getenv("LMH_EPB")) h->epb = std::atoi(e2);
+    if (h->nt != 32 || h->epb < 1) h->epb = 1;
+    if (h->epb > 10) h->epb = 10;
+    if (h->epb > 1) CU(cudaFuncSetAttribute(rollout_kernel_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem * h->epb));
     int32_t rc = h->nt == 32 ? configure_kernels<32>(h->smem) : h->nt == 64 ? configure_kernels<64>(h->smem) : configure_kernels<128>(h->smem);
     if (rc != LMH_OK) { delete h->hm; delete h; return rc; }
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -594,9 +653,9 @@ int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out
 int32_t lmh_launch_info(const LmhBatch* h, int32_t* nt, int32_t* epb, int32_t* smem, int32_t* blocks, int32_t* launches) {
     if (!h) return fail(LMH_EINVAL, "null handle");
     if (nt) *nt = h->nt;
-    if (epb) *epb = 1;
+    if (epb) *epb = h->epb;
     if (smem) *smem = h->smem;
-    if (blocks) *blocks = h->n_env;
+    if (blocks) *blocks = (h->n_env + h->epb - 1) / h->epb;
     if (launches) *launches = h->launches;
     return LMH_OK;
 }

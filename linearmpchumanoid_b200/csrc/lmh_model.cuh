@@ -180,11 +180,16 @@ template <int NT_>
 struct Ctx {
     static constexpr int NT = NT_;
     int tid;
-    int bar_id;
+    int bar_id;          // > 0: several one-warp environments share a block and re-align at align() points
+    LMH_HD void align() const {
+#if defined(__CUDA_ARCH__)
+        if (NT == 32 && bar_id > 0) __syncthreads();
+#endif
+    }
     LMH_HD void sync() const {
 #if defined(__CUDA_ARCH__)
         if (NT == 32) __syncwarp();
-        else if (NT > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT_) : "memory");
+        else if (NT > 32) asm volatile("bar.sync 0, %0;" ::"n"(NT_) : "memory");
 #endif
     }
 };
@@ -1506,6 +1511,11 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
     int iters = 0, fails = 0, nfall = 0;
     for (int stage = 0; stage < 4; ++stage) {
         const double cstage = stage == 0 ? 0.0 : stage == 3 ? dt : half;
+#if defined(__CUDA_ARCH__)
+        // several one-warp environments per block: re-align their instruction streams once per stage so that the
+        // instruction cache (74 % hit rate: the stage code is far larger than the cache) serves them together
+        cx.align();
+#endif
         LMH_FOR(i, 2 * NQ) {
             double xi = stage == 0 ? x[i] : mul_then_add(x[i], cstage, w.xdot[i]);
             if (i < NQ) w.q[i] = xi; else w.v[i - NQ] = xi;
