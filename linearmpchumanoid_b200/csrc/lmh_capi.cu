@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
         const LmhStats& s0 = p.stats[env];
         st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
         st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
+        if (cx.tid == 0) w.dead = s0.alive ? 0 : 1;
     }
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
         const LmhStats& s0 = p.stats[env];
         st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
         st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
+        if (cx.tid == 0) w.dead = s0.alive ? 0 : 1;
     }
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {

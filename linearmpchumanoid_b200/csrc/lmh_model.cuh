@@ -129,7 +129,8 @@ struct EnvWS {
     int32_t pdone[12], ppiv[2];
     int32_t k_index, qp_iters, qp_status, qp_fallback;
     int32_t phase, contact;        // walking extension: phase index and contact mask of this stage
-    int32_t warm_contact, pad1_;   // contact mask the stored working set (free_mask, c) belongs to; -1 = none
+    int32_t warm_contact, dead;    // contact mask the stored working set (free_mask, c) belongs to (-1 = none);
+                                   // dead: the environment fell (state frozen, statistics closed)
     // ---- phase-overlaid scratch
     union {
         struct {                       // model phase
@@ -304,7 +305,7 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane);
 template <class Cx>
 LMH_HDN void ws_reset(const Cx& cx, EnvWS& w) {
     LMH_FOR(i, NC) { w.free_mask[i] = 1; w.c[i] = 0.0; }
-    LMH_FOR(i, 1) w.warm_contact = -1;
+    LMH_FOR(i, 1) { w.warm_contact = -1; w.dead = 0; }
     cx.sync();
 }
 
@@ -1534,7 +1535,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
             LMH_FOR(i, 1) log->k_index[stage] = w.k_index;
             if (stage == 0) { LMH_FOR(i, NJ) log->tau_k1[i] = w.tau[i]; }
         }
-        if (st && stage == 0) {
+        if (st && stage == 0 && w.dead == 0) {
 #if defined(__CUDA_ARCH__)
             if (Cx::NT == 32) {
                 const int i = cx.tid;
@@ -1554,13 +1555,14 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         cx.sync();
     }
     const double sixth = dt / 6.0;
-    LMH_FOR(i, 2 * NQ) x[i] = mul_then_add(x[i], sixth, kacc[i]);
+    const bool dead = w.dead != 0;        // a fallen environment keeps its last state: the batch goes on without it
+    if (!dead) { LMH_FOR(i, 2 * NQ) x[i] = mul_then_add(x[i], sixth, kacc[i]); }
     t = t + dt;
     if (log) {
         LMH_FOR(i, 3) { log->com_k4[i] = w.com[i]; log->rfoot[i] = w.ps[0][i]; log->lfoot[i] = w.ps[1][i]; }
         LMH_FOR(i, 1) { log->qp_iters = iters; log->qp_fail = fails; }
     }
-    if (st) {
+    if (st && !dead) {
         LMH_FOR(i, 1) {
             int k0 = w.k_index;
             if (k0 < 0) k0 = 0;
@@ -1577,14 +1579,14 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         if (Cx::NT == 32) {
             const int i = cx.tid;
             const bool bad = !(fabs(x[i]) < 1e6) || (i < 28 && !(fabs(x[32 + i]) < 1e6)) || !(x[2] > 0.15);
-            if (__any_sync(0xffffffffu, bad)) st->alive = 0;
+            if (__any_sync(0xffffffffu, bad)) { st->alive = 0; if (i == 0) w.dead = 1; }
         } else
 #endif
         {
         LMH_FOR(i, 1) {
             bool ok = x[2] > 0.15;
             for (int j = 0; j < 2 * NQ; ++j) ok = ok && (fabs(x[j]) < 1e6);
-            if (!ok) st->alive = 0;
+            if (!ok) { st->alive = 0; w.dead = 1; }
         }
         }
     }

@@ -1,7 +1,7 @@
 """rank-revealing wrench-space primal active set (prototype of the kernel algorithm)"""
 import sys; sys.path.insert(0,'/root/repo/scratch'); sys.path.insert(0,'/root/repo/oracle')
 import numpy as np, orc_py
-from qp_proto import G, eps, wF
+from qp_common import G, eps, wF
 Gf=G[:6,:16]
 def pchol6(P, tol=1e-10):
     """diagonally pivoted Cholesky of a 6x6 PSD matrix -> B (6x6, zero columns beyond the rank) with P = B B'"""

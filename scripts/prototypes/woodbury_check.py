@@ -1,6 +1,6 @@
 import sys; sys.path.insert(0,'/root/repo/scratch'); sys.path.insert(0,'/root/repo/oracle')
 import numpy as np, orc_py
-from qp_proto import G, eps, wF
+from qp_common import G, eps, wF
 q=np.load('/root/repo/tests/golden/qp_exact.npz')
 O=orc_py.oracle(); s=O.sim()
 rel=lambda a,b: np.abs(a-b).max()/max(1,np.abs(b).max())

@@ -214,7 +214,16 @@ def test_plans_and_edge_cases():
     b.set_state(x, vh, np.zeros(5))
     b.step(3)
     st = b.stats()
-    assert np.isfinite(b.get_state()[0][[0, 1, 2, 4]]).all() and (st["steps"] == 3).all()
+    assert np.isfinite(b.get_state()[0][[0, 1, 2, 4]]).all() and (st["steps"][[0, 1, 2, 4]] == 3).all()
+    # ... and a fallen environment is frozen at its last state (finite), its statistics closed, alive = 0
+    b.step(20)
+    xs = b.get_state()[0]
+    st = b.stats()
+    assert np.isfinite(xs).all() and (st["alive"][[0, 1, 2, 4]] == 1).all()
+    if st["alive"][3] == 0:
+        x_frozen = xs[3].copy()
+        b.step(5)
+        assert np.array_equal(b.get_state()[0][3], x_frozen) and np.isfinite(b.stats()["max_abs_tau"]).all()
 
 
 def test_offline_app_on_the_facade_classes(golden, tmp_path):
