@@ -59,7 +59,7 @@ for si, start in enumerate(sections):
     ts, ti = sum(l[2] for l in lines) or 1, sum(l[3] for l in lines) or 1
     text = open(path).read().split("\n") if os.path.exists(path) else []
     funcs = [(n, m.group(1)) for n, l in enumerate(text, 1)
-             for m in [re.match(r"(?:LMH_HDN?|__global__)\s+.*?(\w+)\(", l)] if m]
+             for m in [re.match(r"(?:LMH_HDN?|__global__|__device__(?: __forceinline__)?)\s+.*?(\w+)\(", l)] if m]
     agg = {}
     for ln, _, s, i in lines:
         k = bisect.bisect_right([f[0] for f in funcs], ln) - 1
