@@ -22,6 +22,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "lmh_capi.h"
 
 #if defined(__CUDACC__)
@@ -107,7 +108,7 @@ struct Plan {
 struct EnvWS {
     // ---- state of the stage being evaluated
     double q[NQ], v[NQ], vh[NQ];   // vh: velocity held by the Robot object from the PREVIOUS stage (controller.cpp:48-79)
-    double vb6[6], vhb6[6];        // base twists of v and vh as [omega; v] in the torso frame (joint rates are unchanged)
+    alignas(16) double vb6[6], vhb6[6];        // base twists of v and vh as [omega; v] in the torso frame (joint rates are unchanged)
     double t;
     // ---- persistent through a stage
     double R0[9], p0[3];           // torso pose
@@ -132,7 +133,7 @@ struct EnvWS {
     int32_t warm_contact, dead;    // contact mask the stored working set (free_mask, c) belongs to (-1 = none);
                                    // dead: the environment fell (state frozen, statistics closed)
     // ---- phase-overlaid scratch
-    union {
+    union alignas(16) {
         struct {                       // model phase
             double Xl[NF * 12];        // local transform first, then parent-relative (R_rel, p_rel)
             union {
@@ -146,8 +147,9 @@ struct EnvWS {
                 } crba;
                 double Xn[2][2 * 18];  // running sole_X_j as (E, B) for both feet, double buffered
                 struct {               // exchange buffers of the one-warp-per-env versions (lmh_warp.cuh)
-                    double vbuf[2][32], abuf[2][32], hbuf[32], contrib[32], col2[32], accs[12];
-                    double frc[NF * 6];
+                    // six-vectors at stride 8 (chain c at 8c, frame i at 8i): 16-byte aligned for vector loads
+                    double vbuf[2][40], abuf[2][40], hbuf[40], contrib[40], col2[40], accs[12];
+                    double frc[NF * 8];
                     double Ybuf[NCH * 36], Ybuf2[NCH * 36];
                 } wr;
             } p;
@@ -163,6 +165,8 @@ struct EnvWS {
         } s;
     } u;
 };
+
+static_assert(offsetof(EnvWS, p0) == offsetof(EnvWS, R0) + 9 * sizeof(double), "(R0, p0) must be one (R, p) pair");
 
 // compact column of generalized coordinate i in the Jacobian of foot s, or -1
 LMH_HD int jf_col(int s, int i) {
@@ -234,19 +238,29 @@ LMH_HD double lmh_rsqrt(double x) {
 
 // in-place Cholesky of a 6x6 SPD matrix held in registers (lower triangle), fully unrolled
 LMH_HD void chol6(double* A) {
-    LMH_UNROLL
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
     for (int k = 0; k < 6; ++k) {
         double s = A[7 * k];
-        LMH_UNROLL
-        for (int m = 0; m < k; ++m) s -= A[6 * k + m] * A[6 * k + m];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int m = 0; m < 6; ++m) if (m < k) s -= A[6 * k + m] * A[6 * k + m];
         const double inv = lmh_rsqrt(s);
         A[7 * k] = s * inv;
-        LMH_UNROLL
-        for (int i = k + 1; i < 6; ++i) {
-            double t = A[6 * i + k];
-            LMH_UNROLL
-            for (int m = 0; m < k; ++m) t -= A[6 * i + m] * A[6 * k + m];
-            A[6 * i + k] = t * inv;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                double t = A[6 * i + k];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for (int m = 0; m < 6; ++m) if (m < k) t -= A[6 * i + m] * A[6 * k + m];
+                A[6 * i + k] = t * inv;
+            }
         }
     }
 }
@@ -430,10 +444,7 @@ LMH_HDN void base_twist_phase(const Cx& cx, EnvWS& w) {
         int which = it / 6, k = it % 6;
         const double* src = which == 0 ? w.v : w.vh;
         double m[6] = {src[3], src[4], src[5], src[0], src[1], src[2]};
-        double Rp[12];
-        for (int e = 0; e < 9; ++e) Rp[e] = w.R0[e];
-        for (int e = 0; e < 3; ++e) Rp[9 + e] = w.p0[e];
-        (which == 0 ? w.vb6 : w.vhb6)[k] = xmotion_k(Rp, m, k);
+        (which == 0 ? w.vb6 : w.vhb6)[k] = xmotion_k(w.R0, m, k);     // (R0, p0) are adjacent: one (R, p) pair
     }
     cx.sync();
 }
@@ -970,8 +981,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         LMH_UNROLL
         for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
         chol6(A);
-        LMH_FOR(e, 36) w.Ls[e] = A[e];
-        LMH_FOR(e, 6) w.Lsi[e] = 1.0 / A[7 * e];
+        LMH_UNROLL
+        for (int e = 0; e < 36; ++e) if (e % Cx::NT == cx.tid) w.Ls[e] = A[e];      // static indices: A stays in registers
+        LMH_UNROLL
+        for (int e = 0; e < 6; ++e) if (e % Cx::NT == cx.tid) w.Lsi[e] = 1.0 / A[7 * e];
     }
     const double* Ls = w.Ls;
     const double* Lsi = w.Lsi;

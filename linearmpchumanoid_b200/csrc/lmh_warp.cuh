@@ -40,6 +40,27 @@ __device__ __forceinline__ void load12(const double* p, double* o) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) o[k] = p[k];
 }
+// 16-byte aligned sources: LDS.128, half the shared-memory wavefronts of the scalar loads
+__device__ __forceinline__ void ld6v(const double* p, double* o) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double2 t = q[k]; o[2 * k] = t.x; o[2 * k + 1] = t.y; }
+}
+__device__ __forceinline__ void ld12v(const double* p, double* o) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double2 t = q[k]; o[2 * k] = t.x; o[2 * k + 1] = t.y; }
+}
+// row r of X m for the lane that holds row k3 = r % 3 of E (e0..e2) and p: E m_ang (r < 3) or E (m_lin + m_ang x p)
+__device__ __forceinline__ double xm_lane(double e0, double e1, double e2, double p0, double p1, double p2, const double* m, bool lin) {
+    double a0 = m[0], a1 = m[1], a2 = m[2];
+    if (lin) {
+        a0 = m[3] + (m[1] * p2 - m[2] * p1);
+        a1 = m[4] + (m[2] * p0 - m[0] * p2);
+        a2 = m[5] + (m[0] * p1 - m[1] * p0);
+    }
+    return e0 * a0 + e1 * a1 + e2 * a2;
+}
 // row r of X m, X = [[E,0],[-E p^,E]], E = R'
 __device__ __forceinline__ double xm_row(const double* Rp, const double* m, int r) {
     if (r < 3) return Rp[r] * m[0] + Rp[3 + r] * m[1] + Rp[6 + r] * m[2];
@@ -96,14 +117,14 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
     double cm0 = 0.0, cm1 = 0.0, cm2 = 0.0;
     if (lane < NF) {
         double Ti[12];
-        load12(Tw + 12 * lane, Ti);
+        ld12v(Tw + 12 * lane, Ti);
         double* O = Xl + 12 * lane;
         if (lane == 0) {
 #pragma unroll
             for (int e = 0; e < 12; ++e) O[e] = Ti[e];
         } else {
             double P[12];
-            load12(Tw + 12 * frame_parent(lane), P);
+            ld12v(Tw + 12 * frame_parent(lane), P);
 #pragma unroll
             for (int r3 = 0; r3 < 3; ++r3) {
 #pragma unroll
@@ -137,91 +158,98 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
 }
 
 // ---- RNEA with zero base acceleration on the held velocity (Dynamics.cpp:29-60,124-200) -> Cg, Jpqp
+// Every lane runs every level (idle lanes shadow the last frame of their chain and store nothing): no divergent
+// regions, so the exchanges of the backward pass can be shuffles.  A lane reads only the column of R it needs
+// straight from shared memory (a lane-dependent index into a register copy would put the copy in local memory).
 __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
     auto& S = w.u.m.p.wr;
     const double* Xl = w.u.m.Xl;
-    const int c6 = 6 * L.c, r = L.r;
+    const int c8 = 8 * L.c, r = L.r;
+    const bool lin = r >= 3;
+    const int k3 = lin ? r - 3 : r;
     // base: f0 = v0 x* (I0 v0), acc0 = 0
     if (lane < 6) {
         double v0[6];
-        load6(w.vhb6, v0);
+        ld6v(w.vhb6, v0);
         const double* I = K.Isp + 6 * lane;
         S.hbuf[lane] = I[0] * v0[0] + I[1] * v0[1] + I[2] * v0[2] + I[3] * v0[3] + I[4] * v0[4] + I[5] * v0[5];
     }
     __syncwarp();
     if (lane < 6) {
         double v0[6], h[6];
-        load6(w.vhb6, v0);
-        load6(S.hbuf, h);
+        ld6v(w.vhb6, v0);
+        ld6v(S.hbuf, h);
         S.frc[lane] = lane < 3 ? cross3(v0, h, lane) + cross3(v0 + 3, h + 3, lane) : cross3(v0, h + 3, lane - 3);
     }
     int cur = 0;
 #pragma unroll 1
     for (int d = 1; d <= MAXDEPTH; ++d) {
         const bool act = L.on && d <= L.len;
-        const int i = L.first + d - 1;
+        const int i = L.first + (d <= L.len ? d : L.len) - 1;
         const bool joint = act && d <= L.nact;
-        double Rp[12], Irow[6], nv[6];
-        double qd = 0.0;
-        if (act) {
-            double pv[6];
-            load12(Xl + 12 * i, Rp);
-            if (d == 1) load6(w.vhb6, pv); else load6(S.vbuf[cur] + c6, pv);
-            double x = xm_row(Rp, pv, r);
-            if (joint) { qd = w.vh[6 + L.j0 + d - 1]; if (r == 2) x += qd; }
-            S.vbuf[cur ^ 1][c6 + r] = x;
-        }
+        const double* X = Xl + 12 * i;
+        const double e0 = X[k3], e1 = X[3 + k3], e2 = X[6 + k3];     // column k3 of R = row k3 of E
+        const double p0 = X[9], p1 = X[10], p2 = X[11];
+        double pv[6], nv[6], Irow[6];
+        ld6v(d == 1 ? w.vhb6 : S.vbuf[cur] + c8, pv);
+        double x = xm_lane(e0, e1, e2, p0, p1, p2, pv, lin);
+        const double qd = joint ? w.vh[6 + L.j0 + d - 1] : 0.0;
+        if (r == 2) x += qd;
+        if (act) S.vbuf[cur ^ 1][c8 + r] = x;
+        load6(K.Isp + 36 * i + 6 * r, Irow);
         __syncwarp();
-        if (act) {
+        ld6v(S.vbuf[cur ^ 1] + c8, nv);
+        double xa = 0.0;
+        if (d > 1) {
             double pa[6];
-            load6(S.vbuf[cur ^ 1] + c6, nv);
-            double x = 0.0;
-            if (d > 1) { load6(S.abuf[cur] + c6, pa); x = xm_row(Rp, pa, r); }
-            if (joint) {
-                const double col = r == 0 ? nv[1] : r == 1 ? -nv[0] : r == 3 ? nv[4] : r == 4 ? -nv[3] : 0.0;
-                x += col * qd;
-                load6(K.Isp + 36 * i + 6 * r, Irow);
-                S.hbuf[c6 + r] = Irow[0] * nv[0] + Irow[1] * nv[1] + Irow[2] * nv[2] + Irow[3] * nv[3] + Irow[4] * nv[4] + Irow[5] * nv[5];
-            }
-            S.abuf[cur ^ 1][c6 + r] = x;
-            if (d == 7) S.accs[c6 + r] = x;          // sole frames (legs only): spatial acceleration for Jdot*qdot
+            ld6v(S.abuf[cur] + c8, pa);
+            xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);
+        }
+        const double col = r == 0 ? nv[1] : r == 1 ? -nv[0] : r == 3 ? nv[4] : r == 4 ? -nv[3] : 0.0;
+        xa += col * qd;
+        const double hb = Irow[0] * nv[0] + Irow[1] * nv[1] + Irow[2] * nv[2] + Irow[3] * nv[3] + Irow[4] * nv[4] + Irow[5] * nv[5];
+        if (act) {
+            S.hbuf[c8 + r] = hb;
+            S.abuf[cur ^ 1][c8 + r] = xa;
+            if (d == 7) S.accs[6 * L.c + r] = xa;    // sole frames (legs only): spatial acceleration for Jdot*qdot
         }
         __syncwarp();
-        if (joint) {
+        {
             double na[6], h[6];
-            load6(S.abuf[cur ^ 1] + c6, na);
-            load6(S.hbuf + c6, h);
-            double x = Irow[0] * na[0] + Irow[1] * na[1] + Irow[2] * na[2] + Irow[3] * na[3] + Irow[4] * na[4] + Irow[5] * na[5];
-            x += r < 3 ? cross3(nv, h, r) + cross3(nv + 3, h + 3, r) : cross3(nv, h + 3, r - 3);
-            S.frc[6 * i + r] = x;
+            ld6v(S.abuf[cur ^ 1] + c8, na);
+            ld6v(S.hbuf + c8, h);
+            double f = Irow[0] * na[0] + Irow[1] * na[1] + Irow[2] * na[2] + Irow[3] * na[3] + Irow[4] * na[4] + Irow[5] * na[5];
+            f += lin ? cross3(nv, h + 3, k3) : cross3(nv, h, k3) + cross3(nv + 3, h + 3, k3);
+            if (joint) S.frc[8 * i + r] = f;
         }
         cur ^= 1;
     }
     __syncwarp();
-    // backward pass: deepest actuated level first
+    // backward pass, deepest actuated level first: row r of X' f = [R n + p x (R f); R f].  A lane forms (R f)[k3];
+    // the angular lanes fetch the other two components of R f from their chain by shuffle.
+    const int k1 = k3 == 2 ? 0 : k3 + 1, k2 = k3 == 0 ? 2 : k3 - 1;
+    const int src1 = 6 * L.c + k1, src2 = 6 * L.c + k2;
 #pragma unroll 1
-    for (int d = MAXDEPTH - 1; d >= 2; --d) {
-        if (L.on && d <= L.nact) {
-            const int i = L.first + d - 1;
-            double Rp[12], f[6];
-            load12(Xl + 12 * i, Rp);
-            load6(S.frc + 6 * i, f);
-            S.frc[6 * (i - 1) + r] += xf_row(Rp, f, r);
+    for (int d = MAXDEPTH - 1; d >= 1; --d) {
+        const bool on = L.on && d <= L.nact;
+        const int i = L.first + (d <= L.nact ? d : L.nact) - 1;
+        const double* X = Xl + 12 * i;
+        double f[6];
+        ld6v(S.frc + 8 * i, f);
+        const double g0 = X[3 * k3], g1 = X[3 * k3 + 1], g2 = X[3 * k3 + 2];     // row k3 of R
+        const double rf = g0 * f[3] + g1 * f[4] + g2 * f[5];
+        const double rf1 = __shfl_sync(0xffffffffu, rf, src1), rf2 = __shfl_sync(0xffffffffu, rf, src2);
+        double o = rf;
+        if (!lin) o = g0 * f[0] + g1 * f[1] + g2 * f[2] + (X[9 + k1] * rf2 - X[9 + k2] * rf1);
+        if (on) {
+            if (d > 1) S.frc[8 * (i - 1) + r] += o; else S.contrib[c8 + r] = o;
         }
         __syncwarp();
     }
-    if (L.on) {
-        double Rp[12], f[6];
-        load12(Xl + 12 * L.first, Rp);
-        load6(S.frc + 6 * L.first, f);
-        S.contrib[c6 + r] = xf_row(Rp, f, r);
-        if (r == 2)
-            for (int d = 1; d <= L.nact; ++d) w.Cg[6 + L.j0 + d - 1] = S.frc[6 * (L.first + d - 1) + 2];
-    }
-    __syncwarp();
+    if (L.on && r < L.nact) w.Cg[6 + L.j0 + r] = S.frc[8 * (L.first + r) + 2];
     if (lane < 6) {
         double s = S.frc[lane];
-        for (int c = NCH - 1; c >= 0; --c) s += S.contrib[6 * c + lane];
+        for (int c = NCH - 1; c >= 0; --c) s += S.contrib[8 * c + lane];
         w.Cg[lane] = s;
     }
     if (lane >= 6 && lane < 18) {       // Jpqp = world-rotated sole accelerations
@@ -236,7 +264,9 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
 __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
     auto& S = w.u.m.p.wr;
     const double* Xl = w.u.m.Xl;
-    const int c6 = 6 * L.c, r = L.r;
+    const int c8 = 8 * L.c, r = L.r;
+    const bool lin = r >= 3;
+    const int k3 = lin ? r - 3 : r;
     double icin[6] = {0, 0, 0, 0, 0, 0};     // row r of the composite inertia arriving from the level below
     double F[6] = {0, 0, 0, 0, 0, 0};        // force vector of joint (c, r), expressed in the frame reached so far
     if (lane < 30) {
@@ -248,14 +278,14 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         const bool act = L.on && d <= L.nact;
         const int i = L.first + d - 1;
         double Rp[12];
+        double bs[3] = {0, 0, 0};             // B[k][r] of this lane (angular lanes), B = -E p^
         if (act) {
-            load12(Xl + 12 * i, Rp);
+            ld12v(Xl + 12 * i, Rp);
             double ic[6];
             load6(K.Isp + 36 * i + 6 * r, ic);
 #pragma unroll
             for (int k = 0; k < 6; ++k) ic[k] += icin[k];
-            S.col2[c6 + r] = ic[2];
-            // B = -E p^ (3x3), E = R'
+            S.col2[c8 + r] = ic[2];
             double y[6];
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
@@ -264,7 +294,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
                 y[3 + cc] = ic[3] * e0 + ic[4] * e1 + ic[5] * e2;
                 y[cc] = ic[0] * e0 + ic[1] * e1 + ic[2] * e2;
             }
-            // + ic[3:6] . B[:, cc],  B[k][cc] = -(E p^)[k][cc] ; (E p^)[k][:] = (E[k][1] p2 - E[k][2] p1, -E[k][0] p2 + E[k][2] p0, E[k][0] p1 - E[k][1] p0)
+            // + ic[3:6] . B[:, cc],  (E p^)[k][:] = (E[k][1] p2 - E[k][2] p1, -E[k][0] p2 + E[k][2] p0, E[k][0] p1 - E[k][1] p0)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const double ek0 = Rp[k], ek1 = Rp[3 + k], ek2 = Rp[6 + k];     // E[k][0..2]
@@ -272,6 +302,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
                 const double b1 = -(-ek0 * Rp[11] + ek2 * Rp[9]);
                 const double b2 = -(ek0 * Rp[10] - ek1 * Rp[9]);
                 y[0] += ic[3 + k] * b0; y[1] += ic[3 + k] * b1; y[2] += ic[3 + k] * b2;
+                bs[k] = r == 0 ? b0 : r == 1 ? b1 : b2;
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) S.Ybuf[36 * L.c + 6 * r + k] = y[k];
@@ -280,7 +311,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         __syncwarp();
         if (act) {
             // this lane's joint: pick up the new vector at its own depth, then cross frame i towards the root
-            if (r == d - 1) load6(S.col2 + c6, F);
+            if (r == d - 1) ld6v(S.col2 + c8, F);
             if (r >= d - 1 && r < L.nact) {
                 double o[6];
                 xf_all(Rp, F, o);
@@ -294,29 +325,27 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
                     for (int k = 0; k < 6; ++k) w.M6[NQ * k + 6 + L.j0 + r] = F[k];
                 }
             }
-            // row r of X' Y : sum_k X[k][r] Y[k][:]
-            double out[6] = {0, 0, 0, 0, 0, 0};
+            // row r of X' Y : sum_k X[k][r] Y[k][:].  X[k][r] = E[k][r] (r < 3, rows 0..2 of Y), X[3+k][r] = B[k][r]
+            // (r < 3) or E[k][r-3] (r >= 3), rows 3..5 of Y: E[k][k3] = R[k3][k] is one lane-dependent row of R
+            const double* Xr = Xl + 12 * i + 3 * k3;
+            const double x0 = Xr[0], x1 = Xr[1], x2 = Xr[2];
             const double* Yc = S.Ybuf + 36 * L.c;
-            if (r < 3) {
+            const double* Yo = Yc + (lin ? 18 : 0);
+            double out[6];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {           // X[k][r] = E[k][r] = R[r][k]
-                    const double x = Rp[3 * r + k];
+            for (int cc = 0; cc < 6; cc += 2) {
+                const double2 a = *reinterpret_cast<const double2*>(Yo + cc), b = *reinterpret_cast<const double2*>(Yo + 6 + cc),
+                              c = *reinterpret_cast<const double2*>(Yo + 12 + cc);
+                out[cc] = x0 * a.x + x1 * b.x + x2 * c.x;
+                out[cc + 1] = x0 * a.y + x1 * b.y + x2 * c.y;
+            }
+            if (!lin) {
 #pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) out[cc] += x * Yc[6 * k + cc];
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {           // X[3+k][r] = B[k][r]
-                    const double ek0 = Rp[k], ek1 = Rp[3 + k], ek2 = Rp[6 + k];
-                    const double x = r == 0 ? -(ek1 * Rp[11] - ek2 * Rp[10]) : r == 1 ? -(-ek0 * Rp[11] + ek2 * Rp[9]) : -(ek0 * Rp[10] - ek1 * Rp[9]);
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) out[cc] += x * Yc[6 * (3 + k) + cc];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {           // X[3+k][r] = E[k][r-3] = R[r-3][k]
-                    const double x = Rp[3 * (r - 3) + k];
-#pragma unroll
-                    for (int cc = 0; cc < 6; ++cc) out[cc] += x * Yc[6 * (3 + k) + cc];
+                for (int cc = 0; cc < 6; cc += 2) {
+                    const double2 a = *reinterpret_cast<const double2*>(Yc + 18 + cc), b = *reinterpret_cast<const double2*>(Yc + 24 + cc),
+                                  c = *reinterpret_cast<const double2*>(Yc + 30 + cc);
+                    out[cc] += bs[0] * a.x + bs[1] * b.x + bs[2] * c.x;
+                    out[cc + 1] += bs[0] * a.y + bs[1] * b.y + bs[2] * c.y;
                 }
             }
 #pragma unroll
@@ -356,7 +385,7 @@ __device__ void jacobian_warp(EnvWS& w, int lane) {
 #pragma unroll 1
         for (int i = start; i <= 6; ++i) {
             double Rp[12];
-            load12(Xl + 12 * (f0 + i), Rp);
+            ld12v(Xl + 12 * (f0 + i), Rp);
             const double u0 = v[3] + (v[1] * Rp[11] - v[2] * Rp[10]);
             const double u1 = v[4] + (v[2] * Rp[9] - v[0] * Rp[11]);
             const double u2 = v[5] + (v[0] * Rp[10] - v[1] * Rp[9]);
