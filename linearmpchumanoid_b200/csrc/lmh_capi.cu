@@ -203,7 +203,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 struct LmhBatch {
     LmhConfig cfg;
     HostModel* hm = nullptr;
-    int32_t n_env = 0, nt = 64, smem = 0, epb = 5;
+    int32_t n_env = 0, nt = 64, smem = 0, epb = 10;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;

@@ -940,14 +940,22 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     }
     // Gram matrix of the rows: Gm[r][c] = [.]_r D^-1 [.]_c'
     LMH_FOR(it, NYR * (NYR + 1) / 2) {
-        int r = 0;
-        while ((r + 1) * (r + 2) / 2 <= it) ++r;      // unrank the lower-triangular index (55 entries)
+        // unrank the lower-triangular index (55 entries): 8 it + 1 = (2r + 1)^2 at the start of row r, exact in float
+        const int r = (int)((sqrtf(8.0f * (float)it + 1.0f) - 1.0f) * 0.5f);
         const int c = it - r * (r + 1) / 2;
         {
             double s0 = 0.0, s1 = 0.0;
             const double* yr = Yt + NQ * r;
             const double* yc = Yt + NQ * c;
-            for (int m = 0; m < NQ; m += 2) { s0 += yr[m] * yc[m]; s1 += yr[m + 1] * yc[m + 1]; }
+            LMH_UNROLL
+            for (int m = 0; m < NQ; m += 2) {
+#if defined(__CUDA_ARCH__)
+                const double2 a = *reinterpret_cast<const double2*>(yr + m), b = *reinterpret_cast<const double2*>(yc + m);
+                s0 += a.x * b.x; s1 += a.y * b.y;
+#else
+                s0 += yr[m] * yc[m]; s1 += yr[m + 1] * yc[m + 1];
+#endif
+            }
             Gm[NYR * r + c] = s0 + s1;
             Gm[NYR * c + r] = s0 + s1;
         }
@@ -982,7 +990,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
         chol6(A);
         LMH_UNROLL
-        for (int e = 0; e < 36; ++e) if (e % Cx::NT == cx.tid) w.Ls[e] = A[e];      // static indices: A stays in registers
+        for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6 && e % Cx::NT == cx.tid) w.Ls[e] = A[e];      // lower triangle; static indices keep A in registers
         LMH_UNROLL
         for (int e = 0; e < 6; ++e) if (e % Cx::NT == cx.tid) w.Lsi[e] = 1.0 / A[7 * e];
     }
@@ -1007,9 +1015,15 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     // has clipped coefficients and the contact phase is the same.  The minimiser is unique: only the path changes.
     bool have_point = false;
     if (w.warm_contact == contact) {
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) have_point = __any_sync(0xffffffffu, ((contact >> (cx.tid / 16)) & 1) && !w.free_mask[cx.tid]);
+        else
+#endif
+        {
         int nclip = 0;
         for (int i = 0; i < NC; ++i) nclip += (((contact >> (i / 16)) & 1) && !w.free_mask[i]) ? 1 : 0;
         have_point = nclip > 0;
+        }
     }
     cx.sync();
     if (!have_point) {
@@ -1244,9 +1258,6 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         double alpha = 1.0;
         // multipliers come out of the cancellation wF f - Jb lam: anything below the round-off of those two terms is
         // zero (such coefficients only move c inside the null space of G, which no output depends on)
-        double rmax = 1.0;
-        for (int k = 0; k < 12; ++k) rmax = fmax(rmax, fabs(K.wForce * w.f12[k]) + fabs(vv[24 + k]));
-        const double mu_tol = -2e-10 * rmax;
 #if defined(__CUDA_ARCH__)
         if (Cx::NT == 32) {
             const int i = cx.tid;
@@ -1257,6 +1268,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
                 have_point = true;
                 if (cmin >= 0.0) done = true; else alpha = -1.0;
             } else if (cmin >= 0.0) {
+                const double mu_tol = -2e-10 * warp_max(i < 12 ? fmax(1.0, fabs(K.wForce * w.f12[i]) + fabs(vv[24 + i])) : 1.0);
                 const bool cand = !fr && ((contact >> (i / 16)) & 1) && mui < mu_tol;
                 const double vmin = warp_min(cand ? mui : 1e300);
                 const unsigned hit = __ballot_sync(0xffffffffu, cand && mui == vmin);
@@ -1273,6 +1285,9 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         } else
 #endif
         {
+        double rmax = 1.0;
+        for (int k = 0; k < 12; ++k) rmax = fmax(rmax, fabs(K.wForce * w.f12[k]) + fabs(vv[24 + k]));
+        const double mu_tol = -2e-10 * rmax;
         double cmin = 0.0;
         for (int i = 0; i < NC; ++i) if (w.free_mask[i] && w.cs[i] < cmin) cmin = w.cs[i];
         if (!have_point) {
@@ -1297,7 +1312,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
 #if defined(LMH_DEBUG_QP) && !defined(__CUDA_ARCH__)
         if (iters < 8) {
             int nf = 0; double cm = 0; for (int i = 0; i < NC; ++i) { nf += w.free_mask[i]; if (w.free_mask[i] && w.cs[i] < cm) cm = w.cs[i]; }
-            printf("it %d nfree %d cmin %.3e alpha %.3e change %d to_free %d done %d mu_tol %.2e mu[change] %.3e\n", iters, nf, cm, alpha, change, to_free, (int)done, mu_tol, change >= 0 ? w.mu[change] : 0.0);
+            printf("it %d nfree %d cmin %.3e alpha %.3e change %d to_free %d done %d mu[change] %.3e\n", iters, nf, cm, alpha, change, to_free, (int)done, change >= 0 ? w.mu[change] : 0.0);
         }
 #endif
         cx.sync();
@@ -1333,12 +1348,24 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     cx.sync();
     {
         double l[6];
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) {       // lane r < 6 forms its own entry, then every lane collects the six
+            const int r = cx.tid < 6 ? cx.tid : 0;
+            double s = w.rhs[r];
+            LMH_UNROLL
+            for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
+            LMH_UNROLL
+            for (int q = 0; q < 6; ++q) l[q] = __shfl_sync(0xffffffffu, s, q);
+        } else
+#endif
+        {
         LMH_UNROLL
         for (int r = 0; r < 6; ++r) {
             double s = w.rhs[r];
             LMH_UNROLL
             for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
             l[r] = s;
+        }
         }
         LMH_UNROLL
         for (int r = 0; r < 6; ++r) {
