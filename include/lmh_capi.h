@@ -157,6 +157,17 @@ int32_t lmh_timer_stop(LmhBatch* h, double* elapsed_ms);
  * the last solve.  elapsed_ms: device time of the launch (includes one evaluation of the model phases). */
 int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out, double* elapsed_ms);
 
+/* Kinematics::desiredOperationalState + Kinematics::compute (src/invKinematics.cpp:11-52: Newton inverse kinematics
+ * on [sole poses, arm/head joints, base attitude, CoM]) for n targets at once on the device, one warp per target.
+ * com3 [n][3], rf6 / lf6 [n][6] = sole position + Euler angles, as main.cpp:24-35 passes them; the arm/head joints keep
+ * the batch's nominal posture and the attitude target is zero, as upstream.  q_out [n][30]; iters / residual (max
+ * |operational error|) / status (0 converged to 1e-10, 1 iteration cap of 200, 2 singular Jacobian) [n]; any output may
+ * be NULL.  apply_to_state != 0 (needs n == n_env): every environment restarts from its own posture with zero
+ * velocity at t = 0 without a host round trip of the state (statistics and step counter are cleared).  The MPC
+ * keeps the batch's CoM height (Mpc3dLip::getZCom of the nominal scenario). */
+int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* rf6, const double* lf6, double* q_out,
+                     int32_t* iters, double* residual, int32_t* status, int32_t apply_to_state);
+
 /* Launch geometry actually used. */
 int32_t lmh_launch_info(const LmhBatch* h, int32_t* threads_per_env, int32_t* envs_per_block, int32_t* smem_bytes,
                         int32_t* blocks, int32_t* kernel_launches_total);

@@ -43,13 +43,13 @@ SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", 
            "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
            "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
            "lmh_stats_dev", "lmh_set_state_dev", "lmh_reset_stats", "lmh_timer_start", "lmh_timer_stop",
-           "lmh_qp_bench", "lmh_launch_info", "lmh_measure_fp64_peak"]
+           "lmh_qp_bench", "lmh_ik_batch", "lmh_launch_info", "lmh_measure_fp64_peak"]
 
 
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... in-tree (cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "lmh_capi.cu")
-    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("lmh_model.cuh", "lmh_warp.cuh", "lmh_setup.hpp", "lmh_nao_table.inc")]
+    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("lmh_model.cuh", "lmh_warp.cuh", "lmh_ik.cuh", "lmh_setup.hpp", "lmh_nao_table.inc")]
     deps.append(os.path.join(_ROOT, "include", "lmh_capi.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -104,6 +104,7 @@ def load_library():
     L.lmh_timer_start.argtypes = [vp]
     L.lmh_timer_stop.argtypes = [vp, vp]
     L.lmh_qp_bench.argtypes = [vp, _i32, _i32, vp, vp]
+    L.lmh_ik_batch.argtypes = [vp, _i32, vp, vp, vp, vp, vp, vp, vp, _i32]
     L.lmh_launch_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.lmh_measure_fp64_peak.argtypes = [_i32, vp, vp, vp]
     _lib = L
@@ -267,6 +268,18 @@ class Batch:
         out, ms = np.zeros((self.n_env, 42)), np.zeros(1)
         _chk(self.L, self.L.lmh_qp_bench(self.h, int(mode), int(repeats), _p(out), _p(ms)))
         return float(ms[0]), out[:, :30], out[:, 30:]
+
+    def ik(self, com, rf, lf, apply=False):
+        """Kinematics::compute for n targets on the device (invKinematics.cpp:11-52): com [n][3], rf / lf [n][6] (sole
+        position + Euler angles).  Returns {"q": [n][30], "iters", "residual", "status"}; apply=True (n == n_env)
+        restarts every environment from its own posture."""
+        com = np.ascontiguousarray(com, np.float64).reshape(-1, 3)
+        n = com.shape[0]
+        rf = np.ascontiguousarray(np.broadcast_to(np.asarray(rf, np.float64).reshape(-1, 6), (n, 6)))
+        lf = np.ascontiguousarray(np.broadcast_to(np.asarray(lf, np.float64).reshape(-1, 6), (n, 6)))
+        q, it, res, st = np.zeros((n, 30)), np.zeros(n, np.int32), np.zeros(n), np.zeros(n, np.int32)
+        _chk(self.L, self.L.lmh_ik_batch(self.h, n, _p(com), _p(rf), _p(lf), _p(q), _p(it), _p(res), _p(st), 1 if apply else 0))
+        return {"q": q, "iters": it, "residual": res, "status": st}
 
     def launch_info(self):
         v = [np.zeros(1, np.int32) for _ in range(5)]

@@ -6,6 +6,7 @@
 // HBM is touched once per launch for the 60+30+1 state doubles (and once per step for the optional
 // log record).  Environments never communicate.
 #include "lmh_setup.hpp"
+#include "lmh_ik.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -182,6 +183,53 @@ __global__ void __launch_bounds__(NT) qp_bench_kernel(Params p, int repeats, int
         qp_stage(cx, w, K, nullptr);
     }
     for (int i = threadIdx.x; i < 42; i += NT) out[(size_t)env * 42 + i] = i < 30 ? w.a[i] : w.f12[i - 30];
+}
+
+// Batched inverse kinematics of the initial posture (lmh_ik.cuh): one warp per target, four targets per block.
+struct IkParams {
+    const Consts* K;
+    const double* q_start;     // [30] posture the Newton iteration starts from (and source of the arm/head targets)
+    const double* com;         // [n][3]
+    const double* rf;          // [n][6]
+    const double* lf;          // [n][6]
+    double* q_out;             // [n][30]
+    int32_t* iters;            // [n]
+    double* residual;          // [n]
+    int32_t* status;           // [n]
+    double* x;                 // state to initialise ([n][60], with vh and t) or null
+    double* vh;
+    double* t;
+    int32_t n, max_iter, env_bytes;
+};
+
+__global__ void __launch_bounds__(128) ik_kernel(IkParams p) {
+    extern __shared__ double smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * 4 + wid;
+    if (env >= p.n) return;
+    EnvWS& w = *reinterpret_cast<EnvWS*>(reinterpret_cast<char*>(smem) + (size_t)wid * p.env_bytes);
+    double* des = w.qppRef;
+    if (lane < NQ) {
+        w.q[lane] = p.q_start[lane];
+        // Kinematics::desiredOperationalState (invKinematics.cpp:11-25): feet poses, the current arm/head joints,
+        // zero attitude, CoM
+        des[lane] = lane < 6 ? p.rf[(size_t)env * 6 + lane] : lane < 12 ? p.lf[(size_t)env * 6 + lane - 6]
+                  : lane < 24 ? p.q_start[18 + lane - 12] : lane < 27 ? 0.0 : p.com[(size_t)env * 3 + lane - 27];
+    }
+    __syncwarp();
+    const IkResult r = ik_solve_warp(w, *p.K, des, p.max_iter, lane);
+    if (lane < NQ) {
+        p.q_out[(size_t)env * NQ + lane] = w.q[lane];
+        if (p.x) {
+            p.x[(size_t)env * 60 + lane] = w.q[lane];
+            p.x[(size_t)env * 60 + NQ + lane] = 0.0;
+            p.vh[(size_t)env * NQ + lane] = 0.0;
+        }
+    }
+    if (lane == 0) {
+        p.iters[env] = r.iters; p.residual[env] = r.residual; p.status[env] = r.status;
+        if (p.x) p.t[env] = 0.0;
+    }
 }
 
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -649,6 +697,50 @@ int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out
     if (a_f_out) CU(cudaMemcpy(a_f_out, d_out, (size_t)h->n_env * 42 * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(d_out);
     h->launches += 1;
+    return LMH_OK;
+}
+
+int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* rf6, const double* lf6, double* q_out,
+                     int32_t* iters, double* residual, int32_t* status, int32_t apply_to_state) {
+    if (!h || n <= 0 || !com3 || !rf6 || !lf6) return fail(LMH_EINVAL, "lmh_ik_batch: bad arguments");
+    if (apply_to_state && n != h->n_env) return fail(LMH_EINVAL, "lmh_ik_batch: apply_to_state needs one target per environment");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n;
+    double *d_in = nullptr, *d_q = nullptr, *d_res = nullptr, *d_q0 = nullptr;
+    int32_t* d_int = nullptr;
+    CU(cudaMalloc(&d_in, N * 15 * sizeof(double)));
+    CU(cudaMalloc(&d_q, N * NQ * sizeof(double)));
+    CU(cudaMalloc(&d_res, N * sizeof(double)));
+    CU(cudaMalloc(&d_int, N * 2 * sizeof(int32_t)));
+    CU(cudaMalloc(&d_q0, NQ * sizeof(double)));
+    CU(cudaMemcpyAsync(d_in, com3, N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_in + N * 3, rf6, N * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_in + N * 9, lf6, N * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_q0, h->hm->q0, NQ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    IkParams p;
+    p.K = h->dK; p.q_start = d_q0; p.com = d_in; p.rf = d_in + N * 3; p.lf = d_in + N * 9;
+    p.q_out = d_q; p.iters = d_int; p.status = d_int + N; p.residual = d_res;
+    p.x = apply_to_state ? h->d_x : nullptr; p.vh = h->d_vh; p.t = h->d_t;
+    p.n = n; p.max_iter = 200;
+    p.env_bytes = (int32_t)((sizeof(EnvWS) + 15) / 16 * 16);
+    CU(cudaFuncSetAttribute(ik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.env_bytes * 4));
+    ik_kernel<<<(n + 3) / 4, 128, (size_t)p.env_bytes * 4, h->stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    if (q_out) CU(cudaMemcpyAsync(q_out, d_q, N * NQ * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, d_int, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(cudaMemcpyAsync(status, d_int + N, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (residual) CU(cudaMemcpyAsync(residual, d_res, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_in); cudaFree(d_q); cudaFree(d_res); cudaFree(d_int); cudaFree(d_q0);
+    if (apply_to_state) {
+        std::vector<LmhStats> st(N);
+        std::memset(st.data(), 0, N * sizeof(LmhStats));
+        for (size_t e = 0; e < N; ++e) st[e].alive = 1;
+        CU(cudaMemcpyAsync(h->d_stats, st.data(), N * sizeof(LmhStats), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->step_counter = 0;
+    }
     return LMH_OK;
 }
 

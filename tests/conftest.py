@@ -36,6 +36,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def ik_golden():
+    """postures of the reference's own Kinematics::compute for seeded targets (tests/golden/make_ik_golden.py)"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "ik_vectors.npz"))
+
+
+@pytest.fixture(scope="session")
 def qp_exact():
     return np.load(os.path.join(ROOT, "tests", "golden", "qp_exact.npz"))
 

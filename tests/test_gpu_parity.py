@@ -292,3 +292,42 @@ def test_qp_microbenchmark_entry(oracle):
     assert msm > 0
     with pytest.raises(lmh.LmhError):
         b.qp_bench(2, 1)
+
+
+def test_batched_inverse_kinematics(oracle, ik_golden):
+    """section 8(f) rank 2: Kinematics::compute for a batch of targets on the device, against the reference build's
+    postures, against the oracle on further seeded targets, and through the definition of the operational state"""
+    g = ik_golden
+    n = len(g["q"])
+    b = lmh.Batch(n)
+    r = b.ik(g["com"], g["rf"], g["lf"])
+    assert (r["status"] == 0).all() and (r["residual"] <= 1e-10).all()
+    assert np.abs(r["q"] - g["q"]).max() < 2e-8                      # both stop at |operational error| <= 1e-10; the
+                                                                     # joint-space gap is that times the conditioning
+    assert (r["iters"] <= g["iters"] + 1).all() and r["iters"][0] == 0   # starts from the nominal posture, not from scratch
+    # further targets, live against the oracle; the nominal target must return the nominal posture at once
+    from golden.make_ik_golden import targets
+    com, rf, lf = targets(40, seed=7)
+    ok = [i for i in range(40) if oracle.sim(com=com[i], rf=rf[i], lf=lf[i]).ik_iterations < 50]
+    r2 = b.ik(com[ok], rf[ok], lf[ok])
+    qo = np.stack([oracle.sim(com=com[i], rf=rf[i], lf=lf[i]).get_state()[0][:30] for i in ok])
+    assert (r2["status"] == 0).all() and np.abs(r2["q"] - qo).max() < 2e-8
+    q0 = b.nominal()[0]
+    r3 = b.ik([[-0.02, 0.0, 0.26]], [0, -0.05, 0, 0, 0, 0], [0, 0.05, 0, 0, 0, 0])
+    assert r3["iters"][0] == 0 and np.array_equal(r3["q"][0], q0)
+    # an unreachable target ends at the iteration cap or a singular Jacobian instead of hanging (upstream's loop has no cap)
+    r4 = b.ik([[-0.02, 0.0, 0.60]], [0, -0.05, 0, 0, 0, 0], [0, 0.05, 0, 0, 0, 0])
+    assert r4["status"][0] in (1, 2)
+    # apply: every environment restarts from its own posture; the stage evaluated there sees the targets
+    r5 = b.ik(g["com"], g["rf"], g["lf"], apply=True)
+    x, vh, t = b.get_state()
+    assert np.array_equal(x[:, :30], r5["q"]) and (x[:, 30:] == 0).all() and (vh == 0).all() and (t == 0).all()
+    d = b.stage()
+    assert np.abs(d["CoM"] - g["com"]).max() < 2e-10
+    assert np.abs(d["T7"][:, 9:] - g["rf"][:, :3]).max() < 2e-10 and np.abs(d["T14"][:, 9:] - g["lf"][:, :3]).max() < 2e-10
+    # closed loop from those postures against the oracle started at the same states
+    b.ik(g["com"], g["rf"], g["lf"], apply=True)
+    b.step(20)
+    xg = b.get_state()[0]
+    xc, _, _, fails = oracle.batch_rollout(oracle.default_config(), n, 20, x0=np.hstack([r5["q"], np.zeros((n, 30))]), n_threads=8)
+    assert fails == 0 and np.abs(xg - xc).max() < 1e-7

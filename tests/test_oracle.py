@@ -182,3 +182,11 @@ def test_qp_solver_against_exact_solutions(oracle, qp_exact):
         xe = qp_exact["x"][i]
         worst = max(worst, relerr(x[:30], xe[:30]), relerr(x[30:42], xe[30:42]))
     assert worst < 1e-7, worst                                    # (a, f) are what parity is judged on; c is eps-regularised
+
+
+def test_inverse_kinematics_matches_reference_vectors(oracle, ik_golden):
+    """Kinematics::compute on seeded targets: restatement vs the reference build's postures (bit for bit when made)"""
+    g = ik_golden
+    for i in range(len(g["q"])):
+        s = oracle.sim(com=g["com"][i], rf=g["rf"][i], lf=g["lf"][i])
+        assert np.abs(s.get_state()[0][:30] - g["q"][i]).max() < 1e-12 and s.ik_iterations == g["iters"][i]
