@@ -168,6 +168,12 @@ int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out
 int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* rf6, const double* lf6, double* q_out,
                      int32_t* iters, double* residual, int32_t* status, int32_t apply_to_state);
 
+/* Data-format glue for viewing rollouts in MuJoCo (host only, no device work): relabelMujocoMatrix
+ * (apps/mujoco/main.cpp:182-200: q_mj = L q[6:30], blocks head / left leg / right leg / left arm / right arm,
+ * L(14,17) = -1; upstream leaves the rest of L uninitialised, here it is zero) and the initial free-joint pose of
+ * MujocoSim.cpp:77-85 (z + 0.035, identity quaternion).  q30 [n][30] -> qpos31 [n][31] = [x y z, quat wxyz, 24 joints]. */
+int32_t lmh_export_mujoco(int32_t n, const double* q30, double* qpos31);
+
 /* Launch geometry actually used. */
 int32_t lmh_launch_info(const LmhBatch* h, int32_t* threads_per_env, int32_t* envs_per_block, int32_t* smem_bytes,
                         int32_t* blocks, int32_t* kernel_launches_total);

@@ -43,7 +43,7 @@ SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", 
            "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
            "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
            "lmh_stats_dev", "lmh_set_state_dev", "lmh_reset_stats", "lmh_timer_start", "lmh_timer_stop",
-           "lmh_qp_bench", "lmh_ik_batch", "lmh_launch_info", "lmh_measure_fp64_peak"]
+           "lmh_qp_bench", "lmh_ik_batch", "lmh_export_mujoco", "lmh_launch_info", "lmh_measure_fp64_peak"]
 
 
 def build_library(force=False, verbose=False):
@@ -105,6 +105,7 @@ def load_library():
     L.lmh_timer_stop.argtypes = [vp, vp]
     L.lmh_qp_bench.argtypes = [vp, _i32, _i32, vp, vp]
     L.lmh_ik_batch.argtypes = [vp, _i32, vp, vp, vp, vp, vp, vp, vp, _i32]
+    L.lmh_export_mujoco.argtypes = [_i32, vp, vp]
     L.lmh_launch_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.lmh_measure_fp64_peak.argtypes = [_i32, vp, vp, vp]
     _lib = L
@@ -125,6 +126,16 @@ def measure_fp64_peak(device=0):
     tf, mhz, sms = np.zeros(1), np.zeros(1), np.zeros(1, np.int32)
     _chk(L, L.lmh_measure_fp64_peak(device, _p(tf), _p(mhz), _p(sms)))
     return float(tf[0]), float(mhz[0]), int(sms[0])
+
+
+def export_mujoco(q):
+    """relabelMujocoMatrix + initial free-joint pose (apps/mujoco/main.cpp:182-200, MujocoSim.cpp:77-85):
+    q [n][30] -> qpos [n][31] = [x, y, z + 0.035, quat wxyz = identity, 24 joints in MuJoCo's order]"""
+    L = load_library()
+    q = np.ascontiguousarray(q, np.float64).reshape(-1, 30)
+    out = np.zeros((q.shape[0], 31))
+    _chk(L, L.lmh_export_mujoco(q.shape[0], _p(q), _p(out)))
+    return out
 
 
 class Batch:

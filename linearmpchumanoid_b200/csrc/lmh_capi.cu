@@ -744,6 +744,22 @@ int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* r
     return LMH_OK;
 }
 
+int32_t lmh_export_mujoco(int32_t n, const double* q30, double* qpos31) {
+    if (n < 0 || !q30 || !qpos31) return fail(LMH_EINVAL, "lmh_export_mujoco: bad arguments");
+    // row block -> first source joint, length (apps/mujoco/main.cpp:182-200): head, left leg, right leg, left arm, right arm
+    static const int row0[5] = {0, 2, 8, 14, 19}, src0[5] = {22, 6, 0, 17, 12}, len[5] = {2, 6, 6, 5, 5};
+    for (int e = 0; e < n; ++e) {
+        const double* q = q30 + (size_t)e * 30;
+        double* o = qpos31 + (size_t)e * 31;
+        o[0] = q[0]; o[1] = q[1]; o[2] = q[2] + 0.035;            // MujocoSim.cpp:77-79: offset between the base frames
+        o[3] = 1.0; o[4] = o[5] = o[6] = 0.0;                      // MujocoSim.cpp:82-85: identity quaternion, as upstream
+        for (int b = 0; b < 5; ++b)
+            for (int k = 0; k < len[b]; ++k) o[7 + row0[b] + k] = q[6 + src0[b] + k];
+        o[7 + 14] = -q[6 + 17];                                    // L(14,17) = -1: LShoulderPitch turns the other way
+    }
+    return LMH_OK;
+}
+
 int32_t lmh_launch_info(const LmhBatch* h, int32_t* nt, int32_t* epb, int32_t* smem, int32_t* blocks, int32_t* launches) {
     if (!h) return fail(LMH_EINVAL, "null handle");
     if (nt) *nt = h->nt;

@@ -72,3 +72,16 @@ def test_product_does_not_touch_the_oracle():
                 assert "orc_" not in txt and "oracle/" not in txt.replace("# oracle", ""), f
     out = os.popen("ldd " + lmh.LIB_PATH).read()
     assert "oracle" not in out and "hostemu" not in out
+
+
+def test_mujoco_export_glue():
+    """relabelMujocoMatrix (apps/mujoco/main.cpp:182-200) and the free-joint pose of MujocoSim.cpp:77-85, written out
+    by hand: head, left leg, right leg, left arm (shoulder pitch negated), right arm; host-only data-format glue"""
+    q = np.arange(60, dtype=float).reshape(2, 30) / 7.0
+    o = lmh.export_mujoco(q)
+    L = np.zeros((24, 24))
+    L[0:2, 22:24] = np.eye(2); L[2:8, 6:12] = np.eye(6); L[8:14, 0:6] = np.eye(6)
+    L[14:19, 17:22] = np.eye(5); L[14, 17] = -1; L[19:24, 12:17] = np.eye(5)
+    for e in range(2):
+        assert np.array_equal(o[e, 7:], L @ q[e, 6:])
+        assert np.array_equal(o[e, :7], [q[e, 0], q[e, 1], q[e, 2] + 0.035, 1, 0, 0, 0])
