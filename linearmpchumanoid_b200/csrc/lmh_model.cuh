@@ -989,10 +989,12 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         LMH_UNROLL
         for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
         chol6(A);
+        // every thread holds the same factor: all of them store it (same value to the same word), which costs 27 plain
+        // stores instead of 27 compare-and-branch pairs; static indices keep A in registers
         LMH_UNROLL
-        for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6 && e % Cx::NT == cx.tid) w.Ls[e] = A[e];      // lower triangle; static indices keep A in registers
+        for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6) w.Ls[e] = A[e];
         LMH_UNROLL
-        for (int e = 0; e < 6; ++e) if (e % Cx::NT == cx.tid) w.Lsi[e] = 1.0 / A[7 * e];
+        for (int e = 0; e < 6; ++e) w.Lsi[e] = 1.0 / A[7 * e];
     }
     const double* Ls = w.Ls;
     const double* Lsi = w.Lsi;

@@ -40,6 +40,18 @@ __device__ __forceinline__ void load12(const double* p, double* o) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) o[k] = p[k];
 }
+// p ? a : b as a select instruction: lane-dependent choices between values that every lane has anyway must not
+// become divergent branches (a lone warp pays ~15 cycles per resolved branch; the FP64 and ALU pipes are mostly idle)
+__device__ __forceinline__ double dsel(bool p, double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tselp.f64 %0, %1, %2, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+    return r;
+}
+__device__ __forceinline__ double dsel3(int k, double x0, double x1, double x2) { return dsel(k == 0, x0, dsel(k == 1, x1, x2)); }
+// component k (lane-dependent) of a x b: all three components, then a select
+__device__ __forceinline__ double cross3_sel(const double* a, const double* b, int k) {
+    return dsel3(k, a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
+}
 // 16-byte aligned sources: LDS.128, half the shared-memory wavefronts of the scalar loads
 __device__ __forceinline__ void ld6v(const double* p, double* o) {
     const double2* q = reinterpret_cast<const double2*>(p);
@@ -53,12 +65,9 @@ __device__ __forceinline__ void ld12v(const double* p, double* o) {
 }
 // row r of X m for the lane that holds row k3 = r % 3 of E (e0..e2) and p: E m_ang (r < 3) or E (m_lin + m_ang x p)
 __device__ __forceinline__ double xm_lane(double e0, double e1, double e2, double p0, double p1, double p2, const double* m, bool lin) {
-    double a0 = m[0], a1 = m[1], a2 = m[2];
-    if (lin) {
-        a0 = m[3] + (m[1] * p2 - m[2] * p1);
-        a1 = m[4] + (m[2] * p0 - m[0] * p2);
-        a2 = m[5] + (m[0] * p1 - m[1] * p0);
-    }
+    const double a0 = dsel(lin, m[3] + (m[1] * p2 - m[2] * p1), m[0]);
+    const double a1 = dsel(lin, m[4] + (m[2] * p0 - m[0] * p2), m[1]);
+    const double a2 = dsel(lin, m[5] + (m[0] * p1 - m[1] * p0), m[2]);
     return e0 * a0 + e1 * a1 + e2 * a2;
 }
 // row r of X m, X = [[E,0],[-E p^,E]], E = R'
@@ -167,6 +176,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
     const int c8 = 8 * L.c, r = L.r;
     const bool lin = r >= 3;
     const int k3 = lin ? r - 3 : r;
+    const double csgn = (k3 == 0) ? 1.0 : (k3 == 1) ? -1.0 : 0.0;
     // base: f0 = v0 x* (I0 v0), acc0 = 0
     if (lane < 6) {
         double v0[6];
@@ -205,8 +215,9 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
             ld6v(S.abuf[cur] + c8, pa);
             xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);
         }
-        const double col = r == 0 ? nv[1] : r == 1 ? -nv[0] : r == 3 ? nv[4] : r == 4 ? -nv[3] : 0.0;
-        xa += col * qd;
+        // (v x S) qd with S = e_z: component r is sgn * v[partner], lane constants (rows 2 and 5: sgn = 0)
+        const double colv = dsel(lin, dsel(r == 3, nv[4], nv[3]), dsel(r == 0, nv[1], nv[0]));
+        xa += (csgn * colv) * qd;
         const double hb = Irow[0] * nv[0] + Irow[1] * nv[1] + Irow[2] * nv[2] + Irow[3] * nv[3] + Irow[4] * nv[4] + Irow[5] * nv[5];
         if (act) {
             S.hbuf[c8 + r] = hb;
@@ -219,7 +230,9 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
             ld6v(S.abuf[cur ^ 1] + c8, na);
             ld6v(S.hbuf + c8, h);
             double f = Irow[0] * na[0] + Irow[1] * na[1] + Irow[2] * na[2] + Irow[3] * na[3] + Irow[4] * na[4] + Irow[5] * na[5];
-            f += lin ? cross3(nv, h + 3, k3) : cross3(nv, h, k3) + cross3(nv + 3, h + 3, k3);
+            // v x* h = [w x n + u x f; w x f]: (w x s)[k3] with s = f (linear rows) or n, plus (u x f)[k3] on the angular rows
+            const double sv[3] = {dsel(lin, h[3], h[0]), dsel(lin, h[4], h[1]), dsel(lin, h[5], h[2])};
+            f += cross3_sel(nv, sv, k3) + dsel(lin, 0.0, cross3_sel(nv + 3, h + 3, k3));
             if (joint) S.frc[8 * i + r] = f;
         }
         cur ^= 1;
@@ -239,8 +252,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         const double g0 = X[3 * k3], g1 = X[3 * k3 + 1], g2 = X[3 * k3 + 2];     // row k3 of R
         const double rf = g0 * f[3] + g1 * f[4] + g2 * f[5];
         const double rf1 = __shfl_sync(0xffffffffu, rf, src1), rf2 = __shfl_sync(0xffffffffu, rf, src2);
-        double o = rf;
-        if (!lin) o = g0 * f[0] + g1 * f[1] + g2 * f[2] + (X[9 + k1] * rf2 - X[9 + k2] * rf1);
+        const double o = dsel(lin, rf, g0 * f[0] + g1 * f[1] + g2 * f[2] + (X[9 + k1] * rf2 - X[9 + k2] * rf1));
         if (on) {
             if (d > 1) S.frc[8 * (i - 1) + r] += o; else S.contrib[c8 + r] = o;
         }
@@ -302,7 +314,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
                 const double b1 = -(-ek0 * Rp[11] + ek2 * Rp[9]);
                 const double b2 = -(ek0 * Rp[10] - ek1 * Rp[9]);
                 y[0] += ic[3 + k] * b0; y[1] += ic[3 + k] * b1; y[2] += ic[3 + k] * b2;
-                bs[k] = r == 0 ? b0 : r == 1 ? b1 : b2;
+                bs[k] = dsel3(r, b0, b1, b2);
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) S.Ybuf[36 * L.c + 6 * r + k] = y[k];
