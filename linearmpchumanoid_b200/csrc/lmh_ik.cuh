@@ -125,7 +125,7 @@ __device__ IkResult ik_solve_warp(EnvWS& w, const Consts& K, const double* des, 
             }
             if (lane < 27) {
                 const int col = lane < NJ ? 6 + lane : 3 + (lane - 24);
-                Jc[col] = j0 / K.mass; Jc[NQ + col] = j1 / K.mass; Jc[2 * NQ + col] = j2 / K.mass;
+                Jc[col] = j0 * K.inv_mass; Jc[NQ + col] = j1 * K.inv_mass; Jc[2 * NQ + col] = j2 * K.inv_mass;
             }
         }
         __syncwarp();

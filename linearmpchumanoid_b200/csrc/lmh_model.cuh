@@ -52,10 +52,11 @@ constexpr int LD1 = 19;
 constexpr int NYR = 10;     // right-hand-side rows carried through the factorisation
 
 // chain c: frames chain_first[c] .. chain_first[c]+chain_len[c]-1, depth 1..chain_len[c]
-LMH_HD int chain_first(int c) { return c == 0 ? 1 : c == 1 ? 8 : c == 2 ? 15 : c == 3 ? 20 : 25; }
-LMH_HD int chain_len(int c) { return c < 2 ? 7 : c < 4 ? 5 : 2; }     // frames (legs include the sole)
-LMH_HD int chain_nact(int c) { return c < 2 ? 6 : c < 4 ? 5 : 2; }    // actuated frames
-LMH_HD int chain_joint0(int c) { return c == 0 ? 0 : c == 1 ? 6 : c == 2 ? 12 : c == 3 ? 17 : 22; }
+// (five one-byte entries packed into a constant: a shift instead of a chain of compares and branches)
+LMH_HD int chain_first(int c) { return (int)((0x19140F0801ull >> (8 * c)) & 0xFF); }    // 1, 8, 15, 20, 25
+LMH_HD int chain_len(int c) { return (int)((0x0205050707ull >> (8 * c)) & 0xFF); }      // frames (legs include the sole)
+LMH_HD int chain_nact(int c) { return (int)((0x0205050606ull >> (8 * c)) & 0xFF); }     // actuated frames
+LMH_HD int chain_joint0(int c) { return (int)((0x16110C0600ull >> (8 * c)) & 0xFF); }   // 0, 6, 12, 17, 22
 // actuated joint index (0..23) of a frame, or -1 (src/Robot.cpp:169-174)
 LMH_HD int frame_joint(int i) {
     if (i == 0 || i == 7 || i == 14) return -1;
@@ -74,6 +75,7 @@ struct Consts {
     double pre[NCH * 12];     // fixed transform between the torso and each chain's first joint (R row-major, p)
     double sole_x;            // sole offset along x of the ankle-roll frame (Robot.cpp:106-117)
     double mass, gravity;
+    double inv_mass;          // 1 / mass: divisions by constants are multiplications on the device
     double qdes[NQ];          // Robot::desiredPosture (Robot.cpp:253-262)
     double Rdes[9];           // desired sole orientation (Robot.cpp:28-31)
     double Gf[6 * 16];        // per-foot wrench generators: rows 0-2 moment, 3-5 force (controller.cpp:156-294)
@@ -124,7 +126,7 @@ struct EnvWS {
     double qppRef[NQ], hGpRef[6], footAccRef[12];
     double ga[NQ], a[NQ], f12[12], tau[NJ], xdot[2 * NQ];
     double Sa[36], Ls[36], Lsi[6], rhs[6], sv[6], lam[6];     // Lsi: 1 / diag(Ls)
-    double c[NC], cs[NC], mu[NC], piv[NC], ladiag[ND1];
+    double c[NC], cs[NC], mu[NC], piv[NC], ladiag[ND1], ladinv[ND1];     // ladinv: 1 / ladiag (one-warp factorisation)
     double red[32];                // reduction scratch
     int32_t free_mask[NC];
     int32_t pdone[12], ppiv[2];
@@ -230,14 +232,23 @@ LMH_HD double mul_then_add(double a, double b, double c) {
 
 LMH_HD double lmh_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    // hardware seed (2^-22) and two Newton steps; the arguments are pivots of positive definite matrices, so the
+    // library's special-case path (a branch and a call) has nothing to do here
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = x * y;
+    double e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = x * y;
+    e = fma(-t, y, 1.0);
+    return fma(0.5 * y, e, y);
 #else
     return 1.0 / sqrt(x);
 #endif
 }
 
 // in-place Cholesky of a 6x6 SPD matrix held in registers (lower triangle), fully unrolled
-LMH_HD void chol6(double* A) {
+LMH_HD void chol6(double* A, double* dinv = nullptr) {      // dinv (or null): 1 / diag(L), a by-product of the rsqrt
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -249,6 +260,7 @@ LMH_HD void chol6(double* A) {
         for (int m = 0; m < 6; ++m) if (m < k) s -= A[6 * k + m] * A[6 * k + m];
         const double inv = lmh_rsqrt(s);
         A[7 * k] = s * inv;
+        if (dinv) dinv[k] = inv;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -432,7 +444,7 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     LMH_FOR(k, 3) {
         double s = 0.0;
         for (int part = 0; part < 8; ++part) s += w.red[3 * part + k];
-        w.com[k] = s / K.mass;
+        w.com[k] = s * K.inv_mass;
     }
     cx.sync();
 }
@@ -668,7 +680,7 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
     }
     // AG = X1G M6, AGpqp = X1G Cg[0:6], X1G = [[R0, -R0 p1G^],[0, R0]]
     LMH_FOR(j, NQ + 1) {
-        double p1G[3] = {w.M6[NQ * 2 + 4] / K.mass, w.M6[NQ * 0 + 5] / K.mass, w.M6[NQ * 1 + 3] / K.mass};
+        double p1G[3] = {w.M6[NQ * 2 + 4] * K.inv_mass, w.M6[NQ * 0 + 5] * K.inv_mass, w.M6[NQ * 1 + 3] * K.inv_mass};
         double top[3], bot[3];
         if (j < NQ) for (int k = 0; k < 3; ++k) { top[k] = w.M6[NQ * k + j]; bot[k] = w.M6[NQ * (3 + k) + j]; }
         else for (int k = 0; k < 3; ++k) { top[k] = w.Cg[k]; bot[k] = w.Cg[3 + k]; }
@@ -734,7 +746,7 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
     LMH_FOR(k, 6) {
         double s = 0.0;
         for (int j = 0; j < NQ; ++j) s += w.AG[NQ * k + j] * vb_at(w, j);
-        if (k < 3) w.angMom[k] = s; else w.comVel[k - 3] = s / K.mass;
+        if (k < 3) w.angMom[k] = s; else w.comVel[k - 3] = s * K.inv_mass;
     }
     cx.sync();
 }
@@ -969,9 +981,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
         double a11 = c00 * c22 - c02 * c02, a12 = c01 * c02 - c00 * c12, a22 = c00 * c11 - c01 * c01;
         double det = c00 * a00 + c01 * a01 + c02 * a02;
-        Ci[0] = a00 / det; Ci[1] = a01 / det; Ci[2] = a02 / det;
-        Ci[3] = Ci[1];     Ci[4] = a11 / det; Ci[5] = a12 / det;
-        Ci[6] = Ci[2];     Ci[7] = Ci[5];     Ci[8] = a22 / det;
+        const double rdet = 1.0 / det;
+        Ci[0] = a00 * rdet; Ci[1] = a01 * rdet; Ci[2] = a02 * rdet;
+        Ci[3] = Ci[1];      Ci[4] = a11 * rdet; Ci[5] = a12 * rdet;
+        Ci[6] = Ci[2];      Ci[7] = Ci[5];      Ci[8] = a22 * rdet;
     }
     LMH_FOR(it, 42) {
         int r = it / 6, c = it % 6;          // r == 6: the ga row
@@ -988,13 +1001,14 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         double A[36];
         LMH_UNROLL
         for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
-        chol6(A);
+        double Ainv[6];
+        chol6(A, Ainv);
         // every thread holds the same factor: all of them store it (same value to the same word), which costs 27 plain
         // stores instead of 27 compare-and-branch pairs; static indices keep A in registers
         LMH_UNROLL
         for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6) w.Ls[e] = A[e];
         LMH_UNROLL
-        for (int e = 0; e < 6; ++e) w.Lsi[e] = 1.0 / A[7 * e];
+        for (int e = 0; e < 6; ++e) w.Lsi[e] = Ainv[e];
     }
     const double* Ls = w.Ls;
     const double* Lsi = w.Lsi;
@@ -1093,13 +1107,12 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         }
         LMH_FOR(col, 13) {            // W[:, col] = Ls^-1 Jb' B[:, col] ; column 12: sv = Ls^-1 rhs (first pass of a stage only)
             if (col < 12 || iters == 1) {
-                const int f = col / 6, k = col % 6;
+                const int cc = col < 12 ? col : 0, f = cc / 6, k = cc % 6;
                 double t[6];
                 for (int m = 0; m < 6; ++m) {
                     double sd = 0.0;
-                    if (col < 12) { for (int i = 0; i < 6; ++i) sd += w.JFc[72 * f + 12 * i + m] * Bm[6 * (6 * f + i) + k]; }
-                    else sd = w.rhs[m];
-                    t[m] = sd;
+                    for (int i = 0; i < 6; ++i) sd += w.JFc[72 * f + 12 * i + m] * Bm[6 * (6 * f + i) + k];
+                    t[m] = col < 12 ? sd : w.rhs[m];
                 }
                 for (int m = 0; m < 6; ++m) {
                     double sd = t[m];
@@ -1439,9 +1452,9 @@ LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
         double qd;
         if (i < 3) qd = w.v[i] + cross_k(w.v + 3, w.q, i);       // v + w x p
         else if (i < 6) {    // Euler rates (generalizedFunctions.cpp:43-50)
-            const double s2 = w.esc[2], c2 = w.esc[3], c1 = w.esc[1], t1 = w.esc[0] / w.esc[1];   // tan = sin/cos
+            const double s2 = w.esc[2], c2 = w.esc[3], ic1 = 1.0 / w.esc[1], t1 = w.esc[0] * ic1;   // tan = sin/cos
             const double* om = w.v + 3;
-            qd = i == 3 ? (c2 / c1) * om[0] + (s2 / c1) * om[1]
+            qd = i == 3 ? (c2 * ic1) * om[0] + (s2 * ic1) * om[1]
                : i == 4 ? -s2 * om[0] + c2 * om[1]
                         : c2 * t1 * om[0] + s2 * t1 * om[1] + om[2];
         } else qd = w.v[i];

@@ -155,7 +155,7 @@ private:
         EnvWS& w = *ws_;
         for (int i = 0; i < NQ; ++i) { w.q[i] = 0.0; w.v[i] = 0.0; w.vh[i] = 0.0; }
         for (int i = 0; i < 28; ++i) { K.mc[4 * i + 3] = kNaoLinks[i].m; }   // masses first: fk_phase sums the CoM
-        K.mass = 1.0;
+        K.mass = 1.0; K.inv_mass = 1.0;
         Ctx<1> cx{0, 0};
         fk_phase(cx, w, K);
         double mass = 0.0;
@@ -186,7 +186,7 @@ private:
                     S[6 * (3 + r3) + 3 + c] = r3 == c ? L.m : 0.0;
                 }
         }
-        K.mass = mass;
+        K.mass = mass; K.inv_mass = 1.0 / mass;
     }
 
     void build_controller_tables() {

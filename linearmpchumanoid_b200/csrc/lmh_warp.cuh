@@ -162,7 +162,7 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
         cm1 += __shfl_xor_sync(0xffffffffu, cm1, o);
         cm2 += __shfl_xor_sync(0xffffffffu, cm2, o);
     }
-    if (lane == 0) { w.com[0] = cm0 / K.mass; w.com[1] = cm1 / K.mass; w.com[2] = cm2 / K.mass; }
+    if (lane == 0) { w.com[0] = cm0 * K.inv_mass; w.com[1] = cm1 * K.inv_mass; w.com[2] = cm2 * K.inv_mass; }
     __syncwarp();
 }
 
@@ -314,7 +314,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
                 const double b1 = -(-ek0 * Rp[11] + ek2 * Rp[9]);
                 const double b2 = -(ek0 * Rp[10] - ek1 * Rp[9]);
                 y[0] += ic[3 + k] * b0; y[1] += ic[3 + k] * b1; y[2] += ic[3 + k] * b2;
-                bs[k] = dsel3(r, b0, b1, b2);
+                bs[k] = dsel(lin, 0.0, dsel3(r, b0, b1, b2));
             }
 #pragma unroll
             for (int k = 0; k < 6; ++k) S.Ybuf[36 * L.c + 6 * r + k] = y[k];
@@ -351,7 +351,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
                 out[cc] = x0 * a.x + x1 * b.x + x2 * c.x;
                 out[cc + 1] = x0 * a.y + x1 * b.y + x2 * c.y;
             }
-            if (!lin) {
+            {           // bs = 0 on the linear lanes: same instructions for the whole warp, no divergent region
 #pragma unroll
                 for (int cc = 0; cc < 6; cc += 2) {
                     const double2 a = *reinterpret_cast<const double2*>(Yc + 18 + cc), b = *reinterpret_cast<const double2*>(Yc + 24 + cc),
@@ -438,7 +438,7 @@ __device__ void wrench_solve_warp(EnvWS& w, int lane) {
 #pragma unroll
         for (int m = 0; m < k; ++m) s -= h[m] * Lk[m];
         const double piv = __shfl_sync(0xffffffffu, s, k);
-        const double rs = rsqrt(piv > 0.0 ? piv : 1e-300);
+        const double rs = lmh_rsqrt(piv > 0.0 ? piv : 1e-300);
         const double lik = lane == k ? piv * rs : s * rs;
         h[k] = lik;
         if (lane == k) myinv = rs;
@@ -490,7 +490,7 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
         }
         const double wj = lane < 3 ? K.wBasePos : lane < 6 ? K.wBaseAng : K.wJoints;
 #pragma unroll
-        for (int j = 0; j < ND1; ++j) if (j == lane) h[j] += wj;
+        for (int j = 0; j < ND1; ++j) h[j] += dsel(j == lane, wj, 0.0);
     } else if (yrow) {
         // row yr of [M6; ga'; U]: a pointer and a scale per lane, no per-entry branching
         const double* src = yr < 6 ? w.M6 + NQ * yr : yr == 6 ? w.ga : w.AG + NQ * (yr - 4);
@@ -512,11 +512,11 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
         }
         s += t;
         const double piv = __shfl_sync(0xffffffffu, s, k);
-        const double rs = rsqrt(piv);
+        const double rs = lmh_rsqrt(piv);
         const double lik = lane == k ? piv * rs : s * rs;
         h[k] = lik;
         if (lane > k && mrow) L1[LD1 * lane + k] = lik;
-        if (lane == k) w.ladiag[k] = lik;
+        if (lane == k) { w.ladiag[k] = lik; w.ladinv[k] = rs; }
         __syncwarp();
     }
     if (yrow) {
@@ -530,7 +530,7 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
 __device__ void qp_backsolve_warp(EnvWS& w, int lane) {
     const double* L1 = w.u.s.L1;
     double ai = lane < ND1 ? w.a[lane] : 0.0;
-    const double invd = lane < ND1 ? 1.0 / w.ladiag[lane] : 0.0;
+    const double invd = lane < ND1 ? w.ladinv[lane] : 0.0;
 #pragma unroll
     for (int k = ND1 - 1; k >= 0; --k) {
         const double xk = __shfl_sync(0xffffffffu, ai * invd, k);
