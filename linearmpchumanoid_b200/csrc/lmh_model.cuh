@@ -368,6 +368,9 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             double L[12] = {ct, -st, 0.0, ca * st, ca * ct, -sa, sa * st, sa * ct, ca, d, -r * sa, r * ca};
             double* O = Xl + 12 * i;
             int c = (i == 1) ? 0 : (i == 8) ? 1 : (i == 15) ? 2 : (i == 20) ? 3 : (i == 25) ? 4 : -1;
+#if defined(__CUDA_ARCH__)
+            if (Cx::NT == 32) c = -1;      // one warp per env: fk_chain_warp starts each chain from (torso . pre) instead
+#endif
             if (c < 0) {
                 for (int k = 0; k < 12; ++k) O[k] = L[k];
             } else {   // fold the fixed torso->chain transform into the first joint of the chain

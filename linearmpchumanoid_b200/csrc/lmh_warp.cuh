@@ -110,6 +110,15 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
         const int c = lane / 3, r3 = lane % 3;
         const int first = chain_first(c), len = chain_len(c);
         double R0 = Tw[3 * r3], R1 = Tw[3 * r3 + 1], R2 = Tw[3 * r3 + 2], pp = Tw[9 + r3];   // torso row
+        {       // times the fixed torso->chain transform (Robot.cpp:92-103,134-152): same for all fifteen lanes, so it
+                // is done here and not as a divergent special case of the five first-joint frames in fk_phase
+            const double* P = K.pre + 12 * c;
+            const double n0 = R0 * P[0] + R1 * P[3] + R2 * P[6];
+            const double n1 = R0 * P[1] + R1 * P[4] + R2 * P[7];
+            const double n2 = R0 * P[2] + R1 * P[5] + R2 * P[8];
+            pp = R0 * P[9] + R1 * P[10] + R2 * P[11] + pp;
+            R0 = n0; R1 = n1; R2 = n2;
+        }
 #pragma unroll 1
         for (int d = 0; d < len; ++d) {
             const double* L = Xl + 12 * (first + d);
