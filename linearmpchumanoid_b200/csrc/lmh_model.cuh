@@ -325,6 +325,7 @@ LMH_HD double xdense(const double* Rp, int a, int b) {
 struct EnvWS;
 struct Consts;
 __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane);
+__device__ void fk_local_warp(EnvWS& w, const Consts& K, int lane);
 #endif
 
 // state that survives from one stage evaluation to the next besides vh: the QP working set (warm start)
@@ -341,6 +342,9 @@ template <class Cx>
 LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     double* Tw = w.u.m.p.Tw;
     double* Xl = w.u.m.Xl;
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) { fk_local_warp(w, K, cx.tid); fk_chain_warp(w, K, cx.tid); return; }
+#endif
     // torso pose (generalizedFunctions.cpp:52-72) and local DH transforms (Robot.cpp:176-223)
     LMH_FOR(i, NF) {
         if (i == 0) {
@@ -368,9 +372,6 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
             double L[12] = {ct, -st, 0.0, ca * st, ca * ct, -sa, sa * st, sa * ct, ca, d, -r * sa, r * ca};
             double* O = Xl + 12 * i;
             int c = (i == 1) ? 0 : (i == 8) ? 1 : (i == 15) ? 2 : (i == 20) ? 3 : (i == 25) ? 4 : -1;
-#if defined(__CUDA_ARCH__)
-            if (Cx::NT == 32) c = -1;      // one warp per env: fk_chain_warp starts each chain from (torso . pre) instead
-#endif
             if (c < 0) {
                 for (int k = 0; k < 12; ++k) O[k] = L[k];
             } else {   // fold the fixed torso->chain transform into the first joint of the chain
@@ -384,9 +385,6 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         }
     }
     cx.sync();
-#if defined(__CUDA_ARCH__)
-    if (Cx::NT == 32) { fk_chain_warp(w, K, cx.tid); return; }
-#endif
     // chained world transforms, one tree level per pass
     for (int d = 1; d <= MAXDEPTH; ++d) {
         LMH_FOR(it, NCH * 12) {

@@ -99,6 +99,47 @@ __device__ __forceinline__ double cross3(const double* a, const double* b, int k
 }
 
 
+// ---- torso pose (generalizedFunctions.cpp:52-72) and local DH transforms (Robot.cpp:176-223): ONE sincos per lane --
+// lanes 1..26 their frame's joint angle, lanes 27..29 roll, pitch, yaw, which reach lane 0 by shuffle (three more
+// sincos calls on lane 0 alone would cost the whole warp three times the call).  The fixed torso->chain transforms
+// are applied by fk_chain_warp, so every joint frame stores its plain DH matrix.
+__device__ void fk_local_warp(EnvWS& w, const Consts& K, int lane) {
+    const bool jointf = lane >= 1 && lane < NF && lane != 7 && lane != 14;
+    const int a = jointf ? frame_joint(lane) : 0;
+    double ang = 0.0;
+    if (jointf) ang = w.q[6 + a] + K.th_off[a];
+    else if (lane >= 27 && lane < 30) ang = w.q[3 + lane - 27];
+    double st, ct;
+    sincos(ang, &st, &ct);
+    const double sr = __shfl_sync(0xffffffffu, st, 27), cr = __shfl_sync(0xffffffffu, ct, 27);
+    const double sp = __shfl_sync(0xffffffffu, st, 28), cp = __shfl_sync(0xffffffffu, ct, 28);
+    const double sy = __shfl_sync(0xffffffffu, st, 29), cy = __shfl_sync(0xffffffffu, ct, 29);
+    if (lane == 0) {
+        double R[12] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                        sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                        -sp,     cp * sr,                cp * cr,
+                        w.q[0], w.q[1], w.q[2]};
+        double* T0 = w.u.m.p.Tw;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T0[k] = R[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w.R0[k] = R[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w.p0[k] = R[9 + k];
+        w.esc[0] = sp; w.esc[1] = cp; w.esc[2] = sy; w.esc[3] = cy;
+    } else if (lane < NF) {
+        // soles: identity rotation, offset along x (Robot.cpp:106-117); joints: Khalil's modified DH (Robot.cpp:200-220)
+        const double ca = jointf ? K.dh_ca[a] : 1.0, sa = jointf ? K.dh_sa[a] : 0.0;
+        const double r = jointf ? K.dh_r[a] : 0.0, d = jointf ? K.dh_d[a] : K.sole_x;
+        double* O = w.u.m.Xl + 12 * lane;
+        O[0] = ct; O[1] = -st; O[2] = 0.0;
+        O[3] = ca * st; O[4] = ca * ct; O[5] = -sa;
+        O[6] = sa * st; O[7] = sa * ct; O[8] = ca;
+        O[9] = d; O[10] = -r * sa; O[11] = r * ca;
+    }
+    __syncwarp();
+}
+
 // ---- forward kinematics after the local transforms are in w.u.m.Xl (Robot.cpp:45-160,225-238,276-298):
 // lane 3c + r3 (< 15) carries row r3 of the world transform of chain c's current frame down the chain (a row-local
 // recurrence: no exchange between levels); then lane i (< 27) turns frame i's local transform into the
