@@ -242,6 +242,10 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         S.frc[lane] = lane < 3 ? cross3(v0, h, lane) + cross3(v0 + 3, h + 3, lane) : cross3(v0, h + 3, lane - 3);
     }
     int cur = 0;
+    // velocity and acceleration of the frame above, all six components, carried in registers from level to level
+    // (every lane of a chain reads the new ones anyway): two exchange-buffer reads per level instead of four
+    double pv[6], pa[6] = {0, 0, 0, 0, 0, 0};
+    ld6v(w.vhb6, pv);
 #pragma unroll 1
     for (int d = 1; d <= MAXDEPTH; ++d) {
         const bool act = L.on && d <= L.len;
@@ -250,8 +254,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         const double* X = Xl + 12 * i;
         const double e0 = X[k3], e1 = X[3 + k3], e2 = X[6 + k3];     // column k3 of R = row k3 of E
         const double p0 = X[9], p1 = X[10], p2 = X[11];
-        double pv[6], nv[6], Irow[6];
-        ld6v(d == 1 ? w.vhb6 : S.vbuf[cur] + c8, pv);
+        double nv[6], Irow[6];
         double x = xm_lane(e0, e1, e2, p0, p1, p2, pv, lin);
         const double qd = joint ? w.vh[6 + L.j0 + d - 1] : 0.0;
         if (r == 2) x += qd;
@@ -259,12 +262,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         load6(K.Isp + 36 * i + 6 * r, Irow);
         __syncwarp();
         ld6v(S.vbuf[cur ^ 1] + c8, nv);
-        double xa = 0.0;
-        if (d > 1) {
-            double pa[6];
-            ld6v(S.abuf[cur] + c8, pa);
-            xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);
-        }
+        double xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);       // zero at the first level: the base does not accelerate
         // (v x S) qd with S = e_z: component r is sgn * v[partner], lane constants (rows 2 and 5: sgn = 0)
         const double colv = dsel(lin, dsel(r == 3, nv[4], nv[3]), dsel(r == 0, nv[1], nv[0]));
         xa += (csgn * colv) * qd;
@@ -280,6 +278,8 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
             ld6v(S.abuf[cur ^ 1] + c8, na);
             ld6v(S.hbuf + c8, h);
             double f = Irow[0] * na[0] + Irow[1] * na[1] + Irow[2] * na[2] + Irow[3] * na[3] + Irow[4] * na[4] + Irow[5] * na[5];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { pv[k] = nv[k]; pa[k] = na[k]; }
             // v x* h = [w x n + u x f; w x f]: (w x s)[k3] with s = f (linear rows) or n, plus (u x f)[k3] on the angular rows
             const double sv[3] = {dsel(lin, h[3], h[0]), dsel(lin, h[4], h[1]), dsel(lin, h[5], h[2])};
             f += cross3_sel(nv, sv, k3) + dsel(lin, 0.0, cross3_sel(nv + 3, h + 3, k3));
