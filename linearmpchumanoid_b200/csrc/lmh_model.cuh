@@ -82,6 +82,7 @@ struct Consts {
     double GtG[16 * 16];      // Gf' Gf
     double GGt[36];           // Gf Gf' (6 x 6), the all-free wrench Gram matrix of one foot
     double Ball[36], Tall[36], BTiall[36];    // its Cholesky factor B (GGt = B B'), B'B and B (B'B)^-1
+    double Pinv[36], Dinv[36];                // GGt^-1 and (wForce I + epsC GGt^-1)^-1: the all-free shortcut of the QP
     double sq_wCoML, isq_wJoints;   // sqrt(wCoML), 1/sqrt(wJoints)
     double KpJ, KdJ, KpM, KdM, KpF, KdF;                                    // controller.hpp:100-111
     double wCoML, wCoMK, wBasePos, wBaseAng, wJoints, wForce, wFoot, epsC;   // controller.hpp:118-124, controller.cpp:109-123
@@ -997,22 +998,6 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         if (r < 6) w.Sa[it] = v; else w.rhs[c] = w.C[c] - v;
     }
     cx.sync();
-    // Ls = chol(Sa): 6x6, every thread redundantly in registers, then parked in shared memory
-    {
-        double A[36];
-        LMH_UNROLL
-        for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
-        double Ainv[6];
-        chol6(A, Ainv);
-        // every thread holds the same factor: all of them store it (same value to the same word), which costs 27 plain
-        // stores instead of 27 compare-and-branch pairs; static indices keep A in registers
-        LMH_UNROLL
-        for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6) w.Ls[e] = A[e];
-        LMH_UNROLL
-        for (int e = 0; e < 6; ++e) w.Lsi[e] = Ainv[e];
-    }
-    const double* Ls = w.Ls;
-    const double* Lsi = w.Lsi;
     // ---- primal active set on c >= 0, every working set solved in the wrench space of the feet.
     // For a free set F let P_F = G_F G_F' = B B' (B: 12 x 12, block diagonal per foot, from a diagonally pivoted
     // Cholesky that stops at the numerical rank: columns beyond the rank are zero).  With f = B zeta the
@@ -1048,8 +1033,115 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     }
     LMH_FOR(i, 1) w.warm_contact = contact;
     cx.sync();
+    // ---- all-free shortcut (no stored working set, both feet in contact: 98 % of the stages of a balancing robot).
+    // With every coefficient free, f ranges over all of R^12 and c is its minimum-norm preimage, so the problem in f is
+    //     min 1/2 f'D f  s.t.  Sa lam = rhs - Jb'f,   D = wF I + eps (G G')^-1  (constant, block diagonal per foot),
+    // whose multiplier solves the 6 x 6 system (Sa + Jb' D^-1 Jb) lam = rhs, f = D^-1 Jb lam, c = G'(G G')^-1 f.
+    // One 6 x 6 factorisation instead of chol(Sa) plus the 12 x 12 wrench-space system; if some c comes out negative
+    // the general iteration below starts from scratch.
     int iters = 0, status = 0;
-    while (true) {
+    bool fast_done = false;
+    double lfast[6] = {0, 0, 0, 0, 0, 0};
+    if (!have_point && contact == 3) {
+        double* U = Wb;                // [2][6][6] : D^-1 Jb_f
+        double* S6 = Ay;               // [6][6]    : lower triangle of Sa + Jb' D^-1 Jb
+        LMH_FOR(it, 72) {
+            const int f = it / 36, k = (it % 36) / 6, sidx = it % 6;
+            double sd = 0.0;
+            for (int l = 0; l < 6; ++l) sd += K.Dinv[6 * k + l] * w.JFc[72 * f + 12 * l + sidx];
+            U[it] = sd;
+        }
+        cx.sync();
+        LMH_FOR(it, 36) {
+            const int r = it / 6, sidx = it % 6;
+            if (sidx <= r) {
+                double sd = w.Sa[it];
+                for (int k = 0; k < 12; ++k) sd += w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * U[36 * (k / 6) + 6 * (k % 6) + sidx];
+                S6[it] = sd;
+            }
+        }
+        cx.sync();
+        {
+            double A[36], Ainv[6];
+            LMH_UNROLL
+            for (int e = 0; e < 36; ++e) A[e] = (e % 6 <= e / 6) ? S6[e] : 0.0;
+            chol6(A, Ainv);
+            LMH_UNROLL
+            for (int r = 0; r < 6; ++r) {
+                double sd = w.rhs[r];
+                LMH_UNROLL
+                for (int m = 0; m < 6; ++m) if (m < r) sd -= A[6 * r + m] * lfast[m];
+                lfast[r] = sd * Ainv[r];
+            }
+            LMH_UNROLL
+            for (int r = 5; r >= 0; --r) {
+                double sd = lfast[r];
+                LMH_UNROLL
+                for (int m = 0; m < 6; ++m) if (m > r) sd -= A[6 * m + r] * lfast[m];
+                lfast[r] = sd * Ainv[r];
+            }
+        }
+        LMH_FOR(it, 12) {              // f = D^-1 Jb lam
+            double sd = 0.0;
+            for (int q = 0; q < 6; ++q) sd += U[6 * it + q] * lfast[q];
+            w.f12[it] = sd;
+        }
+        cx.sync();
+        LMH_FOR(it, 12) {              // y = (G G')^-1 f per foot
+            const int f = it / 6, k = it % 6;
+            double sy = 0.0;
+            for (int l = 0; l < 6; ++l) sy += K.Pinv[6 * k + l] * w.f12[6 * f + l];
+            vv[12 + it] = sy;
+        }
+        cx.sync();
+        double cmin = 0.0;
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) {
+            const int i = cx.tid, foot = i / 16, gi = i % 16;
+            double sc = 0.0;
+            for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k];
+            cmin = warp_min(sc);
+            // feasible: optimal.  Otherwise project onto the orthant, as the first pass of the general iteration
+            // would: the clipped coefficients are the working set it starts from
+            w.c[i] = sc > 0.0 ? sc : 0.0;
+            w.free_mask[i] = (cmin >= 0.0 || sc > 0.0) ? 1 : 0;
+            w.cs[i] = sc; w.mu[i] = 0.0;
+        } else
+#endif
+        {
+            LMH_FOR(i, NC) {
+                const int foot = i / 16, gi = i % 16;
+                double sc = 0.0;
+                for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k];
+                w.cs[i] = sc; w.mu[i] = 0.0;
+            }
+            cx.sync();
+            for (int i = 0; i < NC; ++i) cmin = w.cs[i] < cmin ? w.cs[i] : cmin;
+            LMH_FOR(i, NC) { w.c[i] = w.cs[i] > 0.0 ? w.cs[i] : 0.0; w.free_mask[i] = (cmin >= 0.0 || w.cs[i] > 0.0) ? 1 : 0; }
+        }
+        cx.sync();
+        iters = 1;
+        have_point = true;
+        if (cmin >= 0.0) fast_done = true;
+    }
+    // Ls = chol(Sa): 6x6, every thread redundantly in registers, then parked in shared memory (general iteration only)
+    if (!fast_done) {
+        double A[36];
+        LMH_UNROLL
+        for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
+        double Ainv[6];
+        chol6(A, Ainv);
+        // every thread holds the same factor: all of them store it (same value to the same word), which costs 27 plain
+        // stores instead of 27 compare-and-branch pairs; static indices keep A in registers
+        LMH_UNROLL
+        for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6) w.Ls[e] = A[e];
+        LMH_UNROLL
+        for (int e = 0; e < 6; ++e) w.Lsi[e] = Ainv[e];
+    }
+    const double* Ls = w.Ls;
+    const double* Lsi = w.Lsi;
+    bool first_pass = true;            // of the general iteration in this stage
+    while (!fast_done) {
         ++iters;
         const bool const_basis = !have_point && contact == 3;
         if (const_basis) {            // all free: B and T are constants of the foot geometry
@@ -1107,7 +1199,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             cx.sync();
         }
         LMH_FOR(col, 13) {            // W[:, col] = Ls^-1 Jb' B[:, col] ; column 12: sv = Ls^-1 rhs (first pass of a stage only)
-            if (col < 12 || iters == 1) {
+            if (col < 12 || first_pass) {
                 const int cc = col < 12 ? col : 0, f = cc / 6, k = cc % 6;
                 double t[6];
                 for (int m = 0; m < 6; ++m) {
@@ -1348,6 +1440,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             }
         }
         cx.sync();
+        first_pass = false;
         if (done) break;
         if (iters >= K.qp_max_iter) { status = 1; break; }
     }
@@ -1383,6 +1476,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             l[r] = s;
         }
         }
+        if (fast_done) {
+            LMH_UNROLL
+            for (int r = 0; r < 6; ++r) l[r] = lfast[r];
+        } else {
         LMH_UNROLL
         for (int r = 0; r < 6; ++r) {
             double s = l[r];
@@ -1396,6 +1493,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             LMH_UNROLL
             for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m];
             l[r] = s * Lsi[r];
+        }
         }
         // a = -Ha^-1 (ga + M6' lam) through the same Woodbury pieces
         double coef[7] = {l[0], l[1], l[2], l[3], l[4], l[5], 1.0};

@@ -219,6 +219,20 @@ private:
                 for (int k = 0; k < 16; ++k) s += K.Gf[16 * i + k] * K.Gf[16 * j + k];
                 K.GGt[6 * i + j] = s;
             }
+        {   // all-free shortcut of the QP: Pinv = (G G')^-1, Dinv = (wForce I + epsC Pinv)^-1 per foot
+            std::vector<double> P(K.GGt, K.GGt + 36), e(6), x(6), D(36);
+            for (int i = 0; i < 6; ++i) {
+                for (int k = 0; k < 6; ++k) e[k] = k == i ? 1.0 : 0.0;
+                if (!dense_solve(6, P, e, x.data())) throw std::runtime_error("lmh: singular wrench Gram matrix");
+                for (int k = 0; k < 6; ++k) K.Pinv[6 * k + i] = x[k];
+            }
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) D[6 * i + j] = K.epsC * 0.5 * (K.Pinv[6 * i + j] + K.Pinv[6 * j + i]) + (i == j ? K.wForce : 0.0);
+            for (int i = 0; i < 6; ++i) {
+                for (int k = 0; k < 6; ++k) e[k] = k == i ? 1.0 : 0.0;
+                if (!dense_solve(6, D, e, x.data())) throw std::runtime_error("lmh: singular wrench weight");
+                for (int k = 0; k < 6; ++k) K.Dinv[6 * k + i] = x[k];
+            }
+        }
         {   // all-free wrench basis: GGt = B B' (plain Cholesky: full rank), T = B'B
             double B[36];
             for (int e = 0; e < 36; ++e) B[e] = K.GGt[e];
