@@ -1033,7 +1033,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     }
     LMH_FOR(i, 1) w.warm_contact = contact;
     cx.sync();
-    // ---- all-free shortcut (no stored working set, both feet in contact: 98 % of the stages of a balancing robot).
+    // ---- all-free shortcut (no stored working set, at least one foot in contact: 98 % of the stages of a balancing robot).
     // With every coefficient free, f ranges over all of R^12 and c is its minimum-norm preimage, so the problem in f is
     //     min 1/2 f'D f  s.t.  Sa lam = rhs - Jb'f,   D = wF I + eps (G G')^-1  (constant, block diagonal per foot),
     // whose multiplier solves the 6 x 6 system (Sa + Jb' D^-1 Jb) lam = rhs, f = D^-1 Jb lam, c = G'(G G')^-1 f.
@@ -1042,14 +1042,14 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     int iters = 0, status = 0;
     bool fast_done = false;
     double lfast[6] = {0, 0, 0, 0, 0, 0};
-    if (!have_point && contact == 3) {
+    if (!have_point && contact != 0) {     // a swing foot (walking extension) carries no force: its block of D^-1 is zero
         double* U = Wb;                // [2][6][6] : D^-1 Jb_f
         double* S6 = Ay;               // [6][6]    : lower triangle of Sa + Jb' D^-1 Jb
         LMH_FOR(it, 72) {
             const int f = it / 36, k = (it % 36) / 6, sidx = it % 6;
             double sd = 0.0;
             for (int l = 0; l < 6; ++l) sd += K.Dinv[6 * k + l] * w.JFc[72 * f + 12 * l + sidx];
-            U[it] = sd;
+            U[it] = ((contact >> f) & 1) ? sd : 0.0;
         }
         cx.sync();
         LMH_FOR(it, 36) {
@@ -1104,7 +1104,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             // feasible: optimal.  Otherwise project onto the orthant, as the first pass of the general iteration
             // would: the clipped coefficients are the working set it starts from
             w.c[i] = sc > 0.0 ? sc : 0.0;
-            w.free_mask[i] = (cmin >= 0.0 || sc > 0.0) ? 1 : 0;
+            w.free_mask[i] = (((contact >> foot) & 1) && (cmin >= 0.0 || sc > 0.0)) ? 1 : 0;
             w.cs[i] = sc; w.mu[i] = 0.0;
         } else
 #endif
@@ -1117,7 +1117,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             }
             cx.sync();
             for (int i = 0; i < NC; ++i) cmin = w.cs[i] < cmin ? w.cs[i] : cmin;
-            LMH_FOR(i, NC) { w.c[i] = w.cs[i] > 0.0 ? w.cs[i] : 0.0; w.free_mask[i] = (cmin >= 0.0 || w.cs[i] > 0.0) ? 1 : 0; }
+            LMH_FOR(i, NC) { w.c[i] = w.cs[i] > 0.0 ? w.cs[i] : 0.0; w.free_mask[i] = (((contact >> (i / 16)) & 1) && (cmin >= 0.0 || w.cs[i] > 0.0)) ? 1 : 0; }
         }
         cx.sync();
         iters = 1;
