@@ -8,6 +8,7 @@
 #include "lmh_setup.hpp"
 #include "lmh_ik.cuh"
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -35,6 +36,8 @@ struct Params {
     double* t;          // [E]
     const int32_t* push_step;
     const double* push_dv;   // [E][6]
+    const int32_t* order;    // [E] slot -> environment (or null = identity): environments that are pushed at the same
+                             // step share a block, so that a block's warps need their extra QP iterations together
     LmhStats* stats;
     LmhStepLog* log;    // [log_cap][E] or null
     LmhStageDump* dump; // [E] or null
@@ -99,7 +102,8 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
     double* kacc = x + 60;
     const int env_raw = blockIdx.x * epb + wid;
     const bool live = env_raw < p.n_env;
-    const int env = live ? env_raw : p.n_env - 1;          // idle warps shadow the last environment and write nothing
+    const int slot = live ? env_raw : p.n_env - 1;         // idle warps shadow the last environment and write nothing
+    const int env = p.order ? p.order[slot] : slot;
     Ctx<32> cx{lane, 1};
     const Consts& K = *p.K;
     ws_reset(cx, w);
@@ -257,7 +261,7 @@ struct LmhBatch {
     Consts* dK = nullptr;
     double *d_x = nullptr, *d_vh = nullptr, *d_t = nullptr, *d_push_dv = nullptr, *d_com = nullptr;
     double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr;
-    int32_t *d_plan_id = nullptr, *d_push_step = nullptr;
+    int32_t *d_plan_id = nullptr, *d_push_step = nullptr, *d_order = nullptr;
     LmhStats* d_stats = nullptr;
     LmhStats* d_stats0 = nullptr;
     std::vector<LmhStats> h_stats0;
@@ -268,7 +272,7 @@ struct LmhBatch {
     int32_t* d_contact = nullptr;
     std::vector<double> h_zmp_x, h_zmp_y, h_foot;
     std::vector<int32_t> h_contact;
-    bool has_pushes = false, has_plan_ids = false;
+    bool has_pushes = false, has_plan_ids = false, has_order = false;
 };
 
 namespace {
@@ -282,6 +286,7 @@ Params make_params(LmhBatch* h) {
     p.x = h->d_x; p.vh = h->d_vh; p.t = h->d_t;
     p.push_step = h->has_pushes ? h->d_push_step : nullptr;
     p.push_dv = h->d_push_dv;
+    p.order = (h->has_pushes && h->has_order) ? h->d_order : nullptr;
     p.stats = h->d_stats; p.log = h->d_log; p.dump = nullptr; p.com = h->d_com;
     p.n_env = h->n_env; p.n_steps = 0; p.step0 = h->step_counter; p.log_cap = h->cfg.log_steps;
     return p;
@@ -404,7 +409,7 @@ void lmh_destroy(LmhBatch* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
-    cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
+    cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_order); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
     cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -533,6 +538,22 @@ int32_t lmh_set_pushes(LmhBatch* h, const int32_t* push_step, const double* push
     if (!h) return fail(LMH_EINVAL, "null handle");
     CU(cudaSetDevice(h->cfg.device));
     h->has_pushes = push_step != nullptr && push_dv6 != nullptr;
+    h->has_order = false;
+    if (h->has_pushes && !std::getenv("LMH_NO_ORDER")) {
+        // placement only (every environment computes exactly what it would anywhere else): slots sorted by push step,
+        // larger impulses first within a step
+        std::vector<int32_t> order((size_t)h->n_env);
+        for (int e = 0; e < h->n_env; ++e) order[e] = e;
+        auto mag = [&](int e) { const double* d = push_dv6 + (size_t)e * 6; double m = 0; for (int k = 0; k < 6; ++k) m += d[k] * d[k]; return m; };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (push_step[a] != push_step[b]) return push_step[a] < push_step[b];
+            return mag(a) > mag(b);
+        });
+        if (!h->d_order) CU(cudaMalloc(&h->d_order, sizeof(int32_t) * h->n_env));
+        CU(cudaMemcpyAsync(h->d_order, order.data(), sizeof(int32_t) * h->n_env, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->has_order = true;
+    }
     if (h->has_pushes) {
         CU(cudaMemcpyAsync(h->d_push_step, push_step, sizeof(int32_t) * h->n_env, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(h->d_push_dv, push_dv6, sizeof(double) * 6 * h->n_env, cudaMemcpyHostToDevice, h->stream));
