@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
 // slice of shared memory); the warps of a block are re-aligned at every stage so that they share instruction fetches.
 __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes) {
     extern __shared__ double smem[];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a broadcast: the compiler then knows it is warp-uniform and keeps the workspace base in
+    // a uniform register
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     char* base = reinterpret_cast<char*>(smem) + (size_t)wid * env_bytes;
     EnvWS& w = *reinterpret_cast<EnvWS*>(base);
     double* x = reinterpret_cast<double*>(base) + (sizeof(EnvWS) + 7) / 8;
