@@ -331,3 +331,25 @@ def test_batched_inverse_kinematics(oracle, ik_golden):
     xg = b.get_state()[0]
     xc, _, _, fails = oracle.batch_rollout(oracle.default_config(), n, 20, x0=np.hstack([r5["q"], np.zeros((n, 30))]), n_threads=8)
     assert fails == 0 and np.abs(xg - xc).max() < 1e-7
+
+
+def test_placement_by_push_step_changes_nothing(monkeypatch):
+    """lmh_set_pushes sorts the SLOTS of the one-block-per-SM kernel by push step (environments that need extra QP
+    iterations at the same time share a block); every environment must compute exactly what it computes unsorted"""
+    E, S = 200, 40
+    step, dv = lmh.push_plan(range(E), max_step=15)
+    out = []
+    for no_order in ("", "1"):
+        if no_order:
+            monkeypatch.setenv("LMH_NO_ORDER", "1")
+        else:
+            monkeypatch.delenv("LMH_NO_ORDER", raising=False)
+        b = lmh.Batch(E)
+        b.set_pushes(step, dv)
+        b.step(S)
+        x, vh, t = b.get_state()
+        st = b.stats()
+        out.append((x, vh, t, st["max_abs_tau"], st["qp_iters"]))
+        b.close()
+    for a, c in zip(*out):
+        assert np.array_equal(a, c)
