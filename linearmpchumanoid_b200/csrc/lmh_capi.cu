@@ -9,6 +9,7 @@
 #include "lmh_ik.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -46,6 +47,9 @@ struct Params {
 };
 
 constexpr int kExtraDoubles = 2 * 60;   // x and the RK4 accumulator
+constexpr int kTabDh = 28 * 36, kTabMpc = kTabDh + 120;     // block-shared constant tables: Isp | DH parameters | mpc_r
+constexpr int kMaxDynSmem = 227 * 1024;
+static_assert(offsetof(Consts, dh_d) == offsetof(Consts, th_off) + 4 * 24 * sizeof(double), "th_off..dh_d must be contiguous");
 
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p) {
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
 
 // One warp per environment, EPB environments per block (warp w of block b owns environment b*EPB + w and its own
 // slice of shared memory); the warps of a block are re-aligned at every stage so that they share instruction fetches.
-__global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes) {
+__global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes, int tab_doubles) {
     extern __shared__ double smem[];
     // the warp index through a broadcast: the compiler then knows it is warp-uniform and keeps the workspace base in
     // a uniform register
@@ -108,6 +112,17 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
     const int env = p.order ? p.order[slot] : slot;
     Ctx<32> cx{lane, 1};
     const Consts& K = *p.K;
+    if (tab_doubles > 0) {
+        // behind the environments' slices: one copy per block of the tables every level of the tree recursions reads
+        // (the 29 KB of L1 left beside 227 KB of shared memory do not keep them: they came from L2 half of the time)
+        double* tab = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + (size_t)epb * env_bytes);
+        for (int i = threadIdx.x; i < 28 * 36; i += blockDim.x) tab[i] = K.Isp[i];
+        for (int i = threadIdx.x; i < 120; i += blockDim.x) tab[kTabDh + i] = K.th_off[i];      // th_off, dh_ca, dh_sa, dh_r, dh_d
+        for (int i = threadIdx.x; i < tab_doubles - kTabMpc; i += blockDim.x) tab[kTabMpc + i] = K.mpc_r[i];
+        __syncthreads();
+        cx.isp = tab; cx.dh = tab + kTabDh;
+        if (tab_doubles > kTabMpc) cx.mpc_r = tab + kTabMpc;
+    }
     ws_reset(cx, w);
     for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
@@ -257,7 +272,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 struct LmhBatch {
     LmhConfig cfg;
     HostModel* hm = nullptr;
-    int32_t n_env = 0, nt = 64, smem = 0, epb = 10;
+    int32_t n_env = 0, nt = 64, smem = 0, epb = 10, tab_doubles = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
@@ -321,7 +336,7 @@ int32_t launch_rollout(LmhBatch* h, int32_t n_steps) {
     dim3 grid(h->n_env), block(h->nt);
     if (h->nt == 32 && h->epb > 1) {
         const int nblk = (h->n_env + h->epb - 1) / h->epb;
-        rollout_kernel_multi<<<nblk, 32 * h->epb, (size_t)h->smem * h->epb, h->stream>>>(p, h->epb, h->smem);
+        rollout_kernel_multi<<<nblk, 32 * h->epb, (size_t)h->smem * h->epb + (size_t)h->tab_doubles * sizeof(double), h->stream>>>(p, h->epb, h->smem, h->tab_doubles);
     } else
     if (h->nt == 32) rollout_kernel<32><<<grid, block, h->smem, h->stream>>>(p);
     else if (h->nt == 64) rollout_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
@@ -381,7 +396,15 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     if (const char* e2 = std::getenv("LMH_EPB")) h->epb = std::atoi(e2);
     if (h->nt != 32 || h->epb < 1) h->epb = 1;
     if (h->epb > 10) h->epb = 10;
-    if (h->epb > 1) CU(cudaFuncSetAttribute(rollout_kernel_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem * h->epb));
+    if (h->epb > 1) {
+        // block-shared constant tables behind the slices, as far as the 227 KB allow: Isp + DH (9 KB), then the MPC gains
+        const int64_t slices = (int64_t)h->smem * h->epb;
+        const int n1 = h->hm->K.mpc_n1;
+        if (slices + (int64_t)(kTabMpc + n1) * 8 <= kMaxDynSmem) h->tab_doubles = kTabMpc + n1;
+        else if (slices + (int64_t)kTabMpc * 8 <= kMaxDynSmem) h->tab_doubles = kTabMpc;
+        if (std::getenv("LMH_NO_TABLES")) h->tab_doubles = 0;
+        CU(cudaFuncSetAttribute(rollout_kernel_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slices + (int64_t)h->tab_doubles * 8)));
+    }
     int32_t rc = h->nt == 32 ? configure_kernels<32>(h->smem) : h->nt == 64 ? configure_kernels<64>(h->smem) : configure_kernels<128>(h->smem);
     if (rc != LMH_OK) { delete h->hm; delete h; return rc; }
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

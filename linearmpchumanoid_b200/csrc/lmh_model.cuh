@@ -189,6 +189,11 @@ struct Ctx {
     static constexpr int NT = NT_;
     int tid;
     int bar_id;          // > 0: several one-warp environments share a block and re-align at align() points
+    // block-shared copies (shared memory) of the constant tables the tree recursions read at every level, or null =
+    // read them from the Consts in global memory: Isp [28][36]; dh = th_off, dh_ca, dh_sa, dh_r, dh_d [5][24]; mpc_r
+    const double* isp = nullptr;
+    const double* dh = nullptr;
+    const double* mpc_r = nullptr;
     LMH_HD void align() const {
 #if defined(__CUDA_ARCH__)
         if (NT == 32 && bar_id > 0) __syncthreads();
@@ -326,7 +331,7 @@ LMH_HD double xdense(const double* Rp, int a, int b) {
 struct EnvWS;
 struct Consts;
 __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane);
-__device__ void fk_local_warp(EnvWS& w, const Consts& K, int lane);
+__device__ void fk_local_warp(EnvWS& w, const Consts& K, const double* dh, int lane);
 #endif
 
 // state that survives from one stage evaluation to the next besides vh: the QP working set (warm start)
@@ -344,7 +349,7 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     double* Tw = w.u.m.p.Tw;
     double* Xl = w.u.m.Xl;
 #if defined(__CUDA_ARCH__)
-    if (Cx::NT == 32) { fk_local_warp(w, K, cx.tid); fk_chain_warp(w, K, cx.tid); return; }
+    if (Cx::NT == 32) { fk_local_warp(w, K, cx.dh ? cx.dh : K.th_off, cx.tid); fk_chain_warp(w, K, cx.tid); return; }
 #endif
     // torso pose (generalizedFunctions.cpp:52-72) and local DH transforms (Robot.cpp:176-223)
     LMH_FOR(i, NF) {
@@ -767,7 +772,8 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
         int ax = it / 16, part = it % 16;
         const double* z = (ax == 0 ? P.zmp_x : P.zmp_y) + (size_t)plan_id * P.zmp_len + k0;
         double s = 0.0;
-        for (int i = part; i < n1; i += 16) s += K.mpc_r[i] * z[i];
+        const double* mr = cx.mpc_r ? cx.mpc_r : K.mpc_r;
+        for (int i = part; i < n1; i += 16) s += mr[i] * z[i];
         w.red[it] = s;
     }
     cx.sync();
@@ -1609,8 +1615,9 @@ LMH_HDN void model_phases(const Cx& cx, EnvWS& w, const Consts& K) {
 #if defined(__CUDA_ARCH__)
     if (Cx::NT == 32) {
         const LaneRole L = lane_role(cx.tid);
-        rnea_warp(w, K, L, cx.tid);
-        crba_warp(w, K, L, cx.tid);
+        const double* Isp = cx.isp ? cx.isp : K.Isp;
+        rnea_warp(w, K, Isp, L, cx.tid);
+        crba_warp(w, K, Isp, L, cx.tid);
     } else
 #endif
     {

@@ -103,11 +103,11 @@ __device__ __forceinline__ double cross3(const double* a, const double* b, int k
 // lanes 1..26 their frame's joint angle, lanes 27..29 roll, pitch, yaw, which reach lane 0 by shuffle (three more
 // sincos calls on lane 0 alone would cost the whole warp three times the call).  The fixed torso->chain transforms
 // are applied by fk_chain_warp, so every joint frame stores its plain DH matrix.
-__device__ void fk_local_warp(EnvWS& w, const Consts& K, int lane) {
+__device__ void fk_local_warp(EnvWS& w, const Consts& K, const double* dh, int lane) {
     const bool jointf = lane >= 1 && lane < NF && lane != 7 && lane != 14;
     const int a = jointf ? frame_joint(lane) : 0;
     double ang = 0.0;
-    if (jointf) ang = w.q[6 + a] + K.th_off[a];
+    if (jointf) ang = w.q[6 + a] + dh[a];
     else if (lane >= 27 && lane < 30) ang = w.q[3 + lane - 27];
     double st, ct;
     sincos(ang, &st, &ct);
@@ -129,8 +129,8 @@ __device__ void fk_local_warp(EnvWS& w, const Consts& K, int lane) {
         w.esc[0] = sp; w.esc[1] = cp; w.esc[2] = sy; w.esc[3] = cy;
     } else if (lane < NF) {
         // soles: identity rotation, offset along x (Robot.cpp:106-117); joints: Khalil's modified DH (Robot.cpp:200-220)
-        const double ca = jointf ? K.dh_ca[a] : 1.0, sa = jointf ? K.dh_sa[a] : 0.0;
-        const double r = jointf ? K.dh_r[a] : 0.0, d = jointf ? K.dh_d[a] : K.sole_x;
+        const double ca = jointf ? dh[24 + a] : 1.0, sa = jointf ? dh[48 + a] : 0.0;
+        const double r = jointf ? dh[72 + a] : 0.0, d = jointf ? dh[96 + a] : K.sole_x;
         double* O = w.u.m.Xl + 12 * lane;
         O[0] = ct; O[1] = -st; O[2] = 0.0;
         O[3] = ca * st; O[4] = ca * ct; O[5] = -sa;
@@ -220,7 +220,7 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
 // Every lane runs every level (idle lanes shadow the last frame of their chain and store nothing): no divergent
 // regions, so the exchanges of the backward pass can be shuffles.  A lane reads only the column of R it needs
 // straight from shared memory (a lane-dependent index into a register copy would put the copy in local memory).
-__device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
+__device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const LaneRole& L, int lane) {
     auto& S = w.u.m.p.wr;
     const double* Xl = w.u.m.Xl;
     const int c8 = 8 * L.c, r = L.r;
@@ -231,7 +231,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
     if (lane < 6) {
         double v0[6];
         ld6v(w.vhb6, v0);
-        const double* I = K.Isp + 6 * lane;
+        const double* I = Isp + 6 * lane;
         S.hbuf[lane] = I[0] * v0[0] + I[1] * v0[1] + I[2] * v0[2] + I[3] * v0[3] + I[4] * v0[4] + I[5] * v0[5];
     }
     __syncwarp();
@@ -259,7 +259,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         const double qd = joint ? w.vh[6 + L.j0 + d - 1] : 0.0;
         if (r == 2) x += qd;
         if (act) S.vbuf[cur ^ 1][c8 + r] = x;
-        load6(K.Isp + 36 * i + 6 * r, Irow);
+        load6(Isp + 36 * i + 6 * r, Irow);
         __syncwarp();
         ld6v(S.vbuf[cur ^ 1] + c8, nv);
         double xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);       // zero at the first level: the base does not accelerate
@@ -323,7 +323,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
 }
 
 // ---- CRBA (Dynamics.cpp:62-101) -> M6 = [Ic0 | F2], Hc
-__device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane) {
+__device__ void crba_warp(EnvWS& w, const Consts& K, const double* Isp, const LaneRole& L, int lane) {
     auto& S = w.u.m.p.wr;
     const double* Xl = w.u.m.Xl;
     const int c8 = 8 * L.c, r = L.r;
@@ -344,7 +344,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
         if (act) {
             ld12v(Xl + 12 * i, Rp);
             double ic[6];
-            load6(K.Isp + 36 * i + 6 * r, ic);
+            load6(Isp + 36 * i + 6 * r, ic);
 #pragma unroll
             for (int k = 0; k < 6; ++k) ic[k] += icin[k];
             S.col2[c8 + r] = ic[2];
@@ -422,7 +422,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const LaneRole& L, int lane
     if (lane < 6) {       // Ic0 = I0 + sum over the five chains
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) {
-            double s = K.Isp[6 * lane + cc];
+            double s = Isp[6 * lane + cc];
             for (int c = NCH - 1; c >= 0; --c) s += S.Ybuf2[36 * c + 6 * lane + cc];
             w.M6[NQ * lane + cc] = s;
         }
