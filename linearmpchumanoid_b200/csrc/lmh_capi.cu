@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
 
 // One warp per environment, EPB environments per block (warp w of block b owns environment b*EPB + w and its own
 // slice of shared memory); the warps of a block are re-aligned at every stage so that they share instruction fetches.
-__global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes, int tab_doubles) {
+__global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes, int tab_doubles, int n_full) {
     extern __shared__ double smem[];
     // the warp index through a broadcast: the compiler then knows it is warp-uniform and keeps the workspace base in
     // a uniform register
@@ -106,11 +106,21 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
     EnvWS& w = *reinterpret_cast<EnvWS*>(base);
     double* x = reinterpret_cast<double*>(base) + (sizeof(EnvWS) + 7) / 8;
     double* kacc = x + 60;
-    const int env_raw = blockIdx.x * epb + wid;
-    const bool live = env_raw < p.n_env;
-    const int slot = live ? env_raw : p.n_env - 1;         // idle warps shadow the last environment and write nothing
+    // Blocks 0 .. n_full-1 carry epb environments each (whole waves of one block per SM); what is left is dealt out
+    // evenly over the remaining blocks, so that the last wave runs everywhere with fewer warps per SM (a wave of 8 is
+    // 15 % shorter than a wave of 10) instead of full on some SMs and not at all on the others.
+    int slot, count;
+    if ((int)blockIdx.x < n_full) { slot = blockIdx.x * epb + wid; count = epb; }
+    else {
+        const int tb = blockIdx.x - n_full, nt = gridDim.x - n_full, rest = p.n_env - n_full * epb;
+        const int base_n = rest / nt, rem = rest % nt;
+        count = base_n + (tb < rem ? 1 : 0);
+        slot = n_full * epb + tb * base_n + (tb < rem ? tb : rem) + wid;
+    }
+    const bool live = wid < count;
+    if (!live) slot = p.n_env - 1;
     const int env = p.order ? p.order[slot] : slot;
-    Ctx<32> cx{lane, 1};
+    Ctx<32> cx{lane, 32 * count == (int)blockDim.x ? -1 : 32 * count};
     const Consts& K = *p.K;
     if (tab_doubles > 0) {
         // behind the environments' slices: one copy per block of the tables every level of the tree recursions reads
@@ -123,6 +133,7 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
         cx.isp = tab; cx.dh = tab + kTabDh;
         if (tab_doubles > kTabMpc) cx.mpc_r = tab + kTabMpc;
     }
+    if (!live) return;                                      // the alignment barrier counts the live warps only
     ws_reset(cx, w);
     for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
@@ -143,10 +154,9 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
             for (int k = lane; k < 6; k += 32) x[30 + k] += p.push_dv[(size_t)env * 6 + k];
             cx.sync();
         }
-        LmhStepLog* lg = (live && p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
+        LmhStepLog* lg = (p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
         rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, lg, &st);
     }
-    if (!live) return;
     for (int i = lane; i < 60; i += 32) p.x[(size_t)env * 60 + i] = x[i];
     for (int i = lane; i < 30; i += 32) p.vh[(size_t)env * 30 + i] = w.vh[i];
     for (int i = lane; i < 3; i += 32) p.com[(size_t)env * 3 + i] = w.com[i];
@@ -272,7 +282,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 struct LmhBatch {
     LmhConfig cfg;
     HostModel* hm = nullptr;
-    int32_t n_env = 0, nt = 64, smem = 0, epb = 10, tab_doubles = 0;
+    int32_t n_env = 0, nt = 64, smem = 0, epb = 10, tab_doubles = 0, sm_count = 148, plain_grid = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
@@ -330,13 +340,24 @@ int32_t upload_plans(LmhBatch* h) {
     return LMH_OK;
 }
 
+// Grid of the one-block-per-SM kernel: whole waves of full blocks, then the rest spread evenly over up to sm_count blocks.
+int multi_grid(const LmhBatch* h, int* n_full_out) {
+    const int cap = h->sm_count * h->epb;
+    int n_full = h->plain_grid ? h->n_env / h->epb : ((h->n_env + cap - 1) / cap - 1) * h->sm_count;
+    const int rest = h->n_env - n_full * h->epb;
+    const int tail = h->plain_grid ? (rest > 0 ? 1 : 0) : std::min(rest, h->sm_count);
+    if (n_full_out) *n_full_out = n_full;
+    return n_full + tail;
+}
+
 int32_t launch_rollout(LmhBatch* h, int32_t n_steps) {
     Params p = make_params(h);
     p.n_steps = n_steps;
     dim3 grid(h->n_env), block(h->nt);
     if (h->nt == 32 && h->epb > 1) {
-        const int nblk = (h->n_env + h->epb - 1) / h->epb;
-        rollout_kernel_multi<<<nblk, 32 * h->epb, (size_t)h->smem * h->epb + (size_t)h->tab_doubles * sizeof(double), h->stream>>>(p, h->epb, h->smem, h->tab_doubles);
+        int n_full = 0;
+        const int nblk = multi_grid(h, &n_full);
+        rollout_kernel_multi<<<nblk, 32 * h->epb, (size_t)h->smem * h->epb + (size_t)h->tab_doubles * sizeof(double), h->stream>>>(p, h->epb, h->smem, h->tab_doubles, n_full);
     } else
     if (h->nt == 32) rollout_kernel<32><<<grid, block, h->smem, h->stream>>>(p);
     else if (h->nt == 64) rollout_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
@@ -394,6 +415,8 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     if (const char* extra = std::getenv("LMH_EXTRA_SMEM")) h->smem += std::atoi(extra);   // occupancy experiments only
     h->smem = (h->smem + 15) / 16 * 16;
     if (const char* e2 = std::getenv("LMH_EPB")) h->epb = std::atoi(e2);
+    if (const char* e3 = std::getenv("LMH_PLAIN_GRID")) h->plain_grid = std::atoi(e3);     // experiments only
+    CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     if (h->nt != 32 || h->epb < 1) h->epb = 1;
     if (h->epb > 10) h->epb = 10;
     if (h->epb > 1) {
@@ -811,7 +834,7 @@ int32_t lmh_launch_info(const LmhBatch* h, int32_t* nt, int32_t* epb, int32_t* s
     if (nt) *nt = h->nt;
     if (epb) *epb = h->epb;
     if (smem) *smem = h->smem;
-    if (blocks) *blocks = (h->n_env + h->epb - 1) / h->epb;
+    if (blocks) *blocks = (h->nt == 32 && h->epb > 1) ? multi_grid(h, nullptr) : h->n_env;
     if (launches) *launches = h->launches;
     return LMH_OK;
 }

@@ -188,7 +188,8 @@ template <int NT_>
 struct Ctx {
     static constexpr int NT = NT_;
     int tid;
-    int bar_id;          // > 0: several one-warp environments share a block and re-align at align() points
+    int bar_id;          // several one-warp environments share a block and re-align at align() points: < 0 all warps of
+                         // the block (plain __syncthreads), > 32 the number of threads taking part (32 x live warps)
     // block-shared copies (shared memory) of the constant tables the tree recursions read at every level, or null =
     // read them from the Consts in global memory: Isp [28][36]; dh = th_off, dh_ca, dh_sa, dh_r, dh_d [5][24]; mpc_r
     const double* isp = nullptr;
@@ -196,7 +197,10 @@ struct Ctx {
     const double* mpc_r = nullptr;
     LMH_HD void align() const {
 #if defined(__CUDA_ARCH__)
-        if (NT == 32 && bar_id > 0) __syncthreads();
+        if (NT == 32) {
+            if (bar_id < 0) __syncthreads();                 // every warp of the block is live
+            else if (bar_id > 32) asm volatile("bar.sync 1, %0;" ::"r"(bar_id) : "memory");
+        }
 #endif
     }
     LMH_HD void sync() const {
