@@ -521,22 +521,39 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
 #pragma unroll
     for (int j = 0; j < ND1; ++j) h[j] = 0.0;
     if (mrow) {
+        // Only the lower triangle of D1 is ever read (row i: columns <= i), so a base row needs the base block of both
+        // feet and a leg row the base and leg blocks of its own foot: two passes of 6 columns x 6 terms for every lane
+        // (part 0: base block of foot fa; part 1: base block of the other foot, or the leg block of the own one).
+        const bool isbase = lane < 6, islegR = lane >= 6 && lane < 12;
+        const int fa = lane < 12 ? 0 : 1;                       // base rows start with the right foot
+        const int ci = isbase ? lane : 6 + (lane - 6 - 6 * fa);  // compact column of this row in foot fa
+        const double* Ja = w.JFc + 72 * fa;
+        const double* Jb = isbase ? w.JFc + 72 : Ja + 6;        // second pass: other foot's base block / own leg block
+        const double* Jcb = isbase ? w.JFc + 72 : Ja;           // ... and the column of this row there
+        double jc[6], t0[6], t1[6];
 #pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const int ci = jf_col(f, lane);
-            if (ci >= 0) {
-                const double* Jf = w.JFc + 72 * f;
-                double jc[6];
+        for (int k = 0; k < 6; ++k) jc[k] = K.wFoot * Ja[12 * k + ci];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) jc[k] = K.wFoot * Jf[12 * k + ci];
+        for (int c = 0; c < 6; ++c) {
+            double sj = 0.0;
 #pragma unroll
-                for (int cj = 0; cj < 12; ++cj) {
-                    double sj = 0.0;
+            for (int k = 0; k < 6; ++k) sj += jc[k] * Ja[12 * k + c];
+            t0[c] = sj;
+        }
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) sj += jc[k] * Jf[12 * k + cj];
-                    h[cj < 6 ? cj : 6 + 6 * f + (cj - 6)] += sj;
-                }
-            }
+        for (int k = 0; k < 6; ++k) jc[k] = K.wFoot * Jcb[12 * k + ci];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double sj = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sj += jc[k] * Jb[12 * k + c];
+            t1[c] = sj;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            h[c] = t0[c] + dsel(isbase, t1[c], 0.0);
+            h[6 + c] = dsel(islegR, t1[c], 0.0);                // left-leg rows: the right-leg columns are zero
+            h[12 + c] = t1[c];                                  // read by the left-leg rows only
         }
         const double wj = lane < 3 ? K.wBasePos : lane < 6 ? K.wBaseAng : K.wJoints;
 #pragma unroll
