@@ -259,7 +259,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         const double qd = joint ? w.vh[6 + L.j0 + d - 1] : 0.0;
         if (r == 2) x += qd;
         if (act) S.vbuf[cur ^ 1][c8 + r] = x;
-        load6(Isp + 36 * i + 6 * r, Irow);
+        ld6v(Isp + 36 * i + 6 * r, Irow);
         __syncwarp();
         ld6v(S.vbuf[cur ^ 1] + c8, nv);
         double xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);       // zero at the first level: the base does not accelerate
@@ -344,7 +344,7 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         if (act) {
             ld12v(Xl + 12 * i, Rp);
             double ic[6];
-            load6(Isp + 36 * i + 6 * r, ic);
+            ld6v(Isp + 36 * i + 6 * r, ic);
 #pragma unroll
             for (int k = 0; k < 6; ++k) ic[k] += icin[k];
             S.col2[c8 + r] = ic[2];
