@@ -507,29 +507,37 @@ __device__ void wrench_solve_warp(EnvWS& w, int lane) {
     __syncwarp();
 }
 
-// ---- QP front end for one warp (see assemble_phase / qp_phase of lmh_model.cuh for the algebra): lane i < 18 owns
-// row i of D1 = Wj + wFoot JF'JF, lanes 18..27 own the ten right-hand-side rows [M6; ga'; U]; rows are assembled
-// straight into registers and the left-looking Cholesky runs on them, reading the finished part of row k back from
-// shared memory as a broadcast.  Leaves L1, ladiag and Yt in shared memory where qp_phase expects them.
+// ---- QP front end for one warp (see assemble_phase / qp_phase of lmh_model.cuh for the algebra).  D1 = Wj + wFoot JF'JF
+// couples the base with each leg but not the legs with each other, so the factorisation runs in the order
+// [right leg, left leg, base]: position p <-> coordinate qp_orig(p).  The two 6 x 6 leg blocks are then independent
+// (their columns k and 6+k are eliminated in the same step: 12 sequential pivots instead of 18, no fill between the
+// legs) and only the six base rows are dense.  Lane p < 18 owns row p, lanes 18..27 own the ten right-hand-side rows
+// [M6; ga'; U]; rows live in registers, the finished part of a pivot row is read back from shared memory as a
+// broadcast.  Leaves L1, ladiag/ladinv and Yt (columns 0..17 in factor order) in shared memory; the Gram matrix of Yt
+// does not depend on the order, and qp_backsolve_warp returns a in coordinate order.
+__device__ __forceinline__ int qp_orig(int p) { return p < 12 ? p + 6 : p - 12; }
+
 __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
     double* L1 = w.u.s.L1;
     double* Yt = w.u.s.Yt;
+    double* Xbl = w.u.s.Wb;                           // [12][6] base-leg block, handed from the leg rows to the base rows
     double h[ND1];
     const bool mrow = lane < ND1;
     const int yr = lane - ND1;                       // right-hand-side row of this lane (0..9) if >= 0
     const bool yrow = yr >= 0 && yr < NYR;
+    const bool isbase = lane >= 12 && lane < ND1;
 #pragma unroll
     for (int j = 0; j < ND1; ++j) h[j] = 0.0;
     if (mrow) {
-        // Only the lower triangle of D1 is ever read (row i: columns <= i), so a base row needs the base block of both
-        // feet and a leg row the base and leg blocks of its own foot: two passes of 6 columns x 6 terms for every lane
-        // (part 0: base block of foot fa; part 1: base block of the other foot, or the leg block of the own one).
-        const bool isbase = lane < 6, islegR = lane >= 6 && lane < 12;
-        const int fa = lane < 12 ? 0 : 1;                       // base rows start with the right foot
-        const int ci = isbase ? lane : 6 + (lane - 6 - 6 * fa);  // compact column of this row in foot fa
+        // Only the lower triangle is ever read (row p: columns <= p).  Two passes of 6 columns x 6 terms per lane:
+        // pass 0 against the base block of a foot (a leg row's result is its piece of the base-leg block, which the
+        // base rows need: it travels through Xbl), pass 1 against the own leg block (leg rows) or the base block of
+        // the other foot (base rows).
+        const int fa = lane < 6 ? 0 : lane < 12 ? 1 : 0;
+        const int ci = isbase ? lane - 12 : 6 + (lane - 6 * fa);     // compact column of this row in foot fa
         const double* Ja = w.JFc + 72 * fa;
-        const double* Jb = isbase ? w.JFc + 72 : Ja + 6;        // second pass: other foot's base block / own leg block
-        const double* Jcb = isbase ? w.JFc + 72 : Ja;           // ... and the column of this row there
+        const double* Jb = isbase ? w.JFc + 72 : Ja + 6;
+        const double* Jcb = isbase ? w.JFc + 72 : Ja;
         double jc[6], t0[6], t1[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) jc[k] = K.wFoot * Ja[12 * k + ci];
@@ -549,27 +557,62 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
             for (int k = 0; k < 6; ++k) sj += jc[k] * Jb[12 * k + c];
             t1[c] = sj;
         }
+        if (!isbase) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) Xbl[6 * lane + c] = t0[c];
+        }
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-            h[c] = t0[c] + dsel(isbase, t1[c], 0.0);
-            h[6 + c] = dsel(islegR, t1[c], 0.0);                // left-leg rows: the right-leg columns are zero
-            h[12 + c] = t1[c];                                  // read by the left-leg rows only
+            h[c] = dsel(lane < 6, t1[c], 0.0);                  // right-leg rows; zero for the left-leg rows
+            h[6 + c] = t1[c];                                   // read by the left-leg rows only (base rows: below)
+            h[12 + c] = t0[c] + t1[c];                          // read by the base rows only
         }
-        const double wj = lane < 3 ? K.wBasePos : lane < 6 ? K.wBaseAng : K.wJoints;
-#pragma unroll
-        for (int j = 0; j < ND1; ++j) h[j] += dsel(j == lane, wj, 0.0);
     } else if (yrow) {
         // row yr of [M6; ga'; U]: a pointer and a scale per lane, no per-entry branching
         const double* src = yr < 6 ? w.M6 + NQ * yr : yr == 6 ? w.ga : w.AG + NQ * (yr - 4);
         const double sc = yr < 7 ? 1.0 : K.sq_wCoML;
         const double sc2 = sc * K.isq_wJoints;
 #pragma unroll
-        for (int j = 0; j < ND1; ++j) h[j] = sc * src[j];
+        for (int j = 0; j < ND1; ++j) h[j] = sc * src[j < 12 ? j + 6 : j - 12];
 #pragma unroll
         for (int j = ND1; j < NQ; ++j) Yt[NQ * yr + j] = sc2 * src[j];     // the arm/head part needs no solve
     }
+    __syncwarp();
+    if (isbase) {
+        const int bcol = lane - 12;
 #pragma unroll
-    for (int k = 0; k < ND1; ++k) {
+        for (int c = 0; c < 12; ++c) h[c] = Xbl[6 * c + bcol];
+    }
+    if (mrow) {
+        const int o = qp_orig(lane);
+        const double wj = o < 3 ? K.wBasePos : o < 6 ? K.wBaseAng : K.wJoints;
+#pragma unroll
+        for (int j = 0; j < ND1; ++j) h[j] += dsel(j == lane, wj, 0.0);
+    }
+    // the two leg blocks, columns k and 6 + k together
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double sa = h[k], sb = h[6 + k];
+        const double* La = L1 + LD1 * k;
+        const double* Lb = L1 + LD1 * (6 + k) + 6;
+#pragma unroll
+        for (int m = 0; m < k; ++m) { sa -= h[m] * La[m]; sb -= h[6 + m] * Lb[m]; }
+        const double piva = __shfl_sync(0xffffffffu, sa, k), pivb = __shfl_sync(0xffffffffu, sb, 6 + k);
+        const double rsa = lmh_rsqrt(piva), rsb = lmh_rsqrt(pivb);
+        const double lika = lane == k ? piva * rsa : sa * rsa;
+        const double likb = lane == 6 + k ? pivb * rsb : sb * rsb;
+        h[k] = lika; h[6 + k] = likb;
+        if (mrow) {
+            if (lane > k) L1[LD1 * lane + k] = lika;
+            if (lane > 6 + k) L1[LD1 * lane + 6 + k] = likb;
+        }
+        if (lane == k) { w.ladiag[k] = lika; w.ladinv[k] = rsa; }
+        if (lane == 6 + k) { w.ladiag[6 + k] = likb; w.ladinv[6 + k] = rsb; }
+        __syncwarp();
+    }
+    // the base block
+#pragma unroll
+    for (int k = 12; k < ND1; ++k) {
         double s = h[k], t = 0.0;
         const double* Lk = L1 + LD1 * k;
 #pragma unroll
@@ -593,7 +636,7 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
     __syncwarp();
 }
 
-// back substitution L1' a[0:18] = b with lane i holding a_i (w.a in, w.a out)
+// back substitution L1' a = b in factor order with lane p holding a_p (w.a[0:18] in: factor order; out: coordinate order)
 __device__ void qp_backsolve_warp(EnvWS& w, int lane) {
     const double* L1 = w.u.s.L1;
     double ai = lane < ND1 ? w.a[lane] : 0.0;
@@ -604,7 +647,8 @@ __device__ void qp_backsolve_warp(EnvWS& w, int lane) {
         if (lane == k) ai = xk;
         else if (lane < k) ai -= L1[LD1 * k + lane] * xk;
     }
-    if (lane < ND1) w.a[lane] = ai;
+    __syncwarp();
+    if (lane < ND1) w.a[qp_orig(lane)] = ai;
     __syncwarp();
 }
 
