@@ -1457,7 +1457,9 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     w.qp_fallback = iters > 1 ? 1 : 0;     // stages whose all-free solution was infeasible (contact-limited)
     w.qp_iters = iters;
     w.qp_status = status;
-    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12)
+    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12).  After the shortcut both are already there: f12 = D^-1 Jb lam is the
+    // wrench whose minimum-norm preimage c is (G c = f12 up to rounding), and lam came out of the 6 x 6 system.
+    if (!fast_done) {
     LMH_FOR(r, 12) {
         int foot = r / 6, k = r % 6;
         double s = 0.0;
@@ -1465,10 +1467,12 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         w.f12[r] = s;
     }
     cx.sync();
+    }
     {
-        double l[6];
+        double l[6] = {0, 0, 0, 0, 0, 0};
 #if defined(__CUDA_ARCH__)
-        if (Cx::NT == 32) {       // lane r < 6 forms its own entry, then every lane collects the six
+        if (fast_done) {
+        } else if (Cx::NT == 32) {       // lane r < 6 forms its own entry, then every lane collects the six
             const int r = cx.tid < 6 ? cx.tid : 0;
             double s = w.rhs[r];
             LMH_UNROLL
@@ -1477,7 +1481,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             for (int q = 0; q < 6; ++q) l[q] = __shfl_sync(0xffffffffu, s, q);
         } else
 #endif
-        {
+        if (!fast_done) {
         LMH_UNROLL
         for (int r = 0; r < 6; ++r) {
             double s = w.rhs[r];
