@@ -754,6 +754,26 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
     cx.sync();
     }
     // h = AG vb (current velocity)
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) {
+        // thirty lanes: lane 6 seg + k sums six terms of row k (a 30-term chain on six lanes was 3 % of the stage),
+        // the five partial sums of a row meet through shared memory
+        const int lane = cx.tid, k = lane % 6, seg = lane / 6;
+        if (lane < 30) {
+            double s = 0.0;
+            LMH_UNROLL
+            for (int j = 0; j < 6; ++j) s += w.AG[NQ * k + 6 * seg + j] * vb_at(w, 6 * seg + j);
+            w.red[lane] = s;
+        }
+        cx.sync();
+        if (lane < 6) {
+            const double s = (((w.red[lane] + w.red[6 + lane]) + w.red[12 + lane]) + w.red[18 + lane]) + w.red[24 + lane];
+            if (lane < 3) w.angMom[lane] = s; else w.comVel[lane - 3] = s * K.inv_mass;
+        }
+        cx.sync();
+        return;
+    }
+#endif
     LMH_FOR(k, 6) {
         double s = 0.0;
         for (int j = 0; j < NQ; ++j) s += w.AG[NQ * k + j] * vb_at(w, j);

@@ -642,10 +642,22 @@ __device__ void qp_backsolve_warp(EnvWS& w, int lane) {
     double ai = lane < ND1 ? w.a[lane] : 0.0;
     const double invd = lane < ND1 ? w.ladinv[lane] : 0.0;
 #pragma unroll
-    for (int k = ND1 - 1; k >= 0; --k) {
+    for (int k = ND1 - 1; k >= 12; --k) {            // base
         const double xk = __shfl_sync(0xffffffffu, ai * invd, k);
         if (lane == k) ai = xk;
         else if (lane < k) ai -= L1[LD1 * k + lane] * xk;
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {                   // the legs do not see each other: pivots 6 + k and k together
+        const double t = ai * invd;
+        const double xb = __shfl_sync(0xffffffffu, t, 6 + k), xa = __shfl_sync(0xffffffffu, t, k);
+        if (lane >= 6) {
+            if (lane == 6 + k) ai = xb;
+            else if (lane < 6 + k) ai -= L1[LD1 * (6 + k) + lane] * xb;
+        } else {
+            if (lane == k) ai = xa;
+            else if (lane < k) ai -= L1[LD1 * k + lane] * xa;
+        }
     }
     __syncwarp();
     if (lane < ND1) w.a[qp_orig(lane)] = ai;
