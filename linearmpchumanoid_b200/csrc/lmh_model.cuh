@@ -79,9 +79,7 @@ struct Consts {
     double qdes[NQ];          // Robot::desiredPosture (Robot.cpp:253-262)
     double Rdes[9];           // desired sole orientation (Robot.cpp:28-31)
     double Gf[6 * 16];        // per-foot wrench generators: rows 0-2 moment, 3-5 force (controller.cpp:156-294)
-    double GtG[16 * 16];      // Gf' Gf
     double GGt[36];           // Gf Gf' (6 x 6), the all-free wrench Gram matrix of one foot
-    double Ball[36], Tall[36], BTiall[36];    // its Cholesky factor B (GGt = B B'), B'B and B (B'B)^-1
     double Pinv[36], Dinv[36];                // GGt^-1 and (wForce I + epsC GGt^-1)^-1: the all-free shortcut of the QP
     double sq_wCoML, isq_wJoints;   // sqrt(wCoML), 1/sqrt(wJoints)
     double KpJ, KdJ, KpM, KdM, KpF, KdF;                                    // controller.hpp:100-111
@@ -1173,11 +1171,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     bool first_pass = true;            // of the general iteration in this stage
     while (!fast_done) {
         ++iters;
-        const bool const_basis = !have_point && contact == 3;
-        if (const_basis) {            // all free: B and T are constants of the foot geometry
-            LMH_FOR(it, 72) { Bm[it] = K.Ball[it % 36]; Pm[it] = K.Tall[it % 36]; }
-            cx.sync();
-        } else {
+        {
             LMH_FOR(it, 72) {         // P_F per foot
                 const int f = it / 36, i = (it % 36) / 6, j = it % 6;
                 const double* gi = K.Gf + 16 * i;
@@ -1303,17 +1297,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         }
         }
         const double* zeta = Ay + 13 * 12;
-        if (const_basis) {
-            // all free: y = B T^-1 zeta with the constant matrix B T^-1; no working set, so no multipliers to look at
-            LMH_FOR(it, 12) {
-                const int f = it / 6, i = it % 6;
-                double sy = 0.0;
-                for (int k = 0; k < 6; ++k) sy += K.BTiall[6 * i + k] * zeta[6 * f + k];
-                vv[12 + it] = sy;
-                vv[24 + it] = 0.0;
-            }
-            cx.sync();
-        } else {
+        {
         LMH_FOR(it, 14) {
             if (it < 12) {            // f = B zeta
                 const int f = it / 6;

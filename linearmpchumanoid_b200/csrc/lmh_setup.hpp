@@ -207,12 +207,6 @@ private:
                 double mom[3] = {p[1] * b[2] - p[2] * b[1], p[2] * b[0] - p[0] * b[2], p[0] * b[1] - p[1] * b[0]};
                 for (int k = 0; k < 3; ++k) { K.Gf[16 * k + 4 * v + e] = mom[k]; K.Gf[16 * (3 + k) + 4 * v + e] = b[k]; }
             }
-        for (int i = 0; i < 16; ++i)
-            for (int j = 0; j < 16; ++j) {
-                double s = 0;
-                for (int k = 0; k < 6; ++k) s += K.Gf[16 * k + i] * K.Gf[16 * k + j];
-                K.GtG[16 * i + j] = s;
-            }
         for (int i = 0; i < 6; ++i)
             for (int j = 0; j < 6; ++j) {
                 double s = 0;
@@ -231,26 +225,6 @@ private:
                 for (int k = 0; k < 6; ++k) e[k] = k == i ? 1.0 : 0.0;
                 if (!dense_solve(6, D, e, x.data())) throw std::runtime_error("lmh: singular wrench weight");
                 for (int k = 0; k < 6; ++k) K.Dinv[6 * k + i] = x[k];
-            }
-        }
-        {   // all-free wrench basis: GGt = B B' (plain Cholesky: full rank), T = B'B
-            double B[36];
-            for (int e = 0; e < 36; ++e) B[e] = K.GGt[e];
-            chol6(B);
-            for (int i = 0; i < 6; ++i) for (int j = i + 1; j < 6; ++j) B[6 * i + j] = 0.0;
-            for (int e = 0; e < 36; ++e) K.Ball[e] = B[e];
-            for (int k = 0; k < 6; ++k)
-                for (int l = 0; l < 6; ++l) {
-                    double t = 0;
-                    for (int i = 0; i < 6; ++i) t += B[6 * i + k] * B[6 * i + l];
-                    K.Tall[6 * k + l] = t;
-                }
-            // B T^-1 : solve T X' = B' column by column
-            for (int i = 0; i < 6; ++i) {
-                std::vector<double> Tm(K.Tall, K.Tall + 36), rhs(6), x(6);
-                for (int k = 0; k < 6; ++k) rhs[k] = B[6 * i + k];
-                dense_solve(6, Tm, rhs, x.data());
-                for (int k = 0; k < 6; ++k) K.BTiall[6 * i + k] = x[k];
             }
         }
     }

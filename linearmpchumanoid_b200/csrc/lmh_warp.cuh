@@ -32,14 +32,6 @@ __device__ __forceinline__ LaneRole lane_role(int lane) {
     return L;
 }
 
-__device__ __forceinline__ void load6(const double* p, double* o) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = p[k];
-}
-__device__ __forceinline__ void load12(const double* p, double* o) {
-#pragma unroll
-    for (int k = 0; k < 12; ++k) o[k] = p[k];
-}
 // p ? a : b as a select instruction: lane-dependent choices between values that every lane has anyway must not
 // become divergent branches (a lone warp pays ~15 cycles per resolved branch; the FP64 and ALU pipes are mostly idle)
 __device__ __forceinline__ double dsel(bool p, double a, double b) {
@@ -70,15 +62,6 @@ __device__ __forceinline__ double xm_lane(double e0, double e1, double e2, doubl
     const double a2 = dsel(lin, m[5] + (m[0] * p1 - m[1] * p0), m[2]);
     return e0 * a0 + e1 * a1 + e2 * a2;
 }
-// row r of X m, X = [[E,0],[-E p^,E]], E = R'
-__device__ __forceinline__ double xm_row(const double* Rp, const double* m, int r) {
-    if (r < 3) return Rp[r] * m[0] + Rp[3 + r] * m[1] + Rp[6 + r] * m[2];
-    const int k = r - 3;
-    const double u0 = m[3] + (m[1] * Rp[11] - m[2] * Rp[10]);
-    const double u1 = m[4] + (m[2] * Rp[9] - m[0] * Rp[11]);
-    const double u2 = m[5] + (m[0] * Rp[10] - m[1] * Rp[9]);
-    return Rp[k] * u0 + Rp[3 + k] * u1 + Rp[6 + k] * u2;
-}
 // all six components of X' f : [R n + p x (R f); R f]
 __device__ __forceinline__ void xf_all(const double* Rp, const double* f, double* o) {
     const double r0 = Rp[0] * f[3] + Rp[1] * f[4] + Rp[2] * f[5];
@@ -88,11 +71,6 @@ __device__ __forceinline__ void xf_all(const double* Rp, const double* f, double
     o[1] = Rp[3] * f[0] + Rp[4] * f[1] + Rp[5] * f[2] + (Rp[11] * r0 - Rp[9] * r2);
     o[2] = Rp[6] * f[0] + Rp[7] * f[1] + Rp[8] * f[2] + (Rp[9] * r1 - Rp[10] * r0);
     o[3] = r0; o[4] = r1; o[5] = r2;
-}
-__device__ __forceinline__ double xf_row(const double* Rp, const double* f, int r) {
-    double o[6];
-    xf_all(Rp, f, o);
-    return r == 0 ? o[0] : r == 1 ? o[1] : r == 2 ? o[2] : r == 3 ? o[3] : r == 4 ? o[4] : o[5];
 }
 __device__ __forceinline__ double cross3(const double* a, const double* b, int k) {
     return k == 0 ? a[1] * b[2] - a[2] * b[1] : k == 1 ? a[2] * b[0] - a[0] * b[2] : a[0] * b[1] - a[1] * b[0];

@@ -353,3 +353,23 @@ def test_placement_by_push_step_changes_nothing(monkeypatch):
         b.close()
     for a, c in zip(*out):
         assert np.array_equal(a, c)
+
+
+def test_grid_shape_changes_nothing():
+    """whole waves of ten-environment blocks plus a thinned last wave (9 full blocks per SM would not divide 1483):
+    an environment's result must not depend on how many neighbours its block has or where in the grid it sits"""
+    S = 12
+    ref = None
+    for E in (1483, 37, 1):                      # 148 full blocks + 3 tail blocks of one; 37 blocks of one; one block
+        b = lmh.Batch(E)
+        step, dv = lmh.push_plan(range(E), max_step=6)
+        b.set_pushes(step, dv)
+        b.step(S)
+        x, vh, t = b.get_state()
+        info = b.launch_info()
+        b.close()
+        if ref is None:
+            ref = (x, vh, t)
+            assert info["blocks"] == 151
+        else:
+            assert np.array_equal(x, ref[0][:E]) and np.array_equal(vh, ref[1][:E]) and np.array_equal(t, ref[2][:E])
