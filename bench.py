@@ -218,15 +218,34 @@ def run_qp_microbench(args):
         worst = max(worst, float(np.abs(a[e] - xa).max() / max(1.0, np.abs(xa).max())),
                     float(np.abs(f[e] - xf).max() / max(1.0, np.abs(xf).max())))
     cpu_stage_rate = n / (time.perf_counter() - t0)
+    # condensed LIPM-MPC over the horizons BASELINE names (16-64 samples) on the same frozen states: evaluations/s and the
+    # MPC outputs [pos+, vel+, u0] of both axes against the oracle's Mpc3dLip (dense Hessian solve) at that horizon
+    mpc_sweep = {}
+    for N in (16, 32, 64):
+        hz = N * b.cfg.dt * (1.0 + 1e-9)            # (int)(horizon / dt) == N, as mpcLinearPendulum.hpp:49 computes it
+        bn = lmh.Batch(E, threads_per_env=args.threads_per_env, time_horizon=hz)
+        bn.set_state(X, VH, T)
+        ms_m0, _, _ = bn.qp_bench(0, 1)
+        ms_m1, _, _ = bn.qp_bench(1, 4 * R)
+        dn = bn.stage()
+        son = O.sim(time_horizon=hz)
+        err = 0.0
+        for e in range(min(E, 50)):
+            son.set_state(X[e], float(T[e]), VH[e])
+            do = son.stage(X[e], float(T[e]))
+            err = max(err, float(np.abs(dn["xRef"][e] - do["xRef"]).max()), float(np.abs(dn["yRef"][e] - do["yRef"]).max()))
+        mpc_sweep[str(N)] = {"evaluations_per_s": E * 4 * R / ((ms_m1 - ms_m0) * 1e-3) if ms_m1 > ms_m0 else float("nan"),
+                             "max_abs_err_refs_vs_oracle": err}
+        bn.close()
     line = {"metric": "WBC QP solves/sec (74 var, 18 eq, 32 ineq; cold start, frozen states)", "value": qps, "unit": "QPs/s",
             "n_gpus": 1, "steps": R, "warmup": 2, "ms_per_step": (ms_qp - ms_model) / (R - 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "QP microbenchmark on frozen states (BASELINE configs[4])", "envs": E,
                        "states": "config 2 at step 50", "repeats": R},
-            "mpc_evaluations_per_s": mpcs, "max_rel_err_a_f_vs_oracle": worst, "oracle_sample_envs": n,
+            "mpc_evaluations_per_s": mpcs, "mpc_horizon_sweep": mpc_sweep, "max_rel_err_a_f_vs_oracle": worst, "oracle_sample_envs": n,
             "cpu_baseline": {"value": cpu_stage_rate, "unit": "stage evaluations/s (model + MPC + QP)", "cores": 1, "kind": "port",
                              "sample": f"{n} frozen states, oracle stage evaluation (its QP is ~85% of a stage)"},
-            "gpu_launches": 4}
+            "gpu_launches": 4 + 3 * 3}
     _emit(line)
     b.close()
     return 0
