@@ -120,7 +120,9 @@ int32_t lmh_set_state(LmhBatch* h, const double* x, const double* v_held, const 
 int32_t lmh_get_state(LmhBatch* h, double* x, double* v_held, double* t);
 int32_t lmh_reset(LmhBatch* h);
 /* Velocity impulse added to v[0:6] of env e at the START of step push_step[e] (counted from the last
- * reset / lmh_set_step_counter); push_step < 0 = none.  Extension: the reference has no pushes. */
+ * reset / lmh_set_step_counter); push_step < 0 = none.  Extension: the reference has no pushes.
+ * Side effect on placement only: environments are assigned to thread blocks in the order of their push step, so that
+ * the environments of a block need their extra QP iterations at the same time; results do not depend on it. */
 int32_t lmh_set_pushes(LmhBatch* h, const int32_t* push_step, const double* push_dv6);
 int32_t lmh_set_step_counter(LmhBatch* h, int32_t step);
 
