@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The built library is git-ignored: in a fresh checkout with nvcc on the PATH, build it in-tree (what
+    __graft_entry__.build() does) before the tests look for it.  Without nvcc the tests report it missing."""
+    import shutil
+    import linearmpchumanoid_b200 as lmh
+    if not os.path.exists(lmh.LIB_PATH) and shutil.which("nvcc"):
+        lmh.build_library()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """CPU restatement of the reference (oracle/liblmh_oracle.so): the CHECKER, never the thing under test."""
