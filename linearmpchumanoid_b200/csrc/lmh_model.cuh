@@ -129,6 +129,7 @@ struct EnvWS {
     double red[32];                // reduction scratch
     int32_t free_mask[NC];
     int32_t pdone[12], ppiv[2];
+    int32_t pord[12];              // pivot row of column k of the wrench-space basis of foot f at [6 f + k], or -1 (beyond the rank)
     int32_t k_index, qp_iters, qp_status, qp_fallback;
     int32_t phase, contact;        // walking extension: phase index and contact mask of this stage
     int32_t warm_contact, dead;    // contact mask the stored working set (free_mask, c) belongs to (-1 = none);
@@ -1038,7 +1039,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     double* Pm = w.u.s.Pm;            // [2][36] : residual of the pivoted Cholesky, then T = B'B
     double* Wb = w.u.s.Wb;            // [6][12] : Ls^-1 Jb' B
     double* Ay = w.u.s.Ay;            // 13 x 13 : lower triangle factorised in place, row 12 = rhs / zeta
-    double* vv = w.u.s.vv;            // [36]   : u = T^-1 zeta (12), y = B u (12), r = wF f - Jb lam (12)
+    double* vv = w.u.s.vv;            // [36]   : (12 unused), y with B'y = zeta (12), r = wF f - Jb lam (12)
     const int contact = w.contact;     // bit f: foot f may carry force (both set in the reference's stand task)
     // Warm start: consecutive stage evaluations of an environment nearly always share their working set, and any
     // c >= 0 is a feasible starting point, so the previous solution (w.c, w.free_mask) seeds the iteration when it
@@ -1196,9 +1197,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
                     double best = 1e-10 * dmax0[f];
                     for (int j = 0; j < 6; ++j) if (!w.pdone[6 * f + j] && S[7 * j] > best) { best = S[7 * j]; p = j; }
                     double colv = 0.0;
-                    if (p >= 0 && !w.pdone[it]) colv = p == i ? sqrt(best) : S[6 * i + p] / sqrt(best);
+                    const double rs = lmh_rsqrt(p >= 0 ? best : 1.0);
+                    if (p >= 0 && !w.pdone[it]) colv = p == i ? best * rs : S[6 * i + p] * rs;
                     Bm[6 * it + k] = colv;
-                    if (i == 0) w.ppiv[f] = p;
+                    if (i == 0) { w.ppiv[f] = p; w.pord[6 * f + k] = p; w.piv[16 + 6 * f + k] = rs; }   // piv[16..27]: 1 / B[p_k][k]
                 }
                 cx.sync();
                 LMH_FOR(it, 12) {
@@ -1304,35 +1306,26 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
                 double sd = 0.0;
                 for (int k = 0; k < 6; ++k) sd += Bm[6 * it + k] * zeta[6 * f + k];
                 w.f12[it] = sd;
-            } else {                  // u = T^-1 zeta per foot (unit diagonal on the columns beyond the rank)
+            } else {
+                // y with B'y = zeta, for c_F = G_F'y.  Any solution does (they differ by null(B') = null(G_F')), and in
+                // pivot order B' is upper triangular -- column k is zero on the rows pivoted before it -- so one is had
+                // by back substitution with y = 0 on the rows that were never pivoted (rank-deficient contact sets).
                 const int f = it - 12;
-                double A6[36], u[6];
-                LMH_UNROLL
-                for (int e = 0; e < 36; ++e) A6[e] = Pm[36 * f + e];
-                LMH_UNROLL
-                for (int k = 0; k < 6; ++k) if (A6[7 * k] == 0.0) A6[7 * k] = 1.0;
-                chol6(A6);
-                LMH_UNROLL
-                for (int r = 0; r < 6; ++r) {
-                    double sd = zeta[6 * f + r];
-                    LMH_UNROLL
-                    for (int m = 0; m < r; ++m) sd -= A6[6 * r + m] * u[m];
-                    u[r] = sd / A6[7 * r];
+                double* y = vv + 12 + 6 * f;
+                for (int i = 0; i < 6; ++i) y[i] = 0.0;
+                for (int k = 5; k >= 0; --k) {
+                    const int p = w.pord[6 * f + k];
+                    if (p >= 0) {
+                        double sd = zeta[6 * f + k];
+                        for (int i = 0; i < 6; ++i) sd -= Bm[6 * (6 * f + i) + k] * y[i];      // y[p] is still zero here
+                        y[p] = sd * w.piv[16 + 6 * f + k];
+                    }
                 }
-                LMH_UNROLL
-                for (int r = 5; r >= 0; --r) {
-                    double sd = u[r];
-                    LMH_UNROLL
-                    for (int m = r + 1; m < 6; ++m) sd -= A6[6 * m + r] * u[m];
-                    u[r] = sd / A6[7 * r];
-                }
-                LMH_UNROLL
-                for (int r = 0; r < 6; ++r) vv[6 * f + r] = u[r];
             }
         }
         cx.sync();
         {
-            // lam = Sa^-1 (rhs - Jb'f) in every thread; y = B u; r = wF f - Jb lam
+            // lam = Sa^-1 (rhs - Jb'f) in every thread; r = wF f - Jb lam
             double l[6];
             LMH_UNROLL
             for (int r = 0; r < 6; ++r) {
@@ -1357,10 +1350,8 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             }
             LMH_FOR(it, 12) {
                 const int f = it / 6;
-                double sy = 0.0, sj = 0.0;
-                for (int k = 0; k < 6; ++k) sy += Bm[6 * it + k] * vv[6 * f + k];
+                double sj = 0.0;
                 for (int r = 0; r < 6; ++r) sj += w.JFc[72 * f + 12 * (it % 6) + r] * l[r];
-                vv[12 + it] = sy;
                 vv[24 + it] = K.wForce * w.f12[it] - sj;
             }
         }
