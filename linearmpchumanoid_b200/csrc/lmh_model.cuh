@@ -1210,10 +1210,9 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
                     if (p >= 0) {
                         const double colv = Bm[6 * it + k];
                         for (int j = 0; j < 6; ++j) S[6 * i + j] -= colv * Bm[6 * (6 * f + j) + k];
+                        if (i == p) w.pdone[it] = 1;          // nobody reads the flags in this pass
                     }
                 }
-                cx.sync();
-                LMH_FOR(f, 2) { if (w.ppiv[f] >= 0) w.pdone[6 * f + w.ppiv[f]] = 1; }
                 cx.sync();
             }
             LMH_FOR(it, 72) {         // T = B'B per foot (into Pm)
