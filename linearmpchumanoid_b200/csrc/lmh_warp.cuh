@@ -55,13 +55,6 @@ __device__ __forceinline__ void ld12v(const double* p, double* o) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) { const double2 t = q[k]; o[2 * k] = t.x; o[2 * k + 1] = t.y; }
 }
-// row r of X m for the lane that holds row k3 = r % 3 of E (e0..e2) and p: E m_ang (r < 3) or E (m_lin + m_ang x p)
-__device__ __forceinline__ double xm_lane(double e0, double e1, double e2, double p0, double p1, double p2, const double* m, bool lin) {
-    const double a0 = dsel(lin, m[3] + (m[1] * p2 - m[2] * p1), m[0]);
-    const double a1 = dsel(lin, m[4] + (m[2] * p0 - m[0] * p2), m[1]);
-    const double a2 = dsel(lin, m[5] + (m[0] * p1 - m[1] * p0), m[2]);
-    return e0 * a0 + e1 * a1 + e2 * a2;
-}
 // all six components of X' f : [R n + p x (R f); R f]
 __device__ __forceinline__ void xf_all(const double* Rp, const double* f, double* o) {
     const double r0 = Rp[0] * f[3] + Rp[1] * f[4] + Rp[2] * f[5];
@@ -232,15 +225,19 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         const double* X = Xl + 12 * i;
         const double e0 = X[k3], e1 = X[3 + k3], e2 = X[6 + k3];     // column k3 of R = row k3 of E
         const double p0 = X[9], p1 = X[10], p2 = X[11];
+        // row r of X m = a . m_ang + b . m_lin: angular rows (a, b) = (e, 0); linear rows e . (m_lin + m_ang x p) =
+        // (p x e) . m_ang + e . m_lin.  The pair serves both the velocity and the acceleration of this level.
+        const double a0 = dsel(lin, p1 * e2 - p2 * e1, e0), a1 = dsel(lin, p2 * e0 - p0 * e2, e1), a2 = dsel(lin, p0 * e1 - p1 * e0, e2);
+        const double b0 = dsel(lin, e0, 0.0), b1 = dsel(lin, e1, 0.0), b2 = dsel(lin, e2, 0.0);
         double nv[6], Irow[6];
-        double x = xm_lane(e0, e1, e2, p0, p1, p2, pv, lin);
+        double x = (a0 * pv[0] + a1 * pv[1] + a2 * pv[2]) + (b0 * pv[3] + b1 * pv[4] + b2 * pv[5]);
         const double qd = joint ? w.vh[6 + L.j0 + d - 1] : 0.0;
         if (r == 2) x += qd;
         if (act) S.vbuf[cur ^ 1][c8 + r] = x;
         ld6v(Isp + 36 * i + 6 * r, Irow);
         __syncwarp();
         ld6v(S.vbuf[cur ^ 1] + c8, nv);
-        double xa = xm_lane(e0, e1, e2, p0, p1, p2, pa, lin);       // zero at the first level: the base does not accelerate
+        double xa = (a0 * pa[0] + a1 * pa[1] + a2 * pa[2]) + (b0 * pa[3] + b1 * pa[4] + b2 * pa[5]);   // zero at the first level
         // (v x S) qd with S = e_z: component r is sgn * v[partner], lane constants (rows 2 and 5: sgn = 0)
         const double colv = dsel(lin, dsel(r == 3, nv[4], nv[3]), dsel(r == 0, nv[1], nv[0]));
         xa += (csgn * colv) * qd;
