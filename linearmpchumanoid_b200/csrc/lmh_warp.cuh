@@ -298,101 +298,117 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
 }
 
 // ---- CRBA (Dynamics.cpp:62-101) -> M6 = [Ic0 | F2], Hc
-__device__ void crba_warp(EnvWS& w, const Consts& K, const double* Isp, const LaneRole& L, int lane) {
-    auto& S = w.u.m.p.wr;
-    const double* Xl = w.u.m.Xl;
-    const int c8 = 8 * L.c, r = L.r;
-    const bool lin = r >= 3;
-    const int k3 = lin ? r - 3 : r;
-    double icin[6] = {0, 0, 0, 0, 0, 0};     // row r of the composite inertia arriving from the level below
-    double F[6] = {0, 0, 0, 0, 0, 0};        // force vector of joint (c, r), expressed in the frame reached so far
-    if (lane < 30) {
+// The composite inertia of a chain goes up one frame per level: Ic' = X'(I + Ic)X with X = [[E,0],[B,E]], B = -E p^.
+// Six lanes hold it, and the levels ALTERNATE between two layouts so that the only exchange per level is a 6 x 6
+// transpose through shared memory (six words out, six words in per lane; reading whole rows of the intermediate
+// product for every output row cost six times the wavefronts):
+//   even d: lane r holds ROW r     -> row r of Y = Ic X        -> transpose -> column r of X'Y  (a column of Ic')
+//   odd  d: lane r holds COLUMN r  -> column r of Z = X'Ic     -> transpose -> row r of Z X     (a row of Ic')
+// d = 1 is odd, so every chain arrives at the torso in rows.  Nothing is assumed symmetric (the inertia literals are not).
+// v X for a row vector v = [v_ang, v_lin]: with u = v_lin E, v X = [v_ang E + v_lin B, u] and v_lin B = -(u p^) = p x u
+// (B never has to be formed: eighteen registers less across the exchange)
+__device__ __forceinline__ void crba_row_times_X(const double* Rp, const double* v, double* o) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) w.Hc[36 * L.c + 6 * r + k] = 0.0;
+    for (int cc = 0; cc < 3; ++cc) {          // E[k][cc] = R[cc][k] = Rp[3 cc + k]
+        const double e0 = Rp[3 * cc], e1 = Rp[3 * cc + 1], e2 = Rp[3 * cc + 2];
+        o[3 + cc] = v[3] * e0 + v[4] * e1 + v[5] * e2;
+        o[cc] = v[0] * e0 + v[1] * e1 + v[2] * e2;
     }
-#pragma unroll 1
-    for (int d = MAXDEPTH - 1; d >= 1; --d) {
-        const bool act = L.on && d <= L.nact;
-        const int i = L.first + d - 1;
-        double Rp[12];
-        double bs[3] = {0, 0, 0};             // B[k][r] of this lane (angular lanes), B = -E p^
-        if (act) {
-            ld12v(Xl + 12 * i, Rp);
-            double ic[6];
+    o[0] += Rp[10] * o[5] - Rp[11] * o[4];
+    o[1] += Rp[11] * o[3] - Rp[9] * o[5];
+    o[2] += Rp[9] * o[4] - Rp[10] * o[3];
+}
+// X' v for a column v = [v_ang; v_lin]: with u = E' v_lin, X' v = [E' v_ang + B' v_lin; u] and B' v_lin = p x u
+__device__ __forceinline__ void crba_XT_times_col(const double* Rp, const double* v, double* o) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {             // E[k][a] = Rp[3 a + k]
+        const double e0 = Rp[3 * a], e1 = Rp[3 * a + 1], e2 = Rp[3 * a + 2];
+        o[3 + a] = e0 * v[3] + e1 * v[4] + e2 * v[5];
+        o[a] = e0 * v[0] + e1 * v[1] + e2 * v[2];
+    }
+    o[0] += Rp[10] * o[5] - Rp[11] * o[4];
+    o[1] += Rp[11] * o[3] - Rp[9] * o[5];
+    o[2] += Rp[9] * o[4] - Rp[10] * o[3];
+}
+
+template <bool ROWS>
+__device__ __forceinline__ void crba_level(EnvWS& w, const double* Isp, const LaneRole& L, int d, double* icin, double* F) {
+    auto& S = w.u.m.p.wr;
+    const int c8 = 8 * L.c, r = L.r;
+    const bool act = L.on && d <= L.nact;
+    const int i = L.first + d - 1;
+    double* T = S.Ybuf + 36 * L.c;
+    double Rp[12];
+    if (act) {
+        ld12v(w.u.m.Xl + 12 * i, Rp);
+        double ic[6], t[6];
+        if (ROWS) {
             ld6v(Isp + 36 * i + 6 * r, ic);
 #pragma unroll
             for (int k = 0; k < 6; ++k) ic[k] += icin[k];
-            S.col2[c8 + r] = ic[2];
-            double y[6];
+            S.col2[c8 + r] = ic[2];                              // Ic S, S = e_z (angular): column 2, one entry per lane
+            crba_row_times_X(Rp, ic, t);
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                // E[k][cc] = R[cc][k] = Rp[3*cc + k]
-                const double e0 = Rp[3 * cc], e1 = Rp[3 * cc + 1], e2 = Rp[3 * cc + 2];
-                y[3 + cc] = ic[3] * e0 + ic[4] * e1 + ic[5] * e2;
-                y[cc] = ic[0] * e0 + ic[1] * e1 + ic[2] * e2;
+            for (int k = 0; k < 6; ++k) T[6 * r + k] = t[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ic[k] = Isp[36 * i + 6 * k + r] + icin[k];
+            if (r == 2) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) S.col2[c8 + k] = ic[k];   // the lane of column 2 has all of Ic S
             }
-            // + ic[3:6] . B[:, cc],  (E p^)[k][:] = (E[k][1] p2 - E[k][2] p1, -E[k][0] p2 + E[k][2] p0, E[k][0] p1 - E[k][1] p0)
+            crba_XT_times_col(Rp, ic, t);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double ek0 = Rp[k], ek1 = Rp[3 + k], ek2 = Rp[6 + k];     // E[k][0..2]
-                const double b0 = -(ek1 * Rp[11] - ek2 * Rp[10]);
-                const double b1 = -(-ek0 * Rp[11] + ek2 * Rp[9]);
-                const double b2 = -(ek0 * Rp[10] - ek1 * Rp[9]);
-                y[0] += ic[3 + k] * b0; y[1] += ic[3 + k] * b1; y[2] += ic[3 + k] * b2;
-                bs[k] = dsel(lin, 0.0, dsel3(r, b0, b1, b2));
-            }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) S.Ybuf[36 * L.c + 6 * r + k] = y[k];
-            if (r == 2) w.Hc[36 * L.c + 7 * (d - 1)] = ic[2];
+            for (int k = 0; k < 6; ++k) T[6 * k + r] = t[k];
         }
-        __syncwarp();
-        if (act) {
-            // this lane's joint: pick up the new vector at its own depth, then cross frame i towards the root
-            if (r == d - 1) ld6v(S.col2 + c8, F);
-            if (r >= d - 1 && r < L.nact) {
-                double o[6];
-                xf_all(Rp, F, o);
+        if (r == 2) w.Hc[36 * L.c + 7 * (d - 1)] = ic[2];
+    }
+    __syncwarp();
+    if (act) {
+        // this lane's joint: pick up the new vector at its own depth, then cross frame i towards the root
+        if (r == d - 1) ld6v(S.col2 + c8, F);
+        if (r >= d - 1 && r < L.nact) {
+            double o[6];
+            xf_all(Rp, F, o);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) F[k] = o[k];
-                if (d > 1) {
-                    w.Hc[36 * L.c + 6 * (d - 2) + r] = F[2];
-                    w.Hc[36 * L.c + 6 * r + (d - 2)] = F[2];
-                } else {
+            for (int k = 0; k < 6; ++k) F[k] = o[k];
+            if (d > 1) {
+                w.Hc[36 * L.c + 6 * (d - 2) + r] = F[2];
+                w.Hc[36 * L.c + 6 * r + (d - 2)] = F[2];
+            } else {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) w.M6[NQ * k + 6 + L.j0 + r] = F[k];
-                }
+                for (int k = 0; k < 6; ++k) w.M6[NQ * k + 6 + L.j0 + r] = F[k];
             }
-            // row r of X' Y : sum_k X[k][r] Y[k][:].  X[k][r] = E[k][r] (r < 3, rows 0..2 of Y), X[3+k][r] = B[k][r]
-            // (r < 3) or E[k][r-3] (r >= 3), rows 3..5 of Y: E[k][k3] = R[k3][k] is one lane-dependent row of R
-            const double* Xr = Xl + 12 * i + 3 * k3;
-            const double x0 = Xr[0], x1 = Xr[1], x2 = Xr[2];
-            const double* Yc = S.Ybuf + 36 * L.c;
-            const double* Yo = Yc + (lin ? 18 : 0);
-            double out[6];
+        }
+        double t[6];
+        if (ROWS) {
 #pragma unroll
-            for (int cc = 0; cc < 6; cc += 2) {
-                const double2 a = *reinterpret_cast<const double2*>(Yo + cc), b = *reinterpret_cast<const double2*>(Yo + 6 + cc),
-                              c = *reinterpret_cast<const double2*>(Yo + 12 + cc);
-                out[cc] = x0 * a.x + x1 * b.x + x2 * c.x;
-                out[cc + 1] = x0 * a.y + x1 * b.y + x2 * c.y;
-            }
-            {           // bs = 0 on the linear lanes: same instructions for the whole warp, no divergent region
-#pragma unroll
-                for (int cc = 0; cc < 6; cc += 2) {
-                    const double2 a = *reinterpret_cast<const double2*>(Yc + 18 + cc), b = *reinterpret_cast<const double2*>(Yc + 24 + cc),
-                                  c = *reinterpret_cast<const double2*>(Yc + 30 + cc);
-                    out[cc] += bs[0] * a.x + bs[1] * b.x + bs[2] * c.x;
-                    out[cc + 1] += bs[0] * a.y + bs[1] * b.y + bs[2] * c.y;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) icin[k] = out[k];
+            for (int k = 0; k < 6; ++k) t[k] = T[6 * k + r];      // column r of Y
+            crba_XT_times_col(Rp, t, icin);                    // column r of Ic'
+        } else {
+            ld6v(T + 6 * r, t);                                   // row r of Z
+            crba_row_times_X(Rp, t, icin);                     // row r of Ic'
             if (d == 1) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) S.Ybuf2[36 * L.c + 6 * r + k] = out[k];
+                for (int k = 0; k < 6; ++k) S.Ybuf2[36 * L.c + 6 * r + k] = icin[k];
             }
         }
-        __syncwarp();
+    }
+    __syncwarp();
+}
+
+__device__ void crba_warp(EnvWS& w, const Consts& K, const double* Isp, const LaneRole& L, int lane) {
+    auto& S = w.u.m.p.wr;
+    double icin[6] = {0, 0, 0, 0, 0, 0};     // row / column r of the composite inertia arriving from the level below
+    double F[6] = {0, 0, 0, 0, 0, 0};        // force vector of joint (c, r), expressed in the frame reached so far
+    if (lane < 30) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w.Hc[36 * L.c + 6 * L.r + k] = 0.0;
+    }
+#pragma unroll 1
+    for (int d = MAXDEPTH - 1; d >= 2; d -= 2) {
+        crba_level<true>(w, Isp, L, d, icin, F);
+        crba_level<false>(w, Isp, L, d - 1, icin, F);
     }
     if (lane < 6) {       // Ic0 = I0 + sum over the five chains
 #pragma unroll
@@ -404,8 +420,6 @@ __device__ void crba_warp(EnvWS& w, const Consts& K, const double* Isp, const La
     }
     __syncwarp();
 }
-
-
 
 // ---- sole Jacobians (invKinematics.cpp:72-149), one column per lane: lane = 12*foot + col, col 0..5 the base twist
 // block (sole_X_base e_col), col 6+l the joint l of that leg (sole_X_(joint frame) S).  A column is a unit vector
