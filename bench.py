@@ -43,8 +43,8 @@ FLOP_PER_ENV_STEP = 0.51e6          # SURVEY.md 8(d) / App. C, active-set change
 STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 48 + 24   # state read+write, stats, CoM per launch
 # dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel from the committed ncu --set full capture (E = 4096;
 # the traffic of a launch does not depend on the number of steps it fuses: the state stays on chip)
-NCU_DRAM_BYTES_PER_LAUNCH = 3336192 + 0
-NCU_TRAFFIC_SOURCE = ("profiles/r01_rollout_v15_settled.txt: dram read 3.34 MB + write 0 MB for a 10-step launch of "
+NCU_DRAM_BYTES_PER_LAUNCH = 3339264 + 13568
+NCU_TRAFFIC_SOURCE = ("profiles/r01_rollout_v16_settled.txt: dram read 3.34 MB + write 0.01 MB for a 10-step launch of "
                       "4096 envs (algorithmic: 6.3 MB of state and statistics per launch, independent of the step count; the "
                       "written state was still in the 126 MB L2 when the kernel ended)")
 
