@@ -45,6 +45,10 @@ typedef struct {
     int32_t threads_per_env;      /* 32, 64 or 128; 0 = default */
     int32_t device;        /* CUDA device ordinal */
     int32_t log_steps;     /* capacity of the per-step log (0 = no log) */
+    int32_t envs_per_block;/* one-warp environments per thread block of the fused rollout (threads_per_env = 32 only):
+                              0 = as many as the shared memory holds (the default), else 1..that many */
+    int32_t placement;     /* 0 = lmh_set_pushes places environments that are pushed at the same step in the same
+                              block (default; results do not depend on it), 1 = keep the index order */
 } LmhConfig;
 
 /* Everything one dynamics() evaluation (apps/offline/main.cpp:91-122) produces, row-major. */
@@ -70,16 +74,31 @@ typedef struct {
     double tau_k1[24];         /* torques of the k1 stage */
     int32_t k_index[4];
     int32_t qp_iters, qp_fail;
+    int32_t phase[4];          /* walking extension: phase index of each of the four stages (0 in the stand task) */
+    int32_t contact[4];        /* contact mask of each stage: bit 0 right foot, bit 1 left foot (3 in the stand task) */
 } LmhStepLog;
+
+/* EXTENSION (the reference has no notion of falling): the health rule of a closed-loop step.  A step is COMMITTED
+ * (state, clock, statistics) only if, with x+ the state the RK4 combination would produce,
+ *   max|tau(k1)| < LMH_TAU_LIMIT,  |CoM_xy(k4) - zmp_ref(k_index(k4))| < LMH_COM_ERR_LIMIT,
+ *   every |x+_i| < LMH_STATE_LIMIT (NaN fails),  x+[2] (torso height) > LMH_TORSO_MIN.
+ * Otherwise the environment is FALLEN: state and clock keep the values of the last healthy step, its statistics are
+ * closed (they never see the failing step), alive = 0, and nothing more is evaluated for it: one bad environment
+ * never takes the batch down and never pollutes the per-environment statistics. */
+#define LMH_TAU_LIMIT 100.0
+#define LMH_COM_ERR_LIMIT 0.5
+#define LMH_STATE_LIMIT 1e6
+#define LMH_TORSO_MIN 0.15
 
 /* Per-environment rollout statistics (lmh_get_stats): */
 typedef struct {
-    double max_abs_tau;        /* over k1 stages */
-    double max_com_err;        /* max |CoM_xy(k4) - zmp_ref_xy| */
+    double max_abs_tau;        /* over the k1 stages of the committed steps */
+    double max_com_err;        /* max |CoM_xy(k4) - zmp_ref_xy| over the committed steps */
     double max_abs_qpp;
-    int32_t qp_iters, qp_fail; /* totals over all stages */
-    int32_t steps, alive;      /* steps run; alive = state still finite and torso above 0.15 m */
-    int32_t qp_fallback;       /* stages that needed the c-space fallback of the QP (rank-deficient contact set) */
+    int32_t qp_iters, qp_fail; /* totals over all stages of the committed steps */
+    int32_t steps, alive;      /* steps committed; alive = 0 once a step failed the health rule above */
+    int32_t qp_fallback;       /* stages whose all-free QP solution was infeasible (contact-limited: the general
+                                  active-set iteration ran) */
     int32_t pad;
 } LmhStats;
 
@@ -115,7 +134,10 @@ int32_t lmh_get_plan(const LmhBatch* h, int32_t plan, double* zmp_x, double* zmp
 
 /* State: x [n_env][60] = [q; v]; v_held [n_env][30] = velocity the Robot object still holds from the
  * previous stage evaluation (Robot::v_, refreshed late in Controller::standStep, controller.cpp:48-79);
- * t [n_env].  NULL leaves a field unchanged (set) or unread (get). */
+ * t [n_env].  NULL leaves a field unchanged (set) or unread (get).  lmh_set_state only ENQUEUES the copies on the
+ * handle's stream (so that pinned host buffers overlap with earlier work): the caller's buffers must stay valid and
+ * unmodified until the next lmh_sync or any lmh_get_* call, all of which synchronise.  lmh_get_state returns after
+ * the data has arrived. */
 int32_t lmh_set_state(LmhBatch* h, const double* x, const double* v_held, const double* t);
 int32_t lmh_get_state(LmhBatch* h, double* x, double* v_held, double* t);
 int32_t lmh_reset(LmhBatch* h);

@@ -22,7 +22,7 @@ class LmhError(RuntimeError):
 class LmhConfig(C.Structure):
     _fields_ = [("dt", _f64), ("sim_time", _f64), ("time_horizon", _f64), ("com", _f64 * 3), ("rf", _f64 * 6),
                 ("lf", _f64 * 6), ("mu", _f64), ("mpc_alpha", _f64), ("mpc_beta", _f64), ("qp_max_iter", _i32),
-                ("threads_per_env", _i32), ("device", _i32), ("log_steps", _i32)]
+                ("threads_per_env", _i32), ("device", _i32), ("log_steps", _i32), ("envs_per_block", _i32), ("placement", _i32)]
 
 
 STAGE_DTYPE = np.dtype([("M", "f8", (30, 30)), ("C", "f8", 30), ("Cg", "f8", 30), ("AG", "f8", (6, 30)),
@@ -33,9 +33,13 @@ STAGE_DTYPE = np.dtype([("M", "f8", (30, 30)), ("C", "f8", 30), ("Cg", "f8", 30)
                         ("qpp", "f8", 30), ("tau", "f8", 24), ("T7", "f8", 12), ("T14", "f8", 12), ("xdot", "f8", 60),
                         ("k_index", "i4"), ("qp_status", "i4"), ("qp_iters", "i4"), ("phase", "i4")])
 STEPLOG_DTYPE = np.dtype([("com_k4", "f8", 3), ("rfoot", "f8", 3), ("lfoot", "f8", 3), ("tau_k1", "f8", 24),
-                          ("k_index", "i4", 4), ("qp_iters", "i4"), ("qp_fail", "i4")])
+                          ("k_index", "i4", 4), ("qp_iters", "i4"), ("qp_fail", "i4"), ("phase", "i4", 4),
+                          ("contact", "i4", 4)])
 STATS_DTYPE = np.dtype([("max_abs_tau", "f8"), ("max_com_err", "f8"), ("max_abs_qpp", "f8"), ("qp_iters", "i4"),
                         ("qp_fail", "i4"), ("steps", "i4"), ("alive", "i4"), ("qp_fallback", "i4"), ("pad", "i4")])
+
+# health rule of a closed-loop step (include/lmh_capi.h: LMH_TAU_LIMIT, LMH_COM_ERR_LIMIT, LMH_STATE_LIMIT, LMH_TORSO_MIN)
+TAU_LIMIT, COM_ERR_LIMIT, STATE_LIMIT, TORSO_MIN = 100.0, 0.5, 1e6, 0.15
 
 # every symbol include/lmh_capi.h declares (checked by the CPU test-suite against the built library)
 SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", "lmh_n_env", "lmh_get_nominal",
@@ -144,11 +148,12 @@ class Batch:
     Mirrors what apps/offline/main.cpp builds (Robot + IK + Mpc3dLip + ZMP + foot polynomials +
     Controller) and what its stand() loop does (rk4Step + Clock::step), for a whole batch."""
 
-    def __init__(self, n_env, device=0, threads_per_env=0, log_steps=0, **scenario):
+    def __init__(self, n_env, device=0, threads_per_env=0, log_steps=0, envs_per_block=0, placement=0, **scenario):
         self.L = L = load_library()
         cfg = LmhConfig()
         L.lmh_default_config(C.byref(cfg))
         cfg.device, cfg.threads_per_env, cfg.log_steps = device, threads_per_env, log_steps
+        cfg.envs_per_block, cfg.placement = envs_per_block, placement
         for k, v in scenario.items():
             if not hasattr(cfg, k):
                 raise LmhError(f"unknown scenario field {k}")
@@ -202,6 +207,8 @@ class Batch:
         zy = np.ascontiguousarray(np.atleast_2d(zmp_y), np.float64)
         fc = np.ascontiguousarray(foot_coef, np.float64).reshape(zx.shape[0], 40)
         ids = None if plan_ids is None else np.ascontiguousarray(plan_ids, np.int32)
+        if zy.shape != zx.shape or (ids is not None and ids.size != self.n_env):
+            raise LmhError("set_plans: zmp_x / zmp_y shapes differ or plan_ids is not one id per environment")
         _chk(self.L, self.L.lmh_set_plans(self.h, zx.shape[0], zx.shape[1], _p(zx), _p(zy), _p(fc), _p(ids)))
 
     def set_walk_plans(self, zmp_x, zmp_y, phase_T, foot_coef, contact, plan_ids=None):
@@ -211,6 +218,8 @@ class Batch:
         ct = np.ascontiguousarray(contact, np.int32).reshape(zx.shape[0], -1)
         fc = np.ascontiguousarray(foot_coef, np.float64).reshape(zx.shape[0], ct.shape[1], 40)
         ids = None if plan_ids is None else np.ascontiguousarray(plan_ids, np.int32)
+        if zy.shape != zx.shape or (ids is not None and ids.size != self.n_env):
+            raise LmhError("set_walk_plans: zmp_x / zmp_y shapes differ or plan_ids is not one id per environment")
         _chk(self.L, self.L.lmh_set_walk_plans(self.h, zx.shape[0], zx.shape[1], _p(zx), _p(zy), ct.shape[1], float(phase_T),
                                                _p(fc), _p(ct), _p(ids)))
 
@@ -234,6 +243,8 @@ class Batch:
     def set_pushes(self, push_step, push_dv6):
         ps = None if push_step is None else np.ascontiguousarray(push_step, np.int32)
         dv = None if push_dv6 is None else np.ascontiguousarray(push_dv6, np.float64)
+        if (ps is not None and ps.size != self.n_env) or (dv is not None and dv.size != 6 * self.n_env):
+            raise LmhError("set_pushes: need n_env push steps and n_env x 6 impulses")
         _chk(self.L, self.L.lmh_set_pushes(self.h, _p(ps), _p(dv)))
 
     def set_step_counter(self, step):

@@ -49,6 +49,7 @@ struct Params {
 constexpr int kExtraDoubles = 2 * 60;   // x and the RK4 accumulator
 constexpr int kTabDh = 28 * 36, kTabMpc = kTabDh + 120;     // block-shared constant tables: Isp | DH parameters | mpc_r
 constexpr int kMaxDynSmem = 227 * 1024;
+constexpr int kMaxEpb = 10;              // one-warp environments per block of rollout_kernel_multi (its launch bound)
 static_assert(offsetof(Consts, dh_d) == offsetof(Consts, th_off) + 4 * 24 * sizeof(double), "th_off..dh_d must be contiguous");
 
 template <int NT>
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {
         const int gstep = p.step0 + s;
-        if (gstep == push_at) {
+        if (gstep == push_at && w.dead == 0) {
             for (int k = threadIdx.x; k < 6; k += NT) x[30 + k] += p.push_dv[(size_t)env * 6 + k];
             cx.sync();
         }
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
 
 // One warp per environment, EPB environments per block (warp w of block b owns environment b*EPB + w and its own
 // slice of shared memory); the warps of a block are re-aligned at every stage so that they share instruction fetches.
-__global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb, int env_bytes, int tab_doubles, int n_full) {
+__global__ void __launch_bounds__(32 * kMaxEpb, 1) rollout_kernel_multi(Params p, int epb, int env_bytes, int tab_doubles, int n_full) {
     extern __shared__ double smem[];
     // the warp index through a broadcast: the compiler then knows it is warp-uniform and keeps the workspace base in
     // a uniform register
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(320, 1) rollout_kernel_multi(Params p, int epb
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {
         const int gstep = p.step0 + s;
-        if (gstep == push_at) {
+        if (gstep == push_at && w.dead == 0) {
             for (int k = lane; k < 6; k += 32) x[30 + k] += p.push_dv[(size_t)env * 6 + k];
             cx.sync();
         }
@@ -282,7 +283,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 struct LmhBatch {
     LmhConfig cfg;
     HostModel* hm = nullptr;
-    int32_t n_env = 0, nt = 64, smem = 0, epb = 10, tab_doubles = 0, sm_count = 148, plain_grid = 0;
+    int32_t n_env = 0, nt = 64, smem = 0, epb = 10, tab_doubles = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
@@ -300,6 +301,9 @@ struct LmhBatch {
     std::vector<double> h_zmp_x, h_zmp_y, h_foot;
     std::vector<int32_t> h_contact;
     bool has_pushes = false, has_plan_ids = false, has_order = false;
+    // scratch of lmh_ik_batch / lmh_qp_bench, kept between calls (grown on demand)
+    double* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 namespace {
@@ -340,12 +344,20 @@ int32_t upload_plans(LmhBatch* h) {
     return LMH_OK;
 }
 
+int32_t ensure_scratch(LmhBatch* h, size_t bytes) {
+    if (bytes <= h->scratch_bytes) return LMH_OK;
+    if (h->d_scratch) { cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_bytes = 0; }
+    CU(cudaMalloc(&h->d_scratch, bytes));
+    h->scratch_bytes = bytes;
+    return LMH_OK;
+}
+
 // Grid of the one-block-per-SM kernel: whole waves of full blocks, then the rest spread evenly over up to sm_count blocks.
 int multi_grid(const LmhBatch* h, int* n_full_out) {
     const int cap = h->sm_count * h->epb;
-    int n_full = h->plain_grid ? h->n_env / h->epb : ((h->n_env + cap - 1) / cap - 1) * h->sm_count;
+    int n_full = ((h->n_env + cap - 1) / cap - 1) * h->sm_count;
     const int rest = h->n_env - n_full * h->epb;
-    const int tail = h->plain_grid ? (rest > 0 ? 1 : 0) : std::min(rest, h->sm_count);
+    const int tail = std::min(rest, h->sm_count);
     if (n_full_out) *n_full_out = n_full;
     return n_full + tail;
 }
@@ -382,7 +394,51 @@ void lmh_default_config(LmhConfig* c) {
     for (int k = 0; k < 6; ++k) { c->rf[k] = s.rf[k]; c->lf[k] = s.lf[k]; }
     c->mu = s.mu; c->mpc_alpha = s.mpc_alpha; c->mpc_beta = s.mpc_beta;
     c->qp_max_iter = s.qp_max_iter;
-    c->threads_per_env = 0; c->device = 0; c->log_steps = 0;
+    c->threads_per_env = 0; c->device = 0; c->log_steps = 0; c->envs_per_block = 0; c->placement = 0;
+}
+
+// everything of lmh_create that can fail after the handle exists: the caller destroys the handle on any error
+static int32_t create_on_device(LmhBatch* h, const LmhConfig* cfg, int32_t n_env) {
+    h->smem = (int32_t)(((sizeof(EnvWS) + 7) / 8 + kExtraDoubles) * sizeof(double));
+    h->smem = (h->smem + 15) / 16 * 16;
+    CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    const int epb_max = std::min(kMaxEpb, (kMaxDynSmem - kTabMpc * 8) / h->smem);
+    h->epb = cfg->envs_per_block > 0 ? cfg->envs_per_block : epb_max;
+    if (h->nt != 32) h->epb = 1;
+    if (h->epb > epb_max) return fail(LMH_EINVAL, "lmh_create: envs_per_block exceeds what the shared memory holds");
+    if (h->epb > 1) {
+        // block-shared constant tables behind the slices, as far as the 227 KB allow: Isp + DH (9 KB), then the MPC gains
+        const int64_t slices = (int64_t)h->smem * h->epb;
+        const int n1 = h->hm->K.mpc_n1;
+        h->tab_doubles = slices + (int64_t)(kTabMpc + n1) * 8 <= kMaxDynSmem ? kTabMpc + n1 : kTabMpc;
+        // the attribute belongs to the (process-wide) kernel, not to this handle: always ask for the maximum, so that
+        // handles with different horizons (= different table sizes) can be live together
+        CU(cudaFuncSetAttribute(rollout_kernel_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    }
+    int32_t rc = h->nt == 32 ? configure_kernels<32>(h->smem) : h->nt == 64 ? configure_kernels<64>(h->smem) : configure_kernels<128>(h->smem);
+    if (rc != LMH_OK) return rc;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+    size_t E = (size_t)n_env;
+    CU(cudaMalloc(&h->dK, sizeof(Consts)));
+    CU(cudaMemcpy(h->dK, &h->hm->K, sizeof(Consts), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->d_x, E * 60 * sizeof(double))); CU(cudaMalloc(&h->d_vh, E * 30 * sizeof(double)));
+    CU(cudaMalloc(&h->d_t, E * sizeof(double))); CU(cudaMalloc(&h->d_push_dv, E * 6 * sizeof(double)));
+    CU(cudaMalloc(&h->d_com, E * 3 * sizeof(double)));
+    CU(cudaMalloc(&h->d_plan_id, E * sizeof(int32_t))); CU(cudaMalloc(&h->d_push_step, E * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_stats, E * sizeof(LmhStats)));
+    CU(cudaMalloc(&h->d_dump, E * sizeof(LmhStageDump)));
+    if (cfg->log_steps > 0) {
+        CU(cudaMalloc(&h->d_log, (size_t)cfg->log_steps * E * sizeof(LmhStepLog)));
+        CU(cudaMemset(h->d_log, 0, (size_t)cfg->log_steps * E * sizeof(LmhStepLog)));
+    }
+    h->n_plans = 1;
+    h->zmp_len = (int32_t)h->hm->zmp_x.size();
+    h->h_zmp_x = h->hm->zmp_x; h->h_zmp_y = h->hm->zmp_y; h->h_foot = h->hm->foot_coef;
+    h->h_contact.assign(1, 3);
+    rc = upload_plans(h);
+    if (rc != LMH_OK) return rc;
+    return lmh_reset(h);
 }
 
 int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
@@ -393,12 +449,15 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     if (e != cudaSuccess || ndev <= 0)
         return fail(LMH_ENODEVICE, std::string("lmh_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(LMH_EINVAL, "lmh_create: device ordinal out of range");
+    const int nt = cfg->threads_per_env == 0 ? 32 : cfg->threads_per_env;
+    if (nt != 32 && nt != 64 && nt != 128) return fail(LMH_EINVAL, "lmh_create: threads_per_env must be 32, 64 or 128");
+    if (cfg->envs_per_block < 0 || cfg->placement < 0 || cfg->placement > 1 || cfg->log_steps < 0)
+        return fail(LMH_EINVAL, "lmh_create: envs_per_block / placement / log_steps out of range");
     CU(cudaSetDevice(cfg->device));
     LmhBatch* h = new LmhBatch;
     h->cfg = *cfg;
     h->n_env = n_env;
-    h->nt = cfg->threads_per_env == 0 ? 32 : cfg->threads_per_env;
-    if (h->nt != 32 && h->nt != 64 && h->nt != 128) { delete h; return fail(LMH_EINVAL, "lmh_create: threads_per_env must be 32, 64 or 128"); }
+    h->nt = nt;
     try {
         Scenario s;
         s.dt = cfg->dt; s.sim_time = cfg->sim_time; s.time_horizon = cfg->time_horizon;
@@ -411,45 +470,15 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
         delete h;
         return fail(LMH_EINVAL, std::string("lmh_create: setup failed: ") + ex.what());
     }
-    h->smem = (int32_t)(((sizeof(EnvWS) + 7) / 8 + kExtraDoubles) * sizeof(double));
-    if (const char* extra = std::getenv("LMH_EXTRA_SMEM")) h->smem += std::atoi(extra);   // occupancy experiments only
-    h->smem = (h->smem + 15) / 16 * 16;
-    if (const char* e2 = std::getenv("LMH_EPB")) h->epb = std::atoi(e2);
-    if (const char* e3 = std::getenv("LMH_PLAIN_GRID")) h->plain_grid = std::atoi(e3);     // experiments only
-    CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
-    if (h->nt != 32 || h->epb < 1) h->epb = 1;
-    if (h->epb > 10) h->epb = 10;
-    if (h->epb > 1) {
-        // block-shared constant tables behind the slices, as far as the 227 KB allow: Isp + DH (9 KB), then the MPC gains
-        const int64_t slices = (int64_t)h->smem * h->epb;
-        const int n1 = h->hm->K.mpc_n1;
-        if (slices + (int64_t)(kTabMpc + n1) * 8 <= kMaxDynSmem) h->tab_doubles = kTabMpc + n1;
-        else if (slices + (int64_t)kTabMpc * 8 <= kMaxDynSmem) h->tab_doubles = kTabMpc;
-        if (std::getenv("LMH_NO_TABLES")) h->tab_doubles = 0;
-        CU(cudaFuncSetAttribute(rollout_kernel_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(slices + (int64_t)h->tab_doubles * 8)));
+    const int32_t rc = create_on_device(h, cfg, n_env);
+    if (rc != LMH_OK) {
+        const std::string msg = g_err;      // lmh_destroy must not lose the message
+        lmh_destroy(h);
+        g_err = msg;
+        return rc;
     }
-    int32_t rc = h->nt == 32 ? configure_kernels<32>(h->smem) : h->nt == 64 ? configure_kernels<64>(h->smem) : configure_kernels<128>(h->smem);
-    if (rc != LMH_OK) { delete h->hm; delete h; return rc; }
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
-    size_t E = (size_t)n_env;
-    CU(cudaMalloc(&h->dK, sizeof(Consts)));
-    CU(cudaMemcpy(h->dK, &h->hm->K, sizeof(Consts), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&h->d_x, E * 60 * sizeof(double))); CU(cudaMalloc(&h->d_vh, E * 30 * sizeof(double)));
-    CU(cudaMalloc(&h->d_t, E * sizeof(double))); CU(cudaMalloc(&h->d_push_dv, E * 6 * sizeof(double)));
-    CU(cudaMalloc(&h->d_com, E * 3 * sizeof(double)));
-    CU(cudaMalloc(&h->d_plan_id, E * sizeof(int32_t))); CU(cudaMalloc(&h->d_push_step, E * sizeof(int32_t)));
-    CU(cudaMalloc(&h->d_stats, E * sizeof(LmhStats)));
-    CU(cudaMalloc(&h->d_dump, E * sizeof(LmhStageDump)));
-    if (cfg->log_steps > 0) CU(cudaMalloc(&h->d_log, (size_t)cfg->log_steps * E * sizeof(LmhStepLog)));
-    h->n_plans = 1;
-    h->zmp_len = (int32_t)h->hm->zmp_x.size();
-    h->h_zmp_x = h->hm->zmp_x; h->h_zmp_y = h->hm->zmp_y; h->h_foot = h->hm->foot_coef;
-    h->h_contact.assign(1, 3);
-    rc = upload_plans(h);
-    if (rc != LMH_OK) return rc;
     *out = h;
-    return lmh_reset(h);
+    return LMH_OK;
 }
 
 void lmh_destroy(LmhBatch* h) {
@@ -458,7 +487,7 @@ void lmh_destroy(LmhBatch* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
     cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_order); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
-    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact);
+    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact); cudaFree(h->d_scratch);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -587,7 +616,7 @@ int32_t lmh_set_pushes(LmhBatch* h, const int32_t* push_step, const double* push
     CU(cudaSetDevice(h->cfg.device));
     h->has_pushes = push_step != nullptr && push_dv6 != nullptr;
     h->has_order = false;
-    if (h->has_pushes && !std::getenv("LMH_NO_ORDER")) {
+    if (h->has_pushes && h->cfg.placement == 0) {
         // placement only (every environment computes exactly what it would anywhere else): slots sorted by push step,
         // larger impulses first within a step
         std::vector<int32_t> order((size_t)h->n_env);
@@ -746,8 +775,9 @@ int32_t lmh_timer_stop(LmhBatch* h, double* ms) {
 int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out, double* elapsed_ms) {
     if (!h || repeats <= 0 || mode < 0 || mode > 1) return fail(LMH_EINVAL, "lmh_qp_bench: bad arguments");
     CU(cudaSetDevice(h->cfg.device));
-    double* d_out = nullptr;
-    CU(cudaMalloc(&d_out, (size_t)h->n_env * 42 * sizeof(double)));
+    int32_t rc = ensure_scratch(h, (size_t)h->n_env * 42 * sizeof(double));
+    if (rc != LMH_OK) return rc;
+    double* d_out = h->d_scratch;
     Params p = make_params(h);
     dim3 grid(h->n_env), block(h->nt);
     CU(cudaFuncSetAttribute(qp_bench_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
@@ -764,7 +794,6 @@ int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out
     CU(cudaEventElapsedTime(&f, h->ev0, h->ev1));
     if (elapsed_ms) *elapsed_ms = f;
     if (a_f_out) CU(cudaMemcpy(a_f_out, d_out, (size_t)h->n_env * 42 * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_out);
     h->launches += 1;
     return LMH_OK;
 }
@@ -775,13 +804,11 @@ int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* r
     if (apply_to_state && n != h->n_env) return fail(LMH_EINVAL, "lmh_ik_batch: apply_to_state needs one target per environment");
     CU(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)n;
-    double *d_in = nullptr, *d_q = nullptr, *d_res = nullptr, *d_q0 = nullptr;
-    int32_t* d_int = nullptr;
-    CU(cudaMalloc(&d_in, N * 15 * sizeof(double)));
-    CU(cudaMalloc(&d_q, N * NQ * sizeof(double)));
-    CU(cudaMalloc(&d_res, N * sizeof(double)));
-    CU(cudaMalloc(&d_int, N * 2 * sizeof(int32_t)));
-    CU(cudaMalloc(&d_q0, NQ * sizeof(double)));
+    // one scratch block, kept in the handle: inputs (15 N), postures (30 N), residuals (N), start posture (30), integers (2 N)
+    int32_t rc0 = ensure_scratch(h, (N * 47 + NQ) * sizeof(double) + N * 2 * sizeof(int32_t));
+    if (rc0 != LMH_OK) return rc0;
+    double *d_in = h->d_scratch, *d_q = d_in + N * 15, *d_res = d_q + N * NQ, *d_q0 = d_res + N;
+    int32_t* d_int = reinterpret_cast<int32_t*>(d_q0 + NQ);
     CU(cudaMemcpyAsync(d_in, com3, N * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_in + N * 3, rf6, N * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_in + N * 9, lf6, N * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -801,7 +828,6 @@ int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* r
     if (status) CU(cudaMemcpyAsync(status, d_int + N, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (residual) CU(cudaMemcpyAsync(residual, d_res, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(d_in); cudaFree(d_q); cudaFree(d_res); cudaFree(d_int); cudaFree(d_q0);
     if (apply_to_state) {
         std::vector<LmhStats> st(N);
         std::memset(st.data(), 0, N * sizeof(LmhStats));

@@ -1659,11 +1659,19 @@ LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, 
     cx.sync();
 }
 
-// Running statistics of one environment (kept by thread 0 of the group).
+// Running statistics of one environment (every thread of the group holds the same copy).
 struct StatsAcc {
     double max_tau, max_err, max_qpp;
     int32_t qp_iters, qp_fail, steps, alive, qp_fallback;
 };
+
+// EXTENSION (the reference has no notion of falling): the health rule of a closed-loop step (the checker restates it
+// independently).  A step is COMMITTED -- state, clock, statistics -- only if, with x+ the state the RK4
+// combination would produce,
+//     max|tau(k1)| < LMH_TAU_LIMIT,   |CoM_xy(k4) - zmp_ref(k_index(k4))| < LMH_COM_ERR_LIMIT,
+//     every |x+_i| < LMH_STATE_LIMIT (NaN fails),   x+[2] (torso height) > LMH_TORSO_MIN.
+// Otherwise the environment is FALLEN: state and clock keep the values of the last healthy step, the statistics are
+// closed (they never see the failing step), alive = 0, and no further stage is evaluated for it.
 
 // One RK4 step (rk4.hpp:5-18) + Clock::step (Clock.hpp:11).  x: [60] state in shared memory, kacc:
 // [60] scratch, t: the env clock (same value in every thread of the group).
@@ -1672,7 +1680,22 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
                       int plan_id, LmhStepLog* log, StatsAcc* st) {
     const double dt = K.dt;
     const double half = 0.5 * dt;
+    if (w.dead != 0) {
+        // a fallen environment evaluates nothing; it only keeps its appointments with the warps it shares a block with,
+        // and its log record repeats the last evaluated stage
+#if defined(__CUDA_ARCH__)
+        for (int stage = 0; stage < 4; ++stage) cx.align();
+#endif
+        if (log) {
+            LMH_FOR(i, 3) { log->com_k4[i] = w.com[i]; log->rfoot[i] = w.ps[0][i]; log->lfoot[i] = w.ps[1][i]; }
+            LMH_FOR(i, NJ) log->tau_k1[i] = 0.0;
+            LMH_FOR(i, 4) { log->k_index[i] = w.k_index; log->phase[i] = w.phase; log->contact[i] = w.contact; }
+            LMH_FOR(i, 1) { log->qp_iters = 0; log->qp_fail = 0; }
+        }
+        return;
+    }
     int iters = 0, fails = 0, nfall = 0;
+    double tau_inf = 0.0, qpp_inf = 0.0;
     for (int stage = 0; stage < 4; ++stage) {
         const double cstage = stage == 0 ? 0.0 : stage == 3 ? dt : half;
 #if defined(__CUDA_ARCH__)
@@ -1695,64 +1718,62 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         fails += w.qp_status != 0;
         nfall += w.qp_fallback;
         if (log) {
-            LMH_FOR(i, 1) log->k_index[stage] = w.k_index;
+            LMH_FOR(i, 1) { log->k_index[stage] = w.k_index; log->phase[stage] = w.phase; log->contact[stage] = w.contact; }
             if (stage == 0) { LMH_FOR(i, NJ) log->tau_k1[i] = w.tau[i]; }
         }
-        if (st && stage == 0 && w.dead == 0) {
+        if (stage == 0) {
 #if defined(__CUDA_ARCH__)
             if (Cx::NT == 32) {
                 const int i = cx.tid;
-                const double m = warp_max(i < NJ ? fabs(w.tau[i]) : 0.0), a = warp_max(i < NQ ? fabs(w.xdot[NQ + i]) : 0.0);
-                st->max_tau = fmax(st->max_tau, m); st->max_qpp = fmax(st->max_qpp, a);
+                // NaN-propagating maxima (fmax would drop a NaN torque): a non-finite torque must fail the health test
+                const double ti = i < NJ ? fabs(w.tau[i]) : 0.0, ai = i < NQ ? fabs(w.xdot[NQ + i]) : 0.0;
+                tau_inf = warp_max(ti == ti ? ti : 1e300); qpp_inf = warp_max(ai == ai ? ai : 1e300);
             } else
 #endif
             {
-            LMH_FOR(i, 1) {
-                double m = st->max_tau, a = st->max_qpp;
-                for (int j = 0; j < NJ; ++j) m = fmax(m, fabs(w.tau[j]));
-                for (int j = 0; j < NQ; ++j) a = fmax(a, fabs(w.xdot[NQ + j]));
-                st->max_tau = m; st->max_qpp = a;
-            }
+                for (int j = 0; j < NJ; ++j) { const double v = fabs(w.tau[j]); tau_inf = fmax(tau_inf, v == v ? v : 1e300); }
+                for (int j = 0; j < NQ; ++j) { const double v = fabs(w.xdot[NQ + j]); qpp_inf = fmax(qpp_inf, v == v ? v : 1e300); }
             }
         }
         cx.sync();
     }
     const double sixth = dt / 6.0;
-    const bool dead = w.dead != 0;        // a fallen environment keeps its last state: the batch goes on without it
-    if (!dead) { LMH_FOR(i, 2 * NQ) x[i] = mul_then_add(x[i], sixth, kacc[i]); }
-    t = t + dt;
+    LMH_FOR(i, 2 * NQ) kacc[i] = mul_then_add(x[i], sixth, kacc[i]);       // the candidate x+
+    cx.sync();
+    // health of the step: every thread reaches the same verdict
+    int k0 = w.k_index;
+    if (k0 < 0) k0 = 0;
+    if (k0 >= P.zmp_len) k0 = P.zmp_len - 1;
+    const double ex = w.com[0] - P.zmp_x[(size_t)plan_id * P.zmp_len + k0];
+    const double ey = w.com[1] - P.zmp_y[(size_t)plan_id * P.zmp_len + k0];
+    const double err = sqrt(ex * ex + ey * ey);
+    bool healthy = tau_inf < LMH_TAU_LIMIT && err < LMH_COM_ERR_LIMIT && kacc[2] > LMH_TORSO_MIN;
+#if defined(__CUDA_ARCH__)
+    if (Cx::NT == 32) {
+        const int i = cx.tid;
+        const bool bad = !(fabs(kacc[i]) < LMH_STATE_LIMIT) || (i < 28 && !(fabs(kacc[32 + i]) < LMH_STATE_LIMIT));
+        healthy = healthy && !__any_sync(0xffffffffu, bad);
+    } else
+#endif
+    {
+        for (int j = 0; j < 2 * NQ; ++j) healthy = healthy && (fabs(kacc[j]) < LMH_STATE_LIMIT);
+    }
+    if (healthy) {
+        LMH_FOR(i, 2 * NQ) x[i] = kacc[i];
+        t = t + dt;
+        if (st) {
+            st->max_tau = fmax(st->max_tau, tau_inf); st->max_qpp = fmax(st->max_qpp, qpp_inf); st->max_err = fmax(st->max_err, err);
+            st->qp_iters += iters; st->qp_fail += fails; st->steps += 1; st->qp_fallback += nfall;
+        }
+    } else {
+        if (st) st->alive = 0;
+    }
     if (log) {
         LMH_FOR(i, 3) { log->com_k4[i] = w.com[i]; log->rfoot[i] = w.ps[0][i]; log->lfoot[i] = w.ps[1][i]; }
         LMH_FOR(i, 1) { log->qp_iters = iters; log->qp_fail = fails; }
     }
-    if (st && !dead) {
-        LMH_FOR(i, 1) {
-            int k0 = w.k_index;
-            if (k0 < 0) k0 = 0;
-            if (k0 >= P.zmp_len) k0 = P.zmp_len - 1;
-            double ex = w.com[0] - P.zmp_x[(size_t)plan_id * P.zmp_len + k0];
-            double ey = w.com[1] - P.zmp_y[(size_t)plan_id * P.zmp_len + k0];
-            st->max_err = fmax(st->max_err, sqrt(ex * ex + ey * ey));
-            st->qp_iters += iters; st->qp_fail += fails; st->steps += 1; st->qp_fallback += nfall;
-        }
-    }
-    cx.sync();
-    if (st) {
-#if defined(__CUDA_ARCH__)
-        if (Cx::NT == 32) {
-            const int i = cx.tid;
-            const bool bad = !(fabs(x[i]) < 1e6) || (i < 28 && !(fabs(x[32 + i]) < 1e6)) || !(x[2] > 0.15);
-            if (__any_sync(0xffffffffu, bad)) { st->alive = 0; if (i == 0) w.dead = 1; }
-        } else
-#endif
-        {
-        LMH_FOR(i, 1) {
-            bool ok = x[2] > 0.15;
-            for (int j = 0; j < 2 * NQ; ++j) ok = ok && (fabs(x[j]) < 1e6);
-            if (!ok) { st->alive = 0; w.dead = 1; }
-        }
-        }
-    }
+    cx.sync();                        // nobody reads kacc / w.dead of this step any more
+    if (!healthy) { LMH_FOR(i, 1) w.dead = 1; }
     cx.sync();
 }
 

@@ -21,6 +21,11 @@ struct Sim {
     double t = 0;
     int ik_iters = 0;
     Vec<60> state0;
+    // health rule (EXTENSION, see orc_capi.h): closed statistics of the committed steps
+    bool alive = true;
+    int steps_done = 0;
+    double max_tau = 0, max_err = 0, max_qpp = 0;
+    long it_total = 0, fail_total = 0;
 
     explicit Sim(const OrcConfig& c) : cfg(c) {
         // apps/offline/main.cpp:16-58, same order
@@ -45,6 +50,7 @@ struct Sim {
         t = 0;
         nao.v = Vec<30>();  // a freshly constructed Robot holds zero velocity
         ctrl->qp_solves = ctrl->qp_iterations = ctrl->qp_failures = 0;
+        alive = true; steps_done = 0; max_tau = max_err = max_qpp = 0; it_total = fail_total = 0;
     }
     void fill_dump(const Vec<60>& xdot, OrcStageDump* o) {
         Controller& c = *ctrl;
@@ -76,34 +82,64 @@ struct Sim {
         o->qp_iters = c.qpInfo.iterations;
         o->pad = 0;
     }
-    // one RK4 step with the bookkeeping the logs need (rk4.hpp:12-17 inlined)
+    // one RK4 step with the bookkeeping the logs need (rk4.hpp:12-17 inlined) and the health rule of orc_capi.h
     void step(OrcStepLog* log) {
+        if (!alive) {   // fallen: nothing is evaluated any more; the record repeats the last evaluated stage
+            if (log) fill_log(log, nullptr, nullptr, nullptr, nullptr, 0, 0);
+            return;
+        }
         const double dt = cfg.dt;
         const bool two = cfg.second_wbc != 0;
         long it0 = ctrl->qp_iterations, f0 = ctrl->qp_failures;
         WBCOutput o1;
-        Vec<60> k1 = dynamics(state, t, nao, *ctrl, two, &o1);
-        int kk0 = mpc->last_k;
-        Vec<60> k2 = dynamics(state + (0.5 * dt) * k1, t + 0.5 * dt, nao, *ctrl, two);
-        int kk1 = mpc->last_k;
-        Vec<60> k3 = dynamics(state + (0.5 * dt) * k2, t + 0.5 * dt, nao, *ctrl, two);
-        int kk2 = mpc->last_k;
-        Vec<60> k4 = dynamics(state + dt * k3, t + dt, nao, *ctrl, two);
-        int kk3 = mpc->last_k;
-        state = state + (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4);
-        t += dt;  // Clock::step
-        if (log) {
-            std::memcpy(log->x, state.d, sizeof(log->x));
-            for (int k = 0; k < 3; ++k) {
-                log->com_k4[k] = nao.CoM[k];
-                log->rfoot[k] = nao.T[7](k, 3);
-                log->lfoot[k] = nao.T[14](k, 3);
-            }
-            std::memcpy(log->tau_k1, o1.tau.d, sizeof(log->tau_k1));
-            log->k_index[0] = kk0; log->k_index[1] = kk1; log->k_index[2] = kk2; log->k_index[3] = kk3;
-            log->qp_iters = (int)(ctrl->qp_iterations - it0);
-            log->qp_fail = (int)(ctrl->qp_failures - f0);
+        int kk[4], ph[4], ct[4];
+        auto note = [&](int i) {
+            kk[i] = mpc->last_k; ph[i] = ctrl->last_phase;
+            ct[i] = ctrl->contact.empty() ? 3 : ctrl->contact[ctrl->last_phase];
+        };
+        Vec<60> k1 = dynamics(state, t, nao, *ctrl, two, &o1); note(0);
+        Vec<60> k2 = dynamics(state + (0.5 * dt) * k1, t + 0.5 * dt, nao, *ctrl, two); note(1);
+        Vec<60> k3 = dynamics(state + (0.5 * dt) * k2, t + 0.5 * dt, nao, *ctrl, two); note(2);
+        Vec<60> k4 = dynamics(state + dt * k3, t + dt, nao, *ctrl, two); note(3);
+        Vec<60> xn = state + (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4);
+        double tau_inf = 0, qpp_inf = 0;
+        for (int k = 0; k < 24; ++k) tau_inf = std::fmax(tau_inf, std::fabs(o1.tau[k]));
+        for (int k = 0; k < 30; ++k) qpp_inf = std::fmax(qpp_inf, std::fabs(o1.qpp[k]));
+        int kz = kk[3] < 0 ? 0 : kk[3];
+        const int zl = (int)ctrl->zmp.zmpXRef.size();
+        if (kz >= zl) kz = zl - 1;
+        const double ex = nao.CoM[0] - ctrl->zmp.zmpXRef[kz], ey = nao.CoM[1] - ctrl->zmp.zmpYRef[kz];
+        const double err = std::sqrt(ex * ex + ey * ey);
+        bool healthy = tau_inf < ORC_TAU_LIMIT && err < ORC_COM_ERR_LIMIT && xn[2] > ORC_TORSO_MIN;
+        for (int k = 0; k < 60; ++k) healthy = healthy && (std::fabs(xn[k]) < ORC_STATE_LIMIT);
+        const int dit = (int)(ctrl->qp_iterations - it0), dfl = (int)(ctrl->qp_failures - f0);
+        if (healthy) {
+            state = xn;
+            t += dt;  // Clock::step
+            max_tau = std::fmax(max_tau, tau_inf); max_qpp = std::fmax(max_qpp, qpp_inf); max_err = std::fmax(max_err, err);
+            it_total += dit; fail_total += dfl;
+            ++steps_done;
+        } else {
+            alive = false;
         }
+        if (log) fill_log(log, &o1, kk, ph, ct, dit, dfl);
+    }
+    void fill_log(OrcStepLog* log, const WBCOutput* o1, const int* kk, const int* ph, const int* ct, int dit, int dfl) {
+        std::memcpy(log->x, state.d, sizeof(log->x));
+        for (int k = 0; k < 3; ++k) {
+            log->com_k4[k] = nao.CoM[k];
+            log->rfoot[k] = nao.T[7](k, 3);
+            log->lfoot[k] = nao.T[14](k, 3);
+        }
+        if (o1) std::memcpy(log->tau_k1, o1->tau.d, sizeof(log->tau_k1));
+        else std::memset(log->tau_k1, 0, sizeof(log->tau_k1));
+        for (int i = 0; i < 4; ++i) {
+            log->k_index[i] = kk ? kk[i] : mpc->last_k;
+            log->phase[i] = ph ? ph[i] : ctrl->last_phase;
+            log->contact[i] = ct ? ct[i] : (ctrl->contact.empty() ? 3 : ctrl->contact[ctrl->last_phase]);
+        }
+        log->qp_iters = dit;
+        log->qp_fail = dfl;
     }
 };
 
@@ -217,10 +253,12 @@ void orc_sim_set_walk_plan(void* sp, int32_t zmp_len, const double* zx, const do
         }
 }
 int32_t orc_sim_last_phase(void* sp) { return static_cast<Sim*>(sp)->ctrl->last_phase; }
+int32_t orc_sim_alive(void* sp) { return static_cast<Sim*>(sp)->alive ? 1 : 0; }
+int32_t orc_sim_steps(void* sp) { return static_cast<Sim*>(sp)->steps_done; }
 
-int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t E, const double* x0, const int32_t* push_step,
-                          const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
-                          double* com_out, double* stats) {
+int32_t orc_batch_rollout_ex(const OrcConfig* cfg, int32_t E, const double* x0, const int32_t* push_step,
+                             const double* push_dv, const OrcWalkPlans* plans, int32_t n_steps, int32_t n_threads,
+                             double* x_out, double* com_out, double* stats8, OrcStepLog* log) {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > E) n_threads = E > 0 ? E : 1;
     std::vector<std::thread> pool;
@@ -230,34 +268,50 @@ int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t E, const double* x0, con
             int lo = (int)((long long)E * th / n_threads), hi = (int)((long long)E * (th + 1) / n_threads);
             if (lo >= hi) return;
             Sim sim(*cfg);
+            sim.ctrl->abort_on_nonfinite = false;
             for (int e = lo; e < hi; ++e) {
                 sim.reset(x0 ? x0 + 60 * (size_t)e : nullptr);
-                double max_tau = 0, max_err = 0;
+                if (plans)
+                    orc_sim_set_walk_plan(&sim, plans->zmp_len, plans->zmp_x + (size_t)e * plans->zmp_len,
+                                          plans->zmp_y + (size_t)e * plans->zmp_len, plans->n_phases, plans->phase_T,
+                                          plans->foot_coef + (size_t)e * plans->n_phases * 40,
+                                          plans->contact + (size_t)e * plans->n_phases);
                 for (int s = 0; s < n_steps; ++s) {
-                    if (push_step && push_step[e] == s && push_dv)
+                    if (sim.alive && push_step && push_step[e] == s && push_dv)
                         for (int k = 0; k < 6; ++k) sim.state[30 + k] += push_dv[6 * (size_t)e + k];
-                    OrcStepLog lg;
-                    sim.step(&lg);
-                    for (int k = 0; k < 24; ++k) max_tau = std::fmax(max_tau, std::fabs(lg.tau_k1[k]));
-                    double ex = lg.com_k4[0] - 0.0, ey = lg.com_k4[1] - 0.0;
-                    max_err = std::fmax(max_err, std::sqrt(ex * ex + ey * ey));
+                    sim.step(log ? log + (size_t)e * n_steps + s : nullptr);
                 }
                 if (x_out) std::memcpy(x_out + 60 * (size_t)e, sim.state.d, sizeof(double) * 60);
                 if (com_out)
                     for (int k = 0; k < 3; ++k) com_out[3 * (size_t)e + k] = sim.nao.CoM[k];
-                if (stats) {
-                    stats[4 * (size_t)e + 0] = max_tau;
-                    stats[4 * (size_t)e + 1] = max_err;
-                    stats[4 * (size_t)e + 2] = (double)sim.ctrl->qp_iterations;
-                    stats[4 * (size_t)e + 3] = (double)sim.ctrl->qp_failures;
+                if (stats8) {
+                    double* o = stats8 + 8 * (size_t)e;
+                    o[0] = sim.max_tau; o[1] = sim.max_err; o[2] = sim.max_qpp; o[3] = (double)sim.it_total;
+                    o[4] = (double)sim.fail_total; o[5] = (double)sim.steps_done; o[6] = sim.alive ? 1.0 : 0.0; o[7] = sim.t;
                 }
-                fails[th] += (int)sim.ctrl->qp_failures;
+                fails[th] += (int)sim.fail_total;
             }
         });
     }
     for (auto& t : pool) t.join();
     int total = 0;
     for (int f : fails) total += f;
+    return total;
+}
+
+int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t E, const double* x0, const int32_t* push_step,
+                          const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
+                          double* com_out, double* stats) {
+    std::vector<double> s8(stats ? (size_t)E * 8 : 0);
+    int total = orc_batch_rollout_ex(cfg, E, x0, push_step, push_dv, nullptr, n_steps, n_threads, x_out, com_out,
+                                     stats ? s8.data() : nullptr, nullptr);
+    if (stats)
+        for (int e = 0; e < E; ++e) {
+            stats[4 * (size_t)e + 0] = s8[8 * (size_t)e + 0];
+            stats[4 * (size_t)e + 1] = s8[8 * (size_t)e + 1];
+            stats[4 * (size_t)e + 2] = s8[8 * (size_t)e + 3];
+            stats[4 * (size_t)e + 3] = s8[8 * (size_t)e + 4];
+        }
     return total;
 }
 

@@ -46,7 +46,21 @@ typedef struct {
     double tau_k1[24]; /* torques of the k1 stage (state at the step start) */
     int32_t k_index[4];
     int32_t qp_iters, qp_fail;
+    int32_t phase[4];  /* EXTENSION (walking): phase index of each stage; 0 in the reference's stand task */
+    int32_t contact[4];/* contact mask of each stage: bit 0 right foot, bit 1 left foot; 3 in the stand task */
 } OrcStepLog;
+
+/* EXTENSION (not in the reference, which has no notion of falling): the health rule of a closed-loop step.
+ * A step is COMMITTED (state, clock, statistics) only if, with x+ the state the RK4 combination would produce,
+ *   max|tau(k1)| < ORC_TAU_LIMIT,  |CoM_xy(k4) - zmp_ref(k_index(k4))| < ORC_COM_ERR_LIMIT,
+ *   every |x+_i| < ORC_STATE_LIMIT (NaN fails),  x+[2] (torso height) > ORC_TORSO_MIN.
+ * Otherwise the environment is FALLEN: state and clock keep the values of the last healthy step, its statistics
+ * are closed (they never see the failing step), alive = 0, and no further stage is evaluated for it.  The GPU
+ * path (lmh_model.cuh rk4_step) implements the same rule with the same FP64 comparisons. */
+#define ORC_TAU_LIMIT 100.0
+#define ORC_COM_ERR_LIMIT 0.5
+#define ORC_STATE_LIMIT 1e6
+#define ORC_TORSO_MIN 0.15
 
 void orc_default_config(OrcConfig* cfg);
 void* orc_sim_create(const OrcConfig* cfg);   /* Robot + IK + Mpc3dLip + ZMP + coeffs + Controller */
@@ -76,6 +90,26 @@ void orc_sim_link_table(void* sim, double* mass28, double* com28x3, double* iner
 int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t n_env, const double* x0, const int32_t* push_step,
                           const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
                           double* com_out, double* stats);
+
+/* Per-environment walking plans for orc_batch_rollout_ex: arrays [n_env][...] (same meaning as orc_sim_set_walk_plan). */
+typedef struct {
+    int32_t zmp_len, n_phases;
+    double phase_T;
+    const double* zmp_x;      /* [n_env][zmp_len] */
+    const double* zmp_y;
+    const double* foot_coef;  /* [n_env][n_phases][2][20] */
+    const int32_t* contact;   /* [n_env][n_phases] */
+} OrcWalkPlans;
+
+/* orc_batch_rollout with optional walking plans, the health rule above and the full statistics block:
+ * stats8 E x 8 = {max|tau(k1)|, max |CoM_xy - zmp_ref|, max|qpp(k1)|, qp iterations, qp failures, steps committed,
+ * alive, t}; log (or NULL): [n_env][n_steps] step records.  Returns the total number of QP failures. */
+int32_t orc_batch_rollout_ex(const OrcConfig* cfg, int32_t n_env, const double* x0, const int32_t* push_step,
+                             const double* push_dv, const OrcWalkPlans* plans, int32_t n_steps, int32_t n_threads,
+                             double* x_out, double* com_out, double* stats8, OrcStepLog* log);
+/* alive flag and committed steps of a single sim (health rule) */
+int32_t orc_sim_alive(void* sim);
+int32_t orc_sim_steps(void* sim);
 
 /* EXTENSION (walking, not in the reference): replaces the ZMP reference and installs per-phase foot polynomials
  * (foot_coef: [n_phases][2][20] = x(6) y(6) z(8), ascending powers of the phase-local time) and contact masks

@@ -746,8 +746,17 @@ Vec<74> Controller::solveQP(const Mat<74, 74>& H, const Vec<74>& g) {
                 for (int r = 0; r < 16; ++r) ubA[18 + 16 * foot + r] = 0.0;
     }
     if (!all_finite(Hqp) || !all_finite(gqp) || !all_finite(Aqp) || !all_finite(lbA)) {
-        std::fprintf(stderr, "orc::Controller::solveQP: NaN or Inf in QP data\n");
-        std::abort();  // :448-466
+        if (abort_on_nonfinite) {
+            std::fprintf(stderr, "orc::Controller::solveQP: NaN or Inf in QP data\n");
+            std::abort();  // :448-466
+        }
+        Vec<74> bad;
+        for (int i = 0; i < 74; ++i) bad[i] = std::nan("");
+        qpInfo = QpInfo();
+        qpInfo.status = 4;
+        ++qp_solves;
+        ++qp_failures;
+        return bad;
     }
     Vec<74> x;
     if (qp_long_double)

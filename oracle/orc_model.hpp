@@ -170,6 +170,8 @@ struct Controller {
     Vec<12> footAccRef;
     QpInfo qpInfo;
     bool qp_long_double = false;
+    bool abort_on_nonfinite = true;   // upstream aborts (controller.cpp:448-466); batch rollouts with falling robots
+                                      // turn the abort into a failed solve that returns NaN (the step is then unhealthy)
     // EXTENSION (not in the reference): walking plans.  Time is cut into n phases of length
     // phase_T; phase p = min((int)(t/phase_T), n-1) selects the foot polynomials (evaluated at t - p*phase_T) and
     // which feet may carry force (bit 0 right, bit 1 left; a swing foot's 16 coefficients get bounds [0,0]).

@@ -42,7 +42,17 @@ class OrcStageDump(C.Structure):
 
 class OrcStepLog(C.Structure):
     _fields_ = [("x", f64 * 60), ("com_k4", f64 * 3), ("rfoot", f64 * 3), ("lfoot", f64 * 3), ("tau_k1", f64 * 24),
-                ("k_index", i32 * 4), ("qp_iters", i32), ("qp_fail", i32)]
+                ("k_index", i32 * 4), ("qp_iters", i32), ("qp_fail", i32), ("phase", i32 * 4), ("contact", i32 * 4)]
+
+
+class OrcWalkPlans(C.Structure):
+    _fields_ = [("zmp_len", i32), ("n_phases", i32), ("phase_T", f64), ("zmp_x", C.c_void_p), ("zmp_y", C.c_void_p),
+                ("foot_coef", C.c_void_p), ("contact", C.c_void_p)]
+
+
+STEPLOG_DTYPE = np.dtype([("x", "f8", 60), ("com_k4", "f8", 3), ("rfoot", "f8", 3), ("lfoot", "f8", 3),
+                          ("tau_k1", "f8", 24), ("k_index", "i4", 4), ("qp_iters", "i4"), ("qp_fail", "i4"),
+                          ("phase", "i4", 4), ("contact", "i4", 4)])
 
 
 def build(ref=False):
@@ -82,6 +92,11 @@ class Lib:
         if hasattr(L, "orc_sim_set_walk_plan"):
             L.orc_sim_set_walk_plan.argtypes = [C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, f64, C.c_void_p, C.c_void_p]
             L.orc_sim_last_phase.argtypes = [C.c_void_p]
+        if hasattr(L, "orc_batch_rollout_ex"):
+            L.orc_batch_rollout_ex.argtypes = [C.POINTER(OrcConfig), i32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.orc_sim_alive.argtypes = [C.c_void_p]
+            L.orc_sim_steps.argtypes = [C.c_void_p]
         if hasattr(L, "orc_qp_solve"):
             L.orc_qp_solve.argtypes = [i32, C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p]
@@ -111,6 +126,31 @@ class Lib:
         fails = self.L.orc_batch_rollout(C.byref(cfg), n_env, _p(x0), _p(ps), _p(pd), n_steps, n_threads, _p(x),
                                          _p(com), _p(st))
         return x, com, st, fails
+
+    def batch_rollout_ex(self, cfg, n_env, n_steps, x0=None, push_step=None, push_dv=None, walk=None, n_threads=1,
+                         log=False):
+        """rollout with optional per-env walking plans (dict of scenarios.walk_plan), the health rule of orc_capi.h and
+        the full statistics: returns dict(x, com, stats (structured), log or None, qp_failures)"""
+        x0 = None if x0 is None else np.ascontiguousarray(x0, np.float64)
+        ps = None if push_step is None else np.ascontiguousarray(push_step, np.int32)
+        pd = None if push_dv is None else np.ascontiguousarray(push_dv, np.float64)
+        plans, keep = None, []
+        if walk is not None:
+            zx = np.ascontiguousarray(walk["zmp_x"], np.float64); zy = np.ascontiguousarray(walk["zmp_y"], np.float64)
+            ct = np.ascontiguousarray(walk["contact"], np.int32).reshape(n_env, -1)
+            fc = np.ascontiguousarray(walk["foot_coef"], np.float64).reshape(n_env, ct.shape[1], 40)
+            keep = [zx, zy, ct, fc]
+            plans = OrcWalkPlans(zx.shape[1], ct.shape[1], float(walk["phase_T"]), zx.ctypes.data, zy.ctypes.data,
+                                 fc.ctypes.data, ct.ctypes.data)
+        x, com, st = np.zeros((n_env, 60)), np.zeros((n_env, 3)), np.zeros((n_env, 8))
+        lg = np.zeros((n_env, n_steps), STEPLOG_DTYPE) if log else None
+        fails = self.L.orc_batch_rollout_ex(C.byref(cfg), n_env, _p(x0), _p(ps), _p(pd),
+                                            C.byref(plans) if plans is not None else None, n_steps, n_threads, _p(x),
+                                            _p(com), _p(st), _p(lg))
+        del keep
+        stats = dict(max_abs_tau=st[:, 0], max_com_err=st[:, 1], max_abs_qpp=st[:, 2], qp_iters=st[:, 3].astype(np.int64),
+                     qp_fail=st[:, 4].astype(np.int64), steps=st[:, 5].astype(np.int64), alive=st[:, 6].astype(np.int64), t=st[:, 7])
+        return dict(x=x, com=com, stats=stats, log=lg, qp_failures=fails)
 
     def qp_solve(self, H, g, A, lbA, ubA, long_double=False):
         H = np.ascontiguousarray(H, np.float64)
@@ -172,10 +212,7 @@ class Sim:
         self.lib.L.orc_sim_step(self.h, n, logs)
         if not log:
             return None
-        rec = np.frombuffer(logs, dtype=np.dtype([("x", "f8", 60), ("com_k4", "f8", 3), ("rfoot", "f8", 3),
-                                                  ("lfoot", "f8", 3), ("tau_k1", "f8", 24), ("k_index", "i4", 4),
-                                                  ("qp_iters", "i4"), ("qp_fail", "i4")])).copy()
-        return rec
+        return np.frombuffer(logs, dtype=STEPLOG_DTYPE).copy()
 
     def run_stand(self, max_steps=100000):
         out = np.zeros(max_steps)

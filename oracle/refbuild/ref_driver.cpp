@@ -90,7 +90,7 @@ struct RefSim {
                 log->lfoot[k] = nao.getT()[14](k, 3);
             }
             for (int k = 0; k < 24; ++k) log->tau_k1[k] = tau1(k);
-            for (int k = 0; k < 4; ++k) log->k_index[k] = kk[k];
+            for (int k = 0; k < 4; ++k) { log->k_index[k] = kk[k]; log->phase[k] = 0; log->contact[k] = 3; }   // stand task
             log->qp_iters = 0;
             log->qp_fail = 0;
         }

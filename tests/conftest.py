@@ -63,6 +63,16 @@ def hostemu():
     return hostemu_py
 
 
-def relerr(a, b):
+def scalederr(a, b):
+    """max|a - b| / max(1, max|b|): an ABSOLUTE max-norm error for references below 1, a relative one above.  Used for the
+    model intermediates, several of which are physically zero (a round-off sized reference has no relative error)."""
     a, b = np.asarray(a, float), np.asarray(b, float)
     return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def relerr(a, b):
+    """norm-wise RELATIVE error max|a - b| / max|b| (the north star's "within 1e-6 relative"); an all-zero reference
+    falls back to the absolute error"""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = float(np.abs(b).max())
+    return float(np.abs(a - b).max() / scale) if scale > 0.0 else float(np.abs(a - b).max())

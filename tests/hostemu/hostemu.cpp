@@ -62,7 +62,14 @@ void emu_stage(void* p, const double* x60, double* vheld30, double t, LmhStageDu
     stage_eval(cx, w, e->hm.K, e->plan, 0, dump);
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
 }
+void emu_rollout(void* p, double* x60, double* vheld30, double* t, int32_t n_steps, int32_t push_step, const double* push_dv6,
+                 LmhStepLog* logs, LmhStats* stats);
 void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps, LmhStepLog* logs, LmhStats* stats) {
+    emu_rollout(p, x60, vheld30, t, n_steps, -1, nullptr, logs, stats);
+}
+// n RK4 steps with an optional velocity impulse at the start of step push_step (what the rollout kernels do per env)
+void emu_rollout(void* p, double* x60, double* vheld30, double* t, int32_t n_steps, int32_t push_step, const double* push_dv6,
+                 LmhStepLog* logs, LmhStats* stats) {
     Emu* e = static_cast<Emu*>(p);
     EnvWS& w = e->hm.workspace();
     for (int i = 0; i < NQ; ++i) w.vh[i] = vheld30[i];
@@ -70,7 +77,10 @@ void emu_step(void* p, double* x60, double* vheld30, double* t, int32_t n_steps,
     StatsAcc st{0, 0, 0, 0, 0, 0, 1, 0};
     Ctx<1> cx{0, 0};
     ws_reset(cx, w);
-    for (int s = 0; s < n_steps; ++s) rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, logs ? logs + s : nullptr, &st);
+    for (int s = 0; s < n_steps; ++s) {
+        if (s == push_step && push_dv6 && w.dead == 0) for (int k = 0; k < 6; ++k) x60[30 + k] += push_dv6[k];
+        rk4_step(cx, w, x60, kacc, *t, e->hm.K, e->plan, 0, logs ? logs + s : nullptr, &st);
+    }
     for (int i = 0; i < NQ; ++i) vheld30[i] = w.vh[i];
     if (stats) {
         stats->max_abs_tau = st.max_tau; stats->max_com_err = st.max_err; stats->max_abs_qpp = st.max_qpp;

@@ -16,6 +16,7 @@ _L.emu_tables.argtypes = [_vp] * 8
 _L.emu_stage.argtypes = [_vp, _vp, _vp, _f64, _vp]
 _L.emu_set_walk_plan.argtypes = [_vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp]
 _L.emu_step.argtypes = [_vp, _vp, _vp, _vp, _i32, _vp, _vp]
+_L.emu_rollout.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]
 
 
 def _p(a):
@@ -53,10 +54,11 @@ class Emu:
         _L.emu_stage(self.h, _p(np.ascontiguousarray(x, np.float64)), _p(vh), float(t), _p(d))
         return d[0], vh
 
-    def step(self, x, v_held, t, n):
+    def step(self, x, v_held, t, n, push_step=-1, push_dv=None):
         x = np.ascontiguousarray(x, np.float64).copy()
         vh = np.ascontiguousarray(v_held, np.float64).copy()
         tt = np.array([float(t)])
         lg, st = np.zeros(n, STEPLOG_DTYPE), np.zeros(1, STATS_DTYPE)
-        _L.emu_step(self.h, _p(x), _p(vh), _p(tt), n, _p(lg), _p(st))
+        dv = None if push_dv is None else np.ascontiguousarray(push_dv, np.float64)
+        _L.emu_rollout(self.h, _p(x), _p(vh), _p(tt), n, int(push_step), _p(dv), _p(lg), _p(st))
         return x, vh, float(tt[0]), lg, st[0]

@@ -37,9 +37,9 @@ def test_struct_layouts_match_header():
     body = h[h.index("typedef struct {\n    double M[900]"):h.index("} LmhStageDump;")]
     n_dbl = sum(int(n) for n in re.findall(r"\w+\[(\d+)\]", body.split("int32_t")[0]))
     assert api.STAGE_DTYPE.itemsize == 8 * n_dbl + 16
-    assert api.STEPLOG_DTYPE.itemsize == 8 * (3 + 3 + 3 + 24) + 4 * 6
+    assert api.STEPLOG_DTYPE.itemsize == 8 * (3 + 3 + 3 + 24) + 4 * 14
     assert api.STATS_DTYPE.itemsize == 8 * 3 + 4 * 6
-    assert C.sizeof(api.LmhConfig) == 8 * (3 + 3 + 6 + 6 + 3) + 4 * 4
+    assert C.sizeof(api.LmhConfig) == 8 * (3 + 3 + 6 + 6 + 3) + 4 * 6
 
 
 def test_default_config_is_the_reference_scenario():
