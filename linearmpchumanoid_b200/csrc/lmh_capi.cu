@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(32 * kMaxEpb, 1) rollout_kernel_multi(Params p
     const bool live = wid < count;
     if (!live) slot = p.n_env - 1;
     const int env = p.order ? p.order[slot] : slot;
-    Ctx<32> cx{lane, 32 * count == (int)blockDim.x ? -1 : 32 * count};
+    Ctx<32, true> cx{lane, 32 * count == (int)blockDim.x ? -1 : 32 * count};
     const Consts& K = *p.K;
-    if (tab_doubles > 0) {
+    {
         // behind the environments' slices: one copy per block of the tables every level of the tree recursions reads
         // (the 29 KB of L1 left beside 227 KB of shared memory do not keep them: they came from L2 half of the time)
         double* tab = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + (size_t)epb * env_bytes);

@@ -183,9 +183,11 @@ LMH_HD double jf_full(const EnvWS& w, int row, int col) {
 LMH_HD double vb_at(const EnvWS& w, int j) { return j < 6 ? w.vb6[j] : w.v[j]; }
 
 // ------------------------------------------------------------------------------------------------
-template <int NT_>
+template <int NT_, bool TAB_ = false>
 struct Ctx {
     static constexpr int NT = NT_;
+    static constexpr bool TAB = TAB_;   // isp and dh point into the block's shared memory (known at compile time, so that
+                                        // the tree recursions read them with LDS instead of generic loads)
     int tid;
     int bar_id;          // several one-warp environments share a block and re-align at align() points: < 0 all warps of
                          // the block (plain __syncthreads), > 32 the number of threads taking part (32 x live warps)
@@ -352,7 +354,11 @@ LMH_HDN void fk_phase(const Cx& cx, EnvWS& w, const Consts& K) {
     double* Tw = w.u.m.p.Tw;
     double* Xl = w.u.m.Xl;
 #if defined(__CUDA_ARCH__)
-    if (Cx::NT == 32) { fk_local_warp(w, K, cx.dh ? cx.dh : K.th_off, cx.tid); fk_chain_warp(w, K, cx.tid); return; }
+    if (Cx::NT == 32) {
+        const double* dh = Cx::TAB ? cx.dh : K.th_off;
+        if (Cx::TAB) __builtin_assume(__isShared(dh));
+        fk_local_warp(w, K, dh, cx.tid); fk_chain_warp(w, K, cx.tid); return;
+    }
 #endif
     // torso pose (generalizedFunctions.cpp:52-72) and local DH transforms (Robot.cpp:176-223)
     LMH_FOR(i, NF) {
@@ -1617,7 +1623,8 @@ LMH_HDN void model_phases(const Cx& cx, EnvWS& w, const Consts& K) {
 #if defined(__CUDA_ARCH__)
     if (Cx::NT == 32) {
         const LaneRole L = lane_role(cx.tid);
-        const double* Isp = cx.isp ? cx.isp : K.Isp;
+        const double* Isp = Cx::TAB ? cx.isp : K.Isp;
+        if (Cx::TAB) __builtin_assume(__isShared(Isp));
         rnea_warp(w, K, Isp, L, cx.tid);
         crba_warp(w, K, Isp, L, cx.tid);
     } else

@@ -44,7 +44,46 @@ __device__ __forceinline__ double dsel3(int k, double x0, double x1, double x2) 
 __device__ __forceinline__ double cross3_sel(const double* a, const double* b, int k) {
     return dsel3(k, a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
 }
-// 16-byte aligned sources: LDS.128, half the shared-memory wavefronts of the scalar loads
+// Experiment switches (A/B builds: scripts/ab_bench.py); the defaults are what measured best on B200 (config 2, E = 4096):
+//   LMH_BCAST64 = 0, LMH_XSTRIDE = 8 : 10.92 M env-steps/s     LMH_BCAST64 = 1, LMH_XSTRIDE = 8 : 10.44 M
+//   LMH_BCAST64 = 0, LMH_XSTRIDE = 6 : 11.01 M (default)       LMH_BCAST64 = 1, LMH_XSTRIDE = 6 : 10.67 M
+// i.e. trading shared-memory wavefronts for issue slots loses: at ten warps per SM the kernel is bound by the latency of
+// its dependent instruction chains, not by the shared-memory pipe alone (gpurun_out/r2_ab2.log).
+#ifndef LMH_XSTRIDE
+#define LMH_XSTRIDE 6      // doubles between the chains' slots in the exchange buffers: 6 = lane order (lane 6c + r writes word
+                           // 6c + r: no bank conflicts), 8 = one 64-byte line per chain
+#endif
+#ifndef LMH_BCAST64
+#define LMH_BCAST64 0      // 1: chain-broadcast six-vectors / transforms through LDS.64 (one wavefront each) instead of LDS.128
+#endif
+// A six-vector / an (R, p) record that EVERY lane of a chain reads from the same address: five distinct addresses per
+// warp.  An LDS.64 serves that in one wavefront; an LDS.128 is processed a quarter-warp at a time (3-4 wavefronts for 16
+// bytes per lane), so the scalar form moves the same data through the shared-memory pipe in 6 instead of ~10 wavefronts.
+// (explicit ld.shared.f64: plain C++ loads would be fused back into LDS.128, and C++ volatile loads are strongly ordered
+// -- one in flight at a time, which halved the throughput when it was tried)
+__device__ __forceinline__ void ld6b(const double* p, double* o) {
+#if LMH_BCAST64
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o[k]) : "r"(a + 8u * k) : "memory");
+#else
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const double2 t = q[k]; o[2 * k] = t.x; o[2 * k + 1] = t.y; }
+#endif
+}
+__device__ __forceinline__ void ld12b(const double* p, double* o) {
+#if LMH_BCAST64
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o[k]) : "r"(a + 8u * k) : "memory");
+#else
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double2 t = q[k]; o[2 * k] = t.x; o[2 * k + 1] = t.y; }
+#endif
+}
+// 16-byte aligned sources, a different address per lane: LDS.128, half the shared-memory wavefronts of the scalar loads
 __device__ __forceinline__ void ld6v(const double* p, double* o) {
     const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
@@ -194,29 +233,29 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
 __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const LaneRole& L, int lane) {
     auto& S = w.u.m.p.wr;
     const double* Xl = w.u.m.Xl;
-    const int c8 = 8 * L.c, r = L.r;
+    const int c8 = LMH_XSTRIDE * L.c, r = L.r;
     const bool lin = r >= 3;
     const int k3 = lin ? r - 3 : r;
     const double csgn = (k3 == 0) ? 1.0 : (k3 == 1) ? -1.0 : 0.0;
     // base: f0 = v0 x* (I0 v0), acc0 = 0
     if (lane < 6) {
         double v0[6];
-        ld6v(w.vhb6, v0);
+        ld6b(w.vhb6, v0);
         const double* I = Isp + 6 * lane;
         S.hbuf[lane] = I[0] * v0[0] + I[1] * v0[1] + I[2] * v0[2] + I[3] * v0[3] + I[4] * v0[4] + I[5] * v0[5];
     }
     __syncwarp();
     if (lane < 6) {
         double v0[6], h[6];
-        ld6v(w.vhb6, v0);
-        ld6v(S.hbuf, h);
+        ld6b(w.vhb6, v0);
+        ld6b(S.hbuf, h);
         S.frc[lane] = lane < 3 ? cross3(v0, h, lane) + cross3(v0 + 3, h + 3, lane) : cross3(v0, h + 3, lane - 3);
     }
     int cur = 0;
     // velocity and acceleration of the frame above, all six components, carried in registers from level to level
     // (every lane of a chain reads the new ones anyway): two exchange-buffer reads per level instead of four
     double pv[6], pa[6] = {0, 0, 0, 0, 0, 0};
-    ld6v(w.vhb6, pv);
+    ld6b(w.vhb6, pv);
 #pragma unroll 1
     for (int d = 1; d <= MAXDEPTH; ++d) {
         const bool act = L.on && d <= L.len;
@@ -236,7 +275,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         if (act) S.vbuf[cur ^ 1][c8 + r] = x;
         ld6v(Isp + 36 * i + 6 * r, Irow);
         __syncwarp();
-        ld6v(S.vbuf[cur ^ 1] + c8, nv);
+        ld6b(S.vbuf[cur ^ 1] + c8, nv);
         double xa = (a0 * pa[0] + a1 * pa[1] + a2 * pa[2]) + (b0 * pa[3] + b1 * pa[4] + b2 * pa[5]);   // zero at the first level
         // (v x S) qd with S = e_z: component r is sgn * v[partner], lane constants (rows 2 and 5: sgn = 0)
         const double colv = dsel(lin, dsel(r == 3, nv[4], nv[3]), dsel(r == 0, nv[1], nv[0]));
@@ -250,8 +289,8 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         __syncwarp();
         {
             double na[6], h[6];
-            ld6v(S.abuf[cur ^ 1] + c8, na);
-            ld6v(S.hbuf + c8, h);
+            ld6b(S.abuf[cur ^ 1] + c8, na);
+            ld6b(S.hbuf + c8, h);
             double f = Irow[0] * na[0] + Irow[1] * na[1] + Irow[2] * na[2] + Irow[3] * na[3] + Irow[4] * na[4] + Irow[5] * na[5];
 #pragma unroll
             for (int k = 0; k < 6; ++k) { pv[k] = nv[k]; pa[k] = na[k]; }
@@ -273,7 +312,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         const int i = L.first + (d <= L.nact ? d : L.nact) - 1;
         const double* X = Xl + 12 * i;
         double f[6];
-        ld6v(S.frc + 8 * i, f);
+        ld6b(S.frc + 8 * i, f);
         const double g0 = X[3 * k3], g1 = X[3 * k3 + 1], g2 = X[3 * k3 + 2];     // row k3 of R
         const double rf = g0 * f[3] + g1 * f[4] + g2 * f[5];
         const double rf1 = __shfl_sync(0xffffffffu, rf, src1), rf2 = __shfl_sync(0xffffffffu, rf, src2);
@@ -286,7 +325,7 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
     if (L.on && r < L.nact) w.Cg[6 + L.j0 + r] = S.frc[8 * (L.first + r) + 2];
     if (lane < 6) {
         double s = S.frc[lane];
-        for (int c = NCH - 1; c >= 0; --c) s += S.contrib[8 * c + lane];
+        for (int c = NCH - 1; c >= 0; --c) s += S.contrib[LMH_XSTRIDE * c + lane];
         w.Cg[lane] = s;
     }
     if (lane >= 6 && lane < 18) {       // Jpqp = world-rotated sole accelerations
@@ -334,13 +373,13 @@ __device__ __forceinline__ void crba_XT_times_col(const double* Rp, const double
 template <bool ROWS>
 __device__ __forceinline__ void crba_level(EnvWS& w, const double* Isp, const LaneRole& L, int d, double* icin, double* F) {
     auto& S = w.u.m.p.wr;
-    const int c8 = 8 * L.c, r = L.r;
+    const int c8 = LMH_XSTRIDE * L.c, r = L.r;
     const bool act = L.on && d <= L.nact;
     const int i = L.first + d - 1;
     double* T = S.Ybuf + 36 * L.c;
     double Rp[12];
     if (act) {
-        ld12v(w.u.m.Xl + 12 * i, Rp);
+        ld12b(w.u.m.Xl + 12 * i, Rp);
         double ic[6], t[6];
         if (ROWS) {
             ld6v(Isp + 36 * i + 6 * r, ic);
@@ -366,7 +405,7 @@ __device__ __forceinline__ void crba_level(EnvWS& w, const double* Isp, const La
     __syncwarp();
     if (act) {
         // this lane's joint: pick up the new vector at its own depth, then cross frame i towards the root
-        if (r == d - 1) ld6v(S.col2 + c8, F);
+        if (r == d - 1) ld6b(S.col2 + c8, F);
         if (r >= d - 1 && r < L.nact) {
             double o[6];
             xf_all(Rp, F, o);
@@ -436,7 +475,7 @@ __device__ void jacobian_warp(EnvWS& w, int lane) {
 #pragma unroll 1
         for (int i = start; i <= 6; ++i) {
             double Rp[12];
-            ld12v(Xl + 12 * (f0 + i), Rp);
+            ld12b(Xl + 12 * (f0 + i), Rp);
             const double u0 = v[3] + (v[1] * Rp[11] - v[2] * Rp[10]);
             const double u1 = v[4] + (v[2] * Rp[9] - v[0] * Rp[11]);
             const double u2 = v[5] + (v[0] * Rp[10] - v[1] * Rp[9]);

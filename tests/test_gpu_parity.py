@@ -309,7 +309,7 @@ def test_config4_walk_and_push_against_oracle(oracle):
         assert abs(st["max_abs_tau"][e] - so["max_abs_tau"][e]) < 1e-4 * so["max_abs_tau"][e]
         assert abs(st["max_com_err"][e] - so["max_com_err"][e]) < 1e-6
         if st["alive"][e]:
-            assert np.abs(x[e] - r["x"][e]).max() < 1e-7, e
+            assert scalederr(x[e], r["x"][e]) < 1e-7, e                        # (a survivor may be tumbling at 40 rad/s)
             assert abs(st["max_abs_qpp"][e] - so["max_abs_qpp"][e]) < 1e-6 * so["max_abs_qpp"][e]
         else:
             assert np.abs(x[e] - r["x"][e]).max() < 1e-2, e
