@@ -49,6 +49,8 @@ typedef struct {
                               0 = as many as the shared memory holds (the default), else 1..that many */
     int32_t placement;     /* 0 = lmh_set_pushes places environments that are pushed at the same step in the same
                               block (default; results do not depend on it), 1 = keep the index order */
+    double mpc_zcom;       /* Mpc3dLip's zCoM argument (mpcLinearPendulum.hpp:13-16); 0 = the CoM height after the inverse
+                              kinematics of the initial posture, as main.cpp:39 passes it */
 } LmhConfig;
 
 /* Everything one dynamics() evaluation (apps/offline/main.cpp:91-122) produces, row-major. */
@@ -117,6 +119,18 @@ int32_t lmh_get_nominal(const LmhBatch* h, double* q0_30, double* zcom, double* 
 int32_t lmh_get_mpc_gain(const LmhBatch* h, double* r, int32_t r_cap, int32_t* n1, double* rPx2);
 /* Robot::getLinks after the constructor: mass[28], com[28][3], spatial inertia[28][36]. */
 int32_t lmh_get_link_tables(const LmhBatch* h, double* mass28, double* com28x3, double* isp28x36);
+
+/* The same table with the 3 x 3 inertia of every link about its centre of mass, in the joint frame (linkInertia::inertia
+ * after the Robot constructor, Robot.cpp:14-22): inertia [28][9] row-major. */
+int32_t lmh_get_link_inertia(const LmhBatch* h, double* inertia28x9);
+/* createNaoParameters (src/robotParameters.cpp): the raw table -- mass [28], com [28][3], inertia [28][9] in frames
+ * aligned with the world at q = 0.  Host only, no handle. */
+int32_t lmh_get_nao_parameters(double* mass28, double* com28x3, double* inertia28x9);
+/* matTrans (src/Robot.cpp:176-223): the 25 local modified-DH transforms for given theta [25] -> T [25][16] (4 x 4 row-major).  Host only. */
+int32_t lmh_local_transforms(const double* theta25, double* T25x16);
+/* findPolyCoeff (src/generalizedFunctions.cpp:103-163): polynomial (ascending powers) through n_pos positions, n_vel
+ * velocities and n_acc accelerations given as (time, value) rows [n][2]; coeff [n_pos + n_vel + n_acc].  Host only. */
+int32_t lmh_poly_fit(int32_t n_pos, const double* pos, int32_t n_vel, const double* vel, int32_t n_acc, const double* acc, double* coeff);
 
 /* Plans replace the ZMP object and the two coefficient vectors handed to the Controller
  * (controller.hpp:52-57).  zmp_x/zmp_y: [n_plans][zmp_len]; foot_coef: [n_plans][2][20] =
@@ -191,6 +205,65 @@ int32_t lmh_qp_bench(LmhBatch* h, int32_t mode, int32_t repeats, double* a_f_out
  * keeps the batch's CoM height (Mpc3dLip::getZCom of the nominal scenario). */
 int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* rf6, const double* lf6, double* q_out,
                      int32_t* iters, double* residual, int32_t* status, int32_t apply_to_state);
+
+/* General form of the same: the full operational target desop [n][30] = [right sole position + Euler angles (6), left
+ * sole (6), arm and head joints (12), base attitude (3), CoM (3)] as Kinematics::desiredOperationalState returns it
+ * (invKinematics.cpp:11-25), and the posture the Newton iteration starts from, q_start [n][30] (NULL = the batch's
+ * nominal posture for every target; Kinematics::compute starts from the Robot's current joints, invKinematics.cpp:27-33). */
+int32_t lmh_ik_solve(LmhBatch* h, int32_t n, const double* q_start, const double* desop, double* q_out, int32_t* iters,
+                     double* residual, int32_t* status);
+
+/* Robot::updateState (src/Robot.cpp:264-269: forwardKinematics, computeCoM, parentTransMatrix, allVelocityMatrices) for n
+ * postures on the device.  q [n][30] -> T [n][28][16] world transforms (4 x 4, row-major), X [n][28][36] motion
+ * transforms of every frame with respect to its parent (6 x 6, row-major; X[0] = velocityMatrix(T[0])), com [n][3].
+ * Any output may be NULL.  Frame 27 (the massless extra head frame, Robot.cpp:84,153-158) is completed on the host. */
+int32_t lmh_kinematics(LmhBatch* h, int32_t n, const double* q, double* T, double* X, double* com);
+
+/* Mpc3dLip::compute + solve1DQP (src/mpcLinearPendulum.cpp:78-133) for n problems on the device as a DENSE solve per
+ * problem: g = beta Pu'(Px x_k - z), (alpha I + beta Pu'Pu) u = -g through the Cholesky factor of the (constant) Hessian,
+ * shared by the batch and by both axes; x+ = A x_k + B u0.  The horizon, dt, zCoM, alpha, beta are the batch's.
+ * com_xy, vel_xy [n][2]; zmp_x, zmp_y [n][horizon + 1] = zmpRef[k : k + horizon + 1] of each problem; xref, yref [n][3] =
+ * (position, velocity, acceleration) as getXRef / getYRef return them.  use_dmma = 1: the dense tile products run on the
+ * FP64 tensor cores (mma.sync m8n8k4), 0: on the FP64 FMA pipe.  repeats >= 1 solves every problem that many times
+ * (micro-benchmark); elapsed_ms (or NULL): device time of the launch. */
+int32_t lmh_mpc_solve(LmhBatch* h, int32_t n, const double* com_xy, const double* vel_xy, const double* zmp_x,
+                      const double* zmp_y, double* xref, double* yref, int32_t use_dmma, int32_t repeats, double* elapsed_ms);
+/* Setup tables of the same: Px [n1][2], Pu [n1][n1] (row-major; mpcLinearPendulum.cpp:41-68), n1 = horizon + 1. */
+int32_t lmh_get_mpc_tables(const LmhBatch* h, double* Px, double* Pu, int32_t cap, int32_t* n1);
+
+/* ---- host-only scenario pieces (no device work, no handle) ----
+ * footCoeffTrajectory (src/footRefTrajectory.cpp:4-47, findPolyCoeff generalizedFunctions.cpp:103-163): boundary-value
+ * polynomials of one foot over [0, T], ascending powers: x (6), y (6), z (8, through step_height at T/2). */
+int32_t lmh_foot_coeff(const double* cur3, const double* des3, double step_height, double T, double* x6, double* y6, double* z8);
+/* Config 2: one velocity impulse per environment on the base linear x,y velocity, magnitude ~U(0, max_speed), direction
+ * ~U(0, 2 pi), at step ~U{0..max_step}; counter-based generator keyed by (seed, GLOBAL environment id): any sharding
+ * of the ids gives the same per-environment integers and doubles.  push_step [n], push_dv6 [n][6]. */
+int32_t lmh_push_plan(const int64_t* env_ids, int32_t n, uint64_t seed, double max_speed, int32_t max_step, int32_t* push_step,
+                      double* push_dv6);
+/* EXTENSION -- ZMP::walkZMP (declared, never defined upstream: zmpGeneration.hpp:15-22) + per-phase swing polynomials +
+ * contact masks.  A plan is n_footsteps steps (right foot first) of one length, a phase of double support before and after;
+ * the ZMP reference is piecewise constant: under the stance foot in single support, between the feet in double support.
+ * Sizes: n_phases = n_footsteps + 2, zmp_len = n_phases * round(time_per_step / dt) + tail_steps + horizon_steps + 2. */
+typedef struct {
+    int32_t n_footsteps;       /* 4 */
+    int32_t horizon_steps;     /* 160: samples the MPC looks ahead (zmp_len covers the last window) */
+    int32_t tail_steps;        /* 40 */
+    int32_t pad;
+    double time_per_step;      /* 0.4 s per phase (header default 0.5, zmpGeneration.hpp:38) */
+    double dt;                 /* 0.01 */
+    double step_height;        /* 0.02 */
+    double lateral;            /* 0.05: |y| of the feet */
+    double min_len, max_len;   /* step length ~U(min_len, max_len) per environment: 0.02, 0.05 */
+    double fixed_len;          /* >= 0: every environment takes this step length instead (ZMP(Task::Walk,...)); < 0: random */
+} LmhWalkSpec;
+void lmh_default_walk_spec(LmhWalkSpec* spec);
+int32_t lmh_walk_plan_dims(const LmhWalkSpec* spec, int32_t* n_phases, int32_t* zmp_len);
+/* zmp_x, zmp_y [n][zmp_len]; foot_coef [n][n_phases][2][20]; contact [n][n_phases]; step_len [n] (or NULL) */
+int32_t lmh_walk_plan(const LmhWalkSpec* spec, const int64_t* env_ids, int32_t n, uint64_t seed, double* zmp_x, double* zmp_y,
+                      double* foot_coef, int32_t* contact, double* step_len);
+/* generate the plans of environments first_env_id .. first_env_id + n_env - 1 and install them (lmh_set_walk_plans with
+ * one plan per environment) without a trip through the caller */
+int32_t lmh_make_walk_plans(LmhBatch* h, const LmhWalkSpec* spec, int64_t first_env_id, uint64_t seed);
 
 /* Data-format glue for viewing rollouts in MuJoCo (host only, no device work): relabelMujocoMatrix
  * (apps/mujoco/main.cpp:182-200: q_mj = L q[6:30], blocks head / left leg / right leg / left arm / right arm,

@@ -22,7 +22,12 @@ class LmhError(RuntimeError):
 class LmhConfig(C.Structure):
     _fields_ = [("dt", _f64), ("sim_time", _f64), ("time_horizon", _f64), ("com", _f64 * 3), ("rf", _f64 * 6),
                 ("lf", _f64 * 6), ("mu", _f64), ("mpc_alpha", _f64), ("mpc_beta", _f64), ("qp_max_iter", _i32),
-                ("threads_per_env", _i32), ("device", _i32), ("log_steps", _i32), ("envs_per_block", _i32), ("placement", _i32)]
+                ("threads_per_env", _i32), ("device", _i32), ("log_steps", _i32), ("envs_per_block", _i32), ("placement", _i32), ("mpc_zcom", _f64)]
+
+
+class LmhWalkSpec(C.Structure):
+    _fields_ = [("n_footsteps", _i32), ("horizon_steps", _i32), ("tail_steps", _i32), ("pad", _i32), ("time_per_step", _f64),
+                ("dt", _f64), ("step_height", _f64), ("lateral", _f64), ("min_len", _f64), ("max_len", _f64), ("fixed_len", _f64)]
 
 
 STAGE_DTYPE = np.dtype([("M", "f8", (30, 30)), ("C", "f8", 30), ("Cg", "f8", 30), ("AG", "f8", (6, 30)),
@@ -47,7 +52,10 @@ SYMBOLS = ["lmh_last_error", "lmh_default_config", "lmh_create", "lmh_destroy", 
            "lmh_get_state", "lmh_reset", "lmh_set_pushes", "lmh_set_step_counter", "lmh_stage", "lmh_step",
            "lmh_step_timed", "lmh_sync", "lmh_get_stats", "lmh_get_log", "lmh_get_com", "lmh_state_dev",
            "lmh_stats_dev", "lmh_set_state_dev", "lmh_reset_stats", "lmh_timer_start", "lmh_timer_stop",
-           "lmh_qp_bench", "lmh_ik_batch", "lmh_export_mujoco", "lmh_launch_info", "lmh_measure_fp64_peak"]
+           "lmh_qp_bench", "lmh_ik_batch", "lmh_export_mujoco", "lmh_launch_info", "lmh_measure_fp64_peak",
+           "lmh_ik_solve", "lmh_kinematics", "lmh_mpc_solve", "lmh_get_mpc_tables", "lmh_foot_coeff", "lmh_push_plan",
+           "lmh_default_walk_spec", "lmh_walk_plan_dims", "lmh_walk_plan", "lmh_make_walk_plans", "lmh_get_link_inertia",
+           "lmh_get_nao_parameters", "lmh_local_transforms", "lmh_poly_fit"]
 
 
 def build_library(force=False, verbose=False):
@@ -112,6 +120,21 @@ def load_library():
     L.lmh_export_mujoco.argtypes = [_i32, vp, vp]
     L.lmh_launch_info.argtypes = [vp, vp, vp, vp, vp, vp]
     L.lmh_measure_fp64_peak.argtypes = [_i32, vp, vp, vp]
+    L.lmh_ik_solve.argtypes = [vp, _i32, vp, vp, vp, vp, vp, vp]
+    L.lmh_kinematics.argtypes = [vp, _i32, vp, vp, vp, vp]
+    L.lmh_mpc_solve.argtypes = [vp, _i32, vp, vp, vp, vp, vp, vp, _i32, _i32, vp]
+    L.lmh_get_mpc_tables.argtypes = [vp, vp, vp, _i32, vp]
+    L.lmh_foot_coeff.argtypes = [vp, vp, _f64, _f64, vp, vp, vp]
+    L.lmh_push_plan.argtypes = [vp, _i32, C.c_uint64, _f64, _i32, vp, vp]
+    L.lmh_default_walk_spec.argtypes = [C.POINTER(LmhWalkSpec)]
+    L.lmh_default_walk_spec.restype = None
+    L.lmh_walk_plan_dims.argtypes = [C.POINTER(LmhWalkSpec), vp, vp]
+    L.lmh_walk_plan.argtypes = [C.POINTER(LmhWalkSpec), vp, _i32, C.c_uint64, vp, vp, vp, vp, vp]
+    L.lmh_make_walk_plans.argtypes = [vp, C.POINTER(LmhWalkSpec), C.c_int64, C.c_uint64]
+    L.lmh_get_link_inertia.argtypes = [vp, vp]
+    L.lmh_get_nao_parameters.argtypes = [vp, vp, vp]
+    L.lmh_local_transforms.argtypes = [vp, vp]
+    L.lmh_poly_fit.argtypes = [_i32, vp, _i32, vp, _i32, vp, vp]
     _lib = L
     return L
 
@@ -140,6 +163,17 @@ def export_mujoco(q):
     out = np.zeros((q.shape[0], 31))
     _chk(L, L.lmh_export_mujoco(q.shape[0], _p(q), _p(out)))
     return out
+
+
+def walk_spec(**kw):
+    L = load_library()
+    ws = LmhWalkSpec()
+    L.lmh_default_walk_spec(C.byref(ws))
+    for k, v in kw.items():
+        if not hasattr(ws, k):
+            raise LmhError(f"unknown walk-spec field {k}")
+        setattr(ws, k, v)
+    return ws
 
 
 class Batch:
@@ -302,6 +336,51 @@ class Batch:
         q, it, res, st = np.zeros((n, 30)), np.zeros(n, np.int32), np.zeros(n), np.zeros(n, np.int32)
         _chk(self.L, self.L.lmh_ik_batch(self.h, n, _p(com), _p(rf), _p(lf), _p(q), _p(it), _p(res), _p(st), 1 if apply else 0))
         return {"q": q, "iters": it, "residual": res, "status": st}
+
+    def ik_solve(self, desop, q_start=None):
+        """general Kinematics::compute: desop [n][30] operational targets, q_start [n][30] or None (nominal posture)"""
+        des = np.ascontiguousarray(desop, np.float64).reshape(-1, 30)
+        n = des.shape[0]
+        qs = None if q_start is None else np.ascontiguousarray(np.broadcast_to(np.asarray(q_start, np.float64).reshape(-1, 30), (n, 30)))
+        q, it, res, st = np.zeros((n, 30)), np.zeros(n, np.int32), np.zeros(n), np.zeros(n, np.int32)
+        _chk(self.L, self.L.lmh_ik_solve(self.h, n, _p(qs), _p(des), _p(q), _p(it), _p(res), _p(st)))
+        return {"q": q, "iters": it, "residual": res, "status": st}
+
+    def kinematics(self, q):
+        """Robot::updateState for n postures: (T [n][28][4][4], X [n][28][6][6], com [n][3])"""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, 30)
+        n = q.shape[0]
+        T, X, com = np.zeros((n, 28, 4, 4)), np.zeros((n, 28, 6, 6)), np.zeros((n, 3))
+        _chk(self.L, self.L.lmh_kinematics(self.h, n, _p(q), _p(T), _p(X), _p(com)))
+        return T, X, com
+
+    def mpc_tables(self):
+        n1 = np.zeros(1, np.int32)
+        _chk(self.L, self.L.lmh_get_mpc_tables(self.h, None, None, 0, _p(n1)))
+        n = int(n1[0])
+        Px, Pu = np.zeros((n, 2)), np.zeros((n, n))
+        _chk(self.L, self.L.lmh_get_mpc_tables(self.h, _p(Px), _p(Pu), n, _p(n1)))
+        return Px, Pu
+
+    def mpc_solve(self, com_xy, vel_xy, zmp_x, zmp_y, use_dmma=False, repeats=1):
+        """Mpc3dLip::compute as a dense solve per problem on the device: returns (xref [n][3], yref [n][3], ms)"""
+        c = np.ascontiguousarray(com_xy, np.float64).reshape(-1, 2)
+        n = c.shape[0]
+        v = np.ascontiguousarray(vel_xy, np.float64).reshape(n, 2)
+        zx = np.ascontiguousarray(zmp_x, np.float64).reshape(n, -1)
+        zy = np.ascontiguousarray(zmp_y, np.float64).reshape(n, -1)
+        n1 = np.zeros(1, np.int32)
+        _chk(self.L, self.L.lmh_get_mpc_tables(self.h, None, None, 0, _p(n1)))
+        if zx.shape[1] != int(n1[0]) or zy.shape != zx.shape:
+            raise LmhError("mpc_solve: the ZMP windows must hold horizon + 1 samples")
+        xr, yr, ms = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(1)
+        _chk(self.L, self.L.lmh_mpc_solve(self.h, n, _p(c), _p(v), _p(zx), _p(zy), _p(xr), _p(yr), 1 if use_dmma else 0, int(repeats), _p(ms)))
+        return xr, yr, float(ms[0])
+
+    def make_walk_plans(self, first_env_id=0, seed=0x5EED0003, **spec):
+        """generate and install one walking plan per environment inside the library (no trip through Python)"""
+        ws = walk_spec(**spec)
+        _chk(self.L, self.L.lmh_make_walk_plans(self.h, C.byref(ws), int(first_env_id), int(seed)))
 
     def launch_info(self):
         v = [np.zeros(1, np.int32) for _ in range(5)]

@@ -7,6 +7,8 @@
 // log record).  Environments never communicate.
 #include "lmh_setup.hpp"
 #include "lmh_ik.cuh"
+#include "lmh_mpc.cuh"
+#include "lmh_scenarios.hpp"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstddef>
@@ -221,6 +223,8 @@ __global__ void __launch_bounds__(NT) qp_bench_kernel(Params p, int repeats, int
 struct IkParams {
     const Consts* K;
     const double* q_start;     // [30] posture the Newton iteration starts from (and source of the arm/head targets)
+    const double* q_start_each;// [n][30] or null: a starting posture per target
+    const double* desop;       // [n][30] or null: the full operational target (then com / rf / lf are unused)
     const double* com;         // [n][3]
     const double* rf;          // [n][6]
     const double* lf;          // [n][6]
@@ -242,11 +246,12 @@ __global__ void __launch_bounds__(128) ik_kernel(IkParams p) {
     EnvWS& w = *reinterpret_cast<EnvWS*>(reinterpret_cast<char*>(smem) + (size_t)wid * p.env_bytes);
     double* des = w.qppRef;
     if (lane < NQ) {
-        w.q[lane] = p.q_start[lane];
+        w.q[lane] = p.q_start_each ? p.q_start_each[(size_t)env * NQ + lane] : p.q_start[lane];
         // Kinematics::desiredOperationalState (invKinematics.cpp:11-25): feet poses, the current arm/head joints,
         // zero attitude, CoM
-        des[lane] = lane < 6 ? p.rf[(size_t)env * 6 + lane] : lane < 12 ? p.lf[(size_t)env * 6 + lane - 6]
-                  : lane < 24 ? p.q_start[18 + lane - 12] : lane < 27 ? 0.0 : p.com[(size_t)env * 3 + lane - 27];
+        if (p.desop) des[lane] = p.desop[(size_t)env * NQ + lane];
+        else des[lane] = lane < 6 ? p.rf[(size_t)env * 6 + lane] : lane < 12 ? p.lf[(size_t)env * 6 + lane - 6]
+                       : lane < 24 ? p.q_start[18 + lane - 12] : lane < 27 ? 0.0 : p.com[(size_t)env * 3 + lane - 27];
     }
     __syncwarp();
     const IkResult r = ik_solve_warp(w, *p.K, des, p.max_iter, lane);
@@ -262,6 +267,26 @@ __global__ void __launch_bounds__(128) ik_kernel(IkParams p) {
         p.iters[env] = r.iters; p.residual[env] = r.residual; p.status[env] = r.status;
         if (p.x) p.t[env] = 0.0;
     }
+}
+
+// Robot::updateState for a batch of postures: one warp per posture, four per block; dumps the world transforms and the
+// parent-relative transforms of the 27 frames as (R row-major, p) records plus the centre of mass.
+__global__ void __launch_bounds__(128) kin_kernel(const Consts* K, const double* q, double* Tw_out, double* Xl_out, double* com_out,
+                                                  int n, int env_bytes) {
+    extern __shared__ double smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * 4 + wid;
+    if (env >= n) return;
+    EnvWS& w = *reinterpret_cast<EnvWS*>(reinterpret_cast<char*>(smem) + (size_t)wid * env_bytes);
+    if (lane < NQ) w.q[lane] = q[(size_t)env * NQ + lane];
+    __syncwarp();
+    Ctx<32> cx{lane, 0};
+    fk_phase(cx, w, *K);
+    for (int i = lane; i < NF * 12; i += 32) {
+        if (Tw_out) Tw_out[(size_t)env * NF * 12 + i] = w.u.m.p.Tw[i];
+        if (Xl_out) Xl_out[(size_t)env * NF * 12 + i] = w.u.m.Xl[i];
+    }
+    if (com_out && lane < 3) com_out[(size_t)env * 3 + lane] = w.com[lane];
 }
 
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -301,7 +326,8 @@ struct LmhBatch {
     std::vector<double> h_zmp_x, h_zmp_y, h_foot;
     std::vector<int32_t> h_contact;
     bool has_pushes = false, has_plan_ids = false, has_order = false;
-    // scratch of lmh_ik_batch / lmh_qp_bench, kept between calls (grown on demand)
+    double* d_mpc = nullptr;            // dense MPC tables (PuT | L | LT | Dinv | DinvT | Px | rdiag), uploaded on first use
+    // scratch of lmh_ik_batch / lmh_qp_bench / lmh_kinematics / lmh_mpc_solve, kept between calls (grown on demand)
     double* d_scratch = nullptr;
     size_t scratch_bytes = 0;
 };
@@ -394,7 +420,7 @@ void lmh_default_config(LmhConfig* c) {
     for (int k = 0; k < 6; ++k) { c->rf[k] = s.rf[k]; c->lf[k] = s.lf[k]; }
     c->mu = s.mu; c->mpc_alpha = s.mpc_alpha; c->mpc_beta = s.mpc_beta;
     c->qp_max_iter = s.qp_max_iter;
-    c->threads_per_env = 0; c->device = 0; c->log_steps = 0; c->envs_per_block = 0; c->placement = 0;
+    c->threads_per_env = 0; c->device = 0; c->log_steps = 0; c->envs_per_block = 0; c->placement = 0; c->mpc_zcom = 0.0;
 }
 
 // everything of lmh_create that can fail after the handle exists: the caller destroys the handle on any error
@@ -465,6 +491,7 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
         for (int k = 0; k < 6; ++k) { s.rf[k] = cfg->rf[k]; s.lf[k] = cfg->lf[k]; }
         s.mu = cfg->mu; s.mpc_alpha = cfg->mpc_alpha; s.mpc_beta = cfg->mpc_beta;
         s.qp_max_iter = cfg->qp_max_iter > 0 ? cfg->qp_max_iter : 200;
+        s.mpc_zcom = cfg->mpc_zcom;
         h->hm = new HostModel(s);
     } catch (const std::exception& ex) {
         delete h;
@@ -487,7 +514,7 @@ void lmh_destroy(LmhBatch* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
     cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_order); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
-    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact); cudaFree(h->d_scratch);
+    cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact); cudaFree(h->d_scratch); cudaFree(h->d_mpc);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -523,6 +550,41 @@ int32_t lmh_get_link_tables(const LmhBatch* h, double* mass, double* com, double
         if (com) for (int k = 0; k < 3; ++k) com[3 * i + k] = K.mc[4 * i + k];
     }
     if (isp) std::memcpy(isp, K.Isp, sizeof(double) * 28 * 36);
+    return LMH_OK;
+}
+
+int32_t lmh_get_link_inertia(const LmhBatch* h, double* inertia) {
+    if (!h || !inertia) return fail(LMH_EINVAL, "lmh_get_link_inertia: bad arguments");
+    std::memcpy(inertia, h->hm->link_inertia, sizeof(double) * 28 * 9);
+    return LMH_OK;
+}
+
+int32_t lmh_get_nao_parameters(double* mass, double* com, double* inertia) {
+    for (int i = 0; i < 28; ++i) {
+        if (mass) mass[i] = kNaoLinks[i].m;
+        if (com) for (int k = 0; k < 3; ++k) com[3 * i + k] = kNaoLinks[i].c[k];
+        if (inertia) for (int k = 0; k < 9; ++k) inertia[9 * i + k] = kNaoLinks[i].I[k];
+    }
+    return LMH_OK;
+}
+
+int32_t lmh_local_transforms(const double* theta25, double* T25x16) {
+    if (!theta25 || !T25x16) return fail(LMH_EINVAL, "lmh_local_transforms: bad arguments");
+    for (int i = 0; i < 25; ++i) nao_local_transform(i, theta25[i], T25x16 + 16 * i);
+    return LMH_OK;
+}
+
+int32_t lmh_poly_fit(int32_t n_pos, const double* pos, int32_t n_vel, const double* vel, int32_t n_acc, const double* acc, double* coeff) {
+    if (n_pos < 0 || n_vel < 0 || n_acc < 0 || n_pos + n_vel + n_acc <= 0 || !coeff || (n_pos && !pos) || (n_vel && !vel) || (n_acc && !acc))
+        return fail(LMH_EINVAL, "lmh_poly_fit: bad arguments");
+    std::vector<double> pt, pv, vt, vv, at, av;
+    for (int i = 0; i < n_pos; ++i) { pt.push_back(pos[2 * i]); pv.push_back(pos[2 * i + 1]); }
+    for (int i = 0; i < n_vel; ++i) { vt.push_back(vel[2 * i]); vv.push_back(vel[2 * i + 1]); }
+    for (int i = 0; i < n_acc; ++i) { at.push_back(acc[2 * i]); av.push_back(acc[2 * i + 1]); }
+    try {
+        const std::vector<double> c = poly_fit(pt, pv, vt, vv, at, av);
+        std::memcpy(coeff, c.data(), c.size() * sizeof(double));
+    } catch (const std::exception& ex) { return fail(LMH_EINVAL, std::string("lmh_poly_fit: ") + ex.what()); }
     return LMH_OK;
 }
 
@@ -814,7 +876,7 @@ int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* r
     CU(cudaMemcpyAsync(d_in + N * 9, lf6, N * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_q0, h->hm->q0, NQ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     IkParams p;
-    p.K = h->dK; p.q_start = d_q0; p.com = d_in; p.rf = d_in + N * 3; p.lf = d_in + N * 9;
+    p.K = h->dK; p.q_start = d_q0; p.q_start_each = nullptr; p.desop = nullptr; p.com = d_in; p.rf = d_in + N * 3; p.lf = d_in + N * 9;
     p.q_out = d_q; p.iters = d_int; p.status = d_int + N; p.residual = d_res;
     p.x = apply_to_state ? h->d_x : nullptr; p.vh = h->d_vh; p.t = h->d_t;
     p.n = n; p.max_iter = 200;
@@ -837,6 +899,229 @@ int32_t lmh_ik_batch(LmhBatch* h, int32_t n, const double* com3, const double* r
         h->step_counter = 0;
     }
     return LMH_OK;
+}
+
+
+int32_t lmh_ik_solve(LmhBatch* h, int32_t n, const double* q_start, const double* desop, double* q_out, int32_t* iters,
+                     double* residual, int32_t* status) {
+    if (!h || n <= 0 || !desop) return fail(LMH_EINVAL, "lmh_ik_solve: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n;
+    // scratch: targets (30 N), starting postures (30 N), postures (30 N), residuals (N), nominal posture (30), integers (2 N)
+    int32_t rc0 = ensure_scratch(h, (N * 91 + NQ) * sizeof(double) + N * 2 * sizeof(int32_t));
+    if (rc0 != LMH_OK) return rc0;
+    double *d_des = h->d_scratch, *d_qs = d_des + N * NQ, *d_q = d_qs + N * NQ, *d_res = d_q + N * NQ, *d_q0 = d_res + N;
+    int32_t* d_int = reinterpret_cast<int32_t*>(d_q0 + NQ);
+    CU(cudaMemcpyAsync(d_des, desop, N * NQ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (q_start) CU(cudaMemcpyAsync(d_qs, q_start, N * NQ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_q0, h->hm->q0, NQ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    IkParams p;
+    p.K = h->dK; p.q_start = d_q0; p.q_start_each = q_start ? d_qs : nullptr; p.desop = d_des; p.com = nullptr; p.rf = nullptr; p.lf = nullptr;
+    p.q_out = d_q; p.iters = d_int; p.status = d_int + N; p.residual = d_res;
+    p.x = nullptr; p.vh = nullptr; p.t = nullptr;
+    p.n = n; p.max_iter = 200;
+    p.env_bytes = (int32_t)((sizeof(EnvWS) + 15) / 16 * 16);
+    CU(cudaFuncSetAttribute(ik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.env_bytes * 4));
+    ik_kernel<<<(n + 3) / 4, 128, (size_t)p.env_bytes * 4, h->stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    if (q_out) CU(cudaMemcpyAsync(q_out, d_q, N * NQ * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, d_int, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(cudaMemcpyAsync(status, d_int + N, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (residual) CU(cudaMemcpyAsync(residual, d_res, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LMH_OK;
+}
+
+int32_t lmh_kinematics(LmhBatch* h, int32_t n, const double* q, double* T, double* X, double* com) {
+    if (!h || n <= 0 || !q) return fail(LMH_EINVAL, "lmh_kinematics: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)n, rec = (size_t)NF * 12;
+    int32_t rc0 = ensure_scratch(h, N * (NQ + 2 * rec + 3) * sizeof(double));
+    if (rc0 != LMH_OK) return rc0;
+    double *d_q = h->d_scratch, *d_T = d_q + N * NQ, *d_X = d_T + N * rec, *d_c = d_X + N * rec;
+    CU(cudaMemcpyAsync(d_q, q, N * NQ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int env_bytes = (int)((sizeof(EnvWS) + 15) / 16 * 16);
+    CU(cudaFuncSetAttribute(kin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, env_bytes * 4));
+    kin_kernel<<<(n + 3) / 4, 128, (size_t)env_bytes * 4, h->stream>>>(h->dK, d_q, d_T, d_X, d_c, n, env_bytes);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    std::vector<double> hT(N * rec), hX(N * rec);
+    CU(cudaMemcpyAsync(hT.data(), d_T, N * rec * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(hX.data(), d_X, N * rec * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (com) CU(cudaMemcpyAsync(com, d_c, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // expand the (R, p) records: 4 x 4 homogeneous transforms and dense motion transforms [[E,0],[-E p^,E]], E = R'
+    // (velocityMatrix, generalizedFunctions.cpp:11-19); frame 27 = frame 26 times the constant DH transform of the extra
+    // head frame (theta = -pi/2, alpha = 0, r = 0, d = 0.030: Robot.cpp:84, 176-222)
+    const double kPi = 3.14159265358979323846;
+    const double c24 = std::cos(-kPi / 2), s24 = std::sin(-kPi / 2);
+    const double Rp27[12] = {c24, -s24, 0.0, s24, c24, 0.0, 0.0, 0.0, 1.0, 0.030, 0.0, 0.0};     // local transform of frame 27
+    for (size_t e = 0; e < N; ++e) {
+        for (int i = 0; i < 28; ++i) {
+            double Tw[12], Xr[12];
+            if (i < NF) {
+                std::memcpy(Tw, hT.data() + e * rec + 12 * i, sizeof(Tw));
+                std::memcpy(Xr, hX.data() + e * rec + 12 * i, sizeof(Xr));
+            } else {
+                const double* P = hT.data() + e * rec + 12 * 26;
+                for (int r = 0; r < 3; ++r) {
+                    for (int c = 0; c < 3; ++c) Tw[3 * r + c] = P[3 * r] * Rp27[c] + P[3 * r + 1] * Rp27[3 + c] + P[3 * r + 2] * Rp27[6 + c];
+                    Tw[9 + r] = P[3 * r] * Rp27[9] + P[3 * r + 1] * Rp27[10] + P[3 * r + 2] * Rp27[11] + P[9 + r];
+                }
+                // inverseTransformationMatrix(T26) * T27 (Robot.cpp:276-287), as the device does for the other frames
+                for (int r = 0; r < 3; ++r) {
+                    for (int c = 0; c < 3; ++c) Xr[3 * r + c] = P[r] * Tw[c] + P[3 + r] * Tw[3 + c] + P[6 + r] * Tw[6 + c];
+                    Xr[9 + r] = (P[r] * Tw[9] + P[3 + r] * Tw[10] + P[6 + r] * Tw[11]) - (P[r] * P[9] + P[3 + r] * P[10] + P[6 + r] * P[11]);
+                }
+            }
+            if (T) {
+                double* o = T + (e * 28 + i) * 16;
+                for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) o[4 * r + c] = Tw[3 * r + c]; o[4 * r + 3] = Tw[9 + r]; }
+                o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
+            }
+            if (X) {
+                double* o = X + (e * 28 + i) * 36;
+                for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) o[6 * a + b] = xdense(Xr, a, b);
+            }
+        }
+    }
+    return LMH_OK;
+}
+
+static int32_t upload_mpc_tables(LmhBatch* h) {
+    if (h->d_mpc) return LMH_OK;
+    const HostModel& m = *h->hm;
+    const size_t np = m.mpc_np, nt = np / 8;
+    const size_t total = 3 * np * np + 2 * nt * 64 + 2 * np + np;
+    CU(cudaMalloc(&h->d_mpc, total * sizeof(double)));
+    double* d = h->d_mpc;
+    const std::vector<double>* parts[7] = {&m.mpc_PuT, &m.mpc_L, &m.mpc_LT, &m.mpc_Dinv, &m.mpc_DinvT, &m.mpc_Px, &m.mpc_rdiag};
+    for (const auto* v : parts) {
+        CU(cudaMemcpy(d, v->data(), v->size() * sizeof(double), cudaMemcpyHostToDevice));
+        d += v->size();
+    }
+    return LMH_OK;
+}
+
+int32_t lmh_mpc_solve(LmhBatch* h, int32_t n, const double* com_xy, const double* vel_xy, const double* zmp_x,
+                      const double* zmp_y, double* xref, double* yref, int32_t use_dmma, int32_t repeats, double* elapsed_ms) {
+    if (!h || n <= 0 || !com_xy || !vel_xy || !zmp_x || !zmp_y || repeats < 1 || use_dmma < 0 || use_dmma > 1)
+        return fail(LMH_EINVAL, "lmh_mpc_solve: bad arguments");
+    CU(cudaSetDevice(h->cfg.device));
+    int32_t rc = upload_mpc_tables(h);
+    if (rc != LMH_OK) return rc;
+    const HostModel& m = *h->hm;
+    const size_t N = (size_t)n, n1 = (size_t)m.K.mpc_n1, np = (size_t)m.mpc_np, nt = np / 8;
+    rc = ensure_scratch(h, N * (4 + 2 * n1 + 6) * sizeof(double));
+    if (rc != LMH_OK) return rc;
+    double *d_com = h->d_scratch, *d_vel = d_com + 2 * N, *d_zx = d_vel + 2 * N, *d_zy = d_zx + N * n1, *d_xr = d_zy + N * n1, *d_yr = d_xr + 3 * N;
+    CU(cudaMemcpyAsync(d_com, com_xy, 2 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_vel, vel_xy, 2 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_zx, zmp_x, N * n1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_zy, zmp_y, N * n1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    MpcDev M;
+    M.PuT = h->d_mpc; M.L = M.PuT + np * np; M.LT = M.L + np * np; M.Dinv = M.LT + np * np; M.DinvT = M.Dinv + nt * 64;
+    M.Px = M.DinvT + nt * 64; M.rdiag = M.Px + 2 * np;
+    for (int k = 0; k < 4; ++k) M.A[k] = m.K.mpc_A[k];
+    M.B[0] = m.K.mpc_B[0]; M.B[1] = m.K.mpc_B[1];
+    M.n = (int32_t)n1; M.np = (int32_t)np;
+    MpcProblemSet P{d_com, d_vel, d_zx, d_zy, d_xr, d_yr, n};
+    CU(cudaEventRecord(h->ev0, h->stream));
+    if (use_dmma) {
+        const size_t smem = 4 * (np * 8 + 64) * sizeof(double);
+        CU(cudaFuncSetAttribute(mpc_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpc_dmma_kernel<<<(n + 15) / 16, 128, smem, h->stream>>>(M, P, repeats);
+    } else {
+        const size_t smem = 2 * np * 32 * sizeof(double);
+        CU(cudaFuncSetAttribute(mpc_dfma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpc_dfma_kernel<<<(n + 31) / 32, 64, smem, h->stream>>>(M, P, repeats);
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, h->stream));
+    h->launches += 1;
+    if (xref) CU(cudaMemcpyAsync(xref, d_xr, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (yref) CU(cudaMemcpyAsync(yref, d_yr, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    if (elapsed_ms) *elapsed_ms = f;
+    return LMH_OK;
+}
+
+int32_t lmh_get_mpc_tables(const LmhBatch* h, double* Px, double* Pu, int32_t cap, int32_t* n1) {
+    if (!h) return fail(LMH_EINVAL, "null handle");
+    const int n = h->hm->K.mpc_n1;
+    if (n1) *n1 = n;
+    if ((Px || Pu) && cap < n) return fail(LMH_EINVAL, "lmh_get_mpc_tables: capacity below horizon + 1");
+    if (Px) std::memcpy(Px, h->hm->mpc_Px_raw.data(), sizeof(double) * 2 * n);
+    if (Pu) std::memcpy(Pu, h->hm->mpc_Pu_raw.data(), sizeof(double) * (size_t)n * n);
+    return LMH_OK;
+}
+
+int32_t lmh_foot_coeff(const double* cur3, const double* des3, double step_height, double T, double* x6, double* y6, double* z8) {
+    if (!cur3 || !des3 || !(T > 0.0)) return fail(LMH_EINVAL, "lmh_foot_coeff: bad arguments");
+    double c[20];
+    try { foot_coefficients(cur3, des3, step_height, T, c); }
+    catch (const std::exception& ex) { return fail(LMH_EINVAL, std::string("lmh_foot_coeff: ") + ex.what()); }
+    if (x6) std::memcpy(x6, c, 6 * sizeof(double));
+    if (y6) std::memcpy(y6, c + 6, 6 * sizeof(double));
+    if (z8) std::memcpy(z8, c + 12, 8 * sizeof(double));
+    return LMH_OK;
+}
+
+int32_t lmh_push_plan(const int64_t* env_ids, int32_t n, uint64_t seed, double max_speed, int32_t max_step, int32_t* push_step,
+                      double* push_dv6) {
+    if (n < 0 || (n > 0 && (!env_ids || !push_step || !push_dv6)) || max_step < 0) return fail(LMH_EINVAL, "lmh_push_plan: bad arguments");
+    push_plan(env_ids, n, seed, max_speed, max_step, push_step, push_dv6);
+    return LMH_OK;
+}
+
+void lmh_default_walk_spec(LmhWalkSpec* s) {
+    WalkSpec d;
+    std::memset(s, 0, sizeof(*s));
+    s->n_footsteps = d.n_footsteps; s->horizon_steps = d.horizon_steps; s->tail_steps = d.tail_steps;
+    s->time_per_step = d.time_per_step; s->dt = d.dt; s->step_height = d.step_height; s->lateral = d.lateral;
+    s->min_len = d.min_len; s->max_len = d.max_len; s->fixed_len = -1.0;
+}
+
+static bool walk_spec_from(const LmhWalkSpec* s, WalkSpec& w) {
+    if (!s || s->n_footsteps < 0 || s->horizon_steps < 0 || s->tail_steps < 0 || !(s->time_per_step > 0.0) || !(s->dt > 0.0)) return false;
+    w.n_footsteps = s->n_footsteps; w.horizon_steps = s->horizon_steps; w.tail_steps = s->tail_steps;
+    w.time_per_step = s->time_per_step; w.dt = s->dt; w.step_height = s->step_height; w.lateral = s->lateral;
+    w.min_len = s->min_len; w.max_len = s->max_len;
+    return w.per() >= 1;
+}
+
+int32_t lmh_walk_plan_dims(const LmhWalkSpec* spec, int32_t* n_phases, int32_t* zmp_len) {
+    WalkSpec w;
+    if (!walk_spec_from(spec, w)) return fail(LMH_EINVAL, "lmh_walk_plan_dims: bad walk spec");
+    if (n_phases) *n_phases = w.n_phases();
+    if (zmp_len) *zmp_len = w.zmp_len();
+    return LMH_OK;
+}
+
+int32_t lmh_walk_plan(const LmhWalkSpec* spec, const int64_t* env_ids, int32_t n, uint64_t seed, double* zmp_x, double* zmp_y,
+                      double* foot_coef, int32_t* contact, double* step_len) {
+    WalkSpec w;
+    if (!walk_spec_from(spec, w) || n < 0 || (n > 0 && (!env_ids || !zmp_x || !zmp_y || !foot_coef || !contact)))
+        return fail(LMH_EINVAL, "lmh_walk_plan: bad arguments");
+    try { walk_plans(w, env_ids, n, seed, spec->fixed_len, zmp_x, zmp_y, foot_coef, contact, step_len); }
+    catch (const std::exception& ex) { return fail(LMH_EINVAL, std::string("lmh_walk_plan: ") + ex.what()); }
+    return LMH_OK;
+}
+
+int32_t lmh_make_walk_plans(LmhBatch* h, const LmhWalkSpec* spec, int64_t first_env_id, uint64_t seed) {
+    WalkSpec w;
+    if (!h || !walk_spec_from(spec, w)) return fail(LMH_EINVAL, "lmh_make_walk_plans: bad arguments");
+    const size_t E = (size_t)h->n_env, P = (size_t)w.n_phases(), Z = (size_t)w.zmp_len();
+    std::vector<int64_t> ids(E);
+    std::vector<int32_t> ct(E * P), pid(E);
+    std::vector<double> zx(E * Z), zy(E * Z), fc(E * P * 40);
+    for (size_t e = 0; e < E; ++e) { ids[e] = first_env_id + (int64_t)e; pid[e] = (int32_t)e; }
+    int32_t rc = lmh_walk_plan(spec, ids.data(), h->n_env, seed, zx.data(), zy.data(), fc.data(), ct.data(), nullptr);
+    if (rc != LMH_OK) return rc;
+    return lmh_set_walk_plans(h, h->n_env, (int32_t)Z, zx.data(), zy.data(), (int32_t)P, w.time_per_step, fc.data(), ct.data(), pid.data());
 }
 
 int32_t lmh_export_mujoco(int32_t n, const double* q30, double* qpos31) {

@@ -26,6 +26,7 @@ struct Scenario {                       // literals of apps/offline/main.cpp:13-
     double mu = 0.7;                    // controller.hpp:81
     double mpc_alpha = 1e-3, mpc_beta = 1.0;   // mpcLinearPendulum.hpp:47-48
     int qp_max_iter = 200;
+    double mpc_zcom = 0.0;              // 0 = CoM height after the inverse kinematics (main.cpp:39)
 };
 
 struct NaoLinkRow { double m; double c[3]; double I[9]; };
@@ -80,6 +81,23 @@ inline void foot_coefficients(const double cur[3], const double des[3], double s
     for (int i = 0; i < 8; ++i) out20[12 + i] = z[i];
 }
 
+// modified-DH rows of the 25 local transforms (Robot.cpp:176-196): 24 joints + the extra head frame
+inline void nao_dh_row(int i, double* r, double* d, double* alpha) {
+    const double h = 3.14159265358979323846 / 2;      // Robot.cpp:3
+    static const double R[25] = {-0.07071, 0, 0, 0, 0, 0, 0.07071, 0, 0, 0, 0, 0, 0, 0, 0.105, 0, 0.05595, 0, 0, 0.105, 0, 0.05595, 0, 0, 0};
+    static const double D[25] = {0, 0, 0, -0.1, -0.1029, 0, 0, 0, 0, -0.1, -0.1029, 0, 0, 0, -0.015, 0, 0, 0, 0, -0.015, 0, 0, 0, 0, 0.030};
+    const double AL[25] = {0, h, h, 0, 0, -h, -h, -h, h, 0, 0, -h, -h, h, h, -h, h, h, h, h, -h, h, 0, -h, 0};
+    *r = R[i]; *d = D[i]; *alpha = AL[i];
+}
+// one local transform (Khalil's modified DH, Robot.cpp:200-220), 4 x 4 row-major
+inline void nao_local_transform(int i, double theta, double* T16) {
+    double r, d, al;
+    nao_dh_row(i, &r, &d, &al);
+    const double ct = std::cos(theta), st = std::sin(theta), ca = std::cos(al), sa = std::sin(al);
+    const double T[16] = {ct, -st, 0.0, d, ca * st, ca * ct, -sa, -r * sa, sa * st, sa * ct, ca, r * ca, 0.0, 0.0, 0.0, 1.0};
+    std::memcpy(T16, T, sizeof(T));
+}
+
 class HostModel {
 public:
     Consts K;
@@ -87,6 +105,13 @@ public:
     double q0[NQ];
     int ik_iterations = 0;
     Scenario sc;
+    // dense form of the LIPM-MPC QP for the device-side dense solver (lmh_mpc.cuh), padded to np = 8 ceil(n / 8):
+    // beta Pu' (upper triangular), the Cholesky factor L of H = alpha I + beta Pu'Pu and its transpose, the inverses of
+    // its diagonal 8 x 8 blocks (and their transposes), 1 / diag(L), Px
+    std::vector<double> mpc_PuT, mpc_L, mpc_LT, mpc_Dinv, mpc_DinvT, mpc_rdiag, mpc_Px;
+    std::vector<double> mpc_Px_raw, mpc_Pu_raw;
+    double link_inertia[28 * 9];                     // inertia of every link about its CoM in the joint frame (Robot.cpp:14-22)      // Px [n][2], Pu [n][n] as Mpc3dLip::initialize builds them
+    int mpc_np = 0;
 
     explicit HostModel(const Scenario& s = Scenario()) : sc(s), ws_(new EnvWS) {
         std::memset(&K, 0, sizeof(K));
@@ -101,7 +126,7 @@ public:
         foot_coefficients(sc.rf, sc.rf, 0.0, sc.sim_time, foot_coef.data());
         foot_coefficients(sc.lf, sc.lf, 0.0, sc.sim_time, foot_coef.data() + 20);
         solve_initial_posture();
-        build_mpc_gain(ws_->com[2]);     // zCom = CoM height after IK (main.cpp:39)
+        build_mpc_gain(sc.mpc_zcom != 0.0 ? sc.mpc_zcom : ws_->com[2]);     // zCom = CoM height after IK (main.cpp:39)
     }
 
     // model phases of one configuration on the host (used by the IK and by tools)
@@ -125,12 +150,11 @@ private:
         const double kPi = 3.14159265358979323846;   // Robot.cpp:3
         const double h = kPi / 2;
         // modified-DH rows of the 24 joint transforms (Robot.cpp:180-196)
-        const double r[24] = {-0.07071, 0, 0, 0, 0, 0, 0.07071, 0, 0, 0, 0, 0, 0, 0, 0.105, 0, 0.05595, 0, 0, 0.105, 0, 0.05595, 0, 0};
-        const double d[24] = {0, 0, 0, -0.1, -0.1029, 0, 0, 0, 0, -0.1, -0.1029, 0, 0, 0, -0.015, 0, 0, 0, 0, -0.015, 0, 0, 0, 0};
-        const double al[24] = {0, h, h, 0, 0, -h, -h, -h, h, 0, 0, -h, -h, h, h, -h, h, h, h, h, -h, h, 0, -h};
+        (void)h;
         for (int i = 0; i < 24; ++i) {
-            K.dh_r[i] = r[i]; K.dh_d[i] = d[i];
-            K.dh_ca[i] = std::cos(al[i]); K.dh_sa[i] = std::sin(al[i]);   // cos(pi/2) residue kept, as upstream
+            double al;
+            nao_dh_row(i, &K.dh_r[i], &K.dh_d[i], &al);
+            K.dh_ca[i] = std::cos(al); K.dh_sa[i] = std::sin(al);   // cos(pi/2) residue kept, as upstream
             K.th_off[i] = 0.0;
         }
         K.th_off[1] = (3.0 / 4) * kPi; K.th_off[6] = -(1.0 / 2) * kPi; K.th_off[7] = (1.0 / 4) * kPi;   // Robot.cpp:59-87
@@ -168,6 +192,7 @@ private:
             for (int r3 = 0; r3 < 3; ++r3) for (int c = 0; c < 3; ++c) RtI[3 * r3 + c] = R[r3] * L.I[c] + R[3 + r3] * L.I[3 + c] + R[6 + r3] * L.I[6 + c];
             for (int r3 = 0; r3 < 3; ++r3) for (int c = 0; c < 3; ++c) Ij[3 * r3 + c] = RtI[3 * r3] * R[c] + RtI[3 * r3 + 1] * R[3 + c] + RtI[3 * r3 + 2] * R[6 + c];
             mass += L.m;
+            for (int k = 0; k < 9; ++k) link_inertia[9 * i + k] = Ij[k];
             K.mc[4 * i + 0] = cj[0]; K.mc[4 * i + 1] = cj[1]; K.mc[4 * i + 2] = cj[2]; K.mc[4 * i + 3] = L.m;
             // spatial inertia (Dynamics.cpp:4-13) for the torso and the actuated frames only (Dynamics.cpp:15-27)
             double* S = K.Isp + 36 * i;
@@ -274,6 +299,49 @@ private:
         K.mpc_n1 = n; K.mpc_dt = dt; K.mpc_zcom = zcom;
         for (int k = 0; k < 4; ++k) K.mpc_A[k] = A[k];
         K.mpc_B[0] = Bv[0]; K.mpc_B[1] = Bv[1];
+        build_mpc_dense(n, Px, Pu, H);
+        mpc_Px_raw = Px; mpc_Pu_raw = Pu;
+    }
+
+    // H = L L' (the reference hands H to qpOASES at every call, mpcLinearPendulum.cpp:89-90,111-133; H is constant)
+    void build_mpc_dense(int n, const std::vector<double>& Px, const std::vector<double>& Pu, const std::vector<double>& H) {
+        const int np = (n + 7) / 8 * 8;
+        mpc_np = np;
+        auto at = [np](int i, int j) { return (size_t)i * np + j; };
+        mpc_PuT.assign((size_t)np * np, 0.0); mpc_L.assign((size_t)np * np, 0.0); mpc_LT.assign((size_t)np * np, 0.0);
+        mpc_Px.assign((size_t)np * 2, 0.0); mpc_rdiag.assign(np, 1.0);
+        for (int i = 0; i < n; ++i) {
+            mpc_Px[2 * i] = Px[2 * i]; mpc_Px[2 * i + 1] = Px[2 * i + 1];
+            for (int k = 0; k < n; ++k) mpc_PuT[at(i, k)] = sc.mpc_beta * Pu[(size_t)k * n + i];
+        }
+        for (int i = 0; i < np; ++i) mpc_L[at(i, i)] = 1.0;
+        for (int j = 0; j < n; ++j) {                      // Cholesky, column by column
+            double d = H[(size_t)j * n + j];
+            for (int k = 0; k < j; ++k) d -= mpc_L[at(j, k)] * mpc_L[at(j, k)];
+            if (!(d > 0.0)) throw std::runtime_error("lmh: MPC Hessian is not positive definite");
+            const double ljj = std::sqrt(d);
+            mpc_L[at(j, j)] = ljj;
+            for (int i = j + 1; i < n; ++i) {
+                double s = H[(size_t)i * n + j];
+                for (int k = 0; k < j; ++k) s -= mpc_L[at(i, k)] * mpc_L[at(j, k)];
+                mpc_L[at(i, j)] = s / ljj;
+            }
+        }
+        for (int i = 0; i < np; ++i) {
+            mpc_rdiag[i] = 1.0 / mpc_L[at(i, i)];
+            for (int j = 0; j < np; ++j) mpc_LT[at(j, i)] = mpc_L[at(i, j)];
+        }
+        const int nt = np / 8;
+        mpc_Dinv.assign((size_t)nt * 64, 0.0); mpc_DinvT.assign((size_t)nt * 64, 0.0);
+        for (int t = 0; t < nt; ++t)                       // inverse of a lower-triangular 8 x 8 block by forward substitution
+            for (int c = 0; c < 8; ++c)
+                for (int r = c; r < 8; ++r) {
+                    double s = r == c ? 1.0 : 0.0;
+                    for (int k = c; k < r; ++k) s -= mpc_L[at(8 * t + r, 8 * t + k)] * mpc_Dinv[(size_t)64 * t + 8 * k + c];
+                    const double v = s / mpc_L[at(8 * t + r, 8 * t + r)];
+                    mpc_Dinv[(size_t)64 * t + 8 * r + c] = v;
+                    mpc_DinvT[(size_t)64 * t + 8 * c + r] = v;
+                }
     }
 
     static void euler_from(const double* R, const double* ref, double* eta) {   // invKinematics.cpp:257-267

@@ -236,6 +236,14 @@ void orc_sim_link_table(void* sp, double* mass, double* com, double* inertia) {
     }
 }
 
+void orc_sim_frames(void* sp, double* T, double* X) {
+    Sim* s = static_cast<Sim*>(sp);
+    for (int i = 0; i < NUM_FRAMES; ++i) {
+        if (T) std::memcpy(T + 16 * i, s->nao.T[i].d, sizeof(double) * 16);
+        if (X) std::memcpy(X + 36 * i, s->nao.X[i].d, sizeof(double) * 36);
+    }
+}
+
 void orc_sim_set_walk_plan(void* sp, int32_t zmp_len, const double* zx, const double* zy, int32_t n_phases, double phase_T,
                            const double* fc, const int32_t* contact) {
     Sim* s = static_cast<Sim*>(sp);

@@ -81,6 +81,8 @@ void orc_sim_mpc_tables(void* sim, double* Px, double* Pu, int32_t* horizon);
 void orc_sim_foot_coeffs(void* sim, double* r6x, double* r6y, double* r8z, double* l6x, double* l6y, double* l8z);
 int32_t orc_sim_zmp(void* sim, double* zx, double* zy, int32_t cap);
 void orc_sim_link_table(void* sim, double* mass28, double* com28x3, double* inertia28x9);
+/* Robot::getT / getX after the last updateState: world transforms [28][16] and parent-relative motion transforms [28][36], row-major */
+void orc_sim_frames(void* sim, double* T28x16, double* X28x36);
 
 /* Batch of independent environments split statically over n_threads host threads.
  * x0: E x 60 (or NULL = IK posture, zero velocity); push_step[e] (or <0 = none) and

@@ -92,6 +92,8 @@ class Lib:
         if hasattr(L, "orc_sim_set_walk_plan"):
             L.orc_sim_set_walk_plan.argtypes = [C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, f64, C.c_void_p, C.c_void_p]
             L.orc_sim_last_phase.argtypes = [C.c_void_p]
+        if hasattr(L, "orc_sim_frames"):
+            L.orc_sim_frames.argtypes = [C.c_void_p] * 3
         if hasattr(L, "orc_batch_rollout_ex"):
             L.orc_batch_rollout_ex.argtypes = [C.POINTER(OrcConfig), i32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -242,6 +244,12 @@ class Sim:
         zx, zy = np.zeros(100000), np.zeros(100000)
         n = self.lib.L.orc_sim_zmp(self.h, _p(zx), _p(zy), 100000)
         return zx[:n].copy(), zy[:n].copy()
+
+    def frames(self):
+        """Robot::getT / getX after the last updateState: (T [28][4][4], X [28][6][6])"""
+        T, X = np.zeros((28, 4, 4)), np.zeros((28, 6, 6))
+        self.lib.L.orc_sim_frames(self.h, _p(T), _p(X))
+        return T, X
 
     def link_table(self):
         m, c, I = np.zeros(28), np.zeros((28, 3)), np.zeros((28, 3, 3))

@@ -227,6 +227,14 @@ void orc_sim_link_table(void* sp, double* mass, double* com, double* inertia) {
     }
 }
 
+void orc_sim_frames(void* sp, double* T, double* X) {
+    RefSim* s = static_cast<RefSim*>(sp);
+    for (int i = 0; i < 28; ++i) {
+        if (T) cp(T + 16 * i, s->nao.getT()[(size_t)i]);
+        if (X) cp(X + 36 * i, s->nao.getX()[(size_t)i]);
+    }
+}
+
 int32_t orc_batch_rollout(const OrcConfig* cfg, int32_t E, const double* x0, const int32_t* push_step,
                           const double* push_dv, int32_t n_steps, int32_t n_threads, double* x_out,
                           double* com_out, double* stats) {

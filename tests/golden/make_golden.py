@@ -32,7 +32,7 @@ out.update(link_mass=m, link_com=c, link_inertia=I)
 rng = np.random.default_rng(20261018)
 KEYS = ["M", "C", "Cg", "AG", "AGpqp", "Jpqp", "JFeet", "CoM", "comVel", "comAngMom", "xRef", "yRef", "qppRef",
         "hGpRef", "footAccRef", "g", "qpp", "tau", "f", "T7", "T14", "xdot"]
-X, VH, T, dumps = [], [], [], {k: [] for k in KEYS + ["Ha", "a", "k_index", "qp_iters"]}
+X, VH, T, dumps = [], [], [], {k: [] for k in KEYS + ["Ha", "a", "k_index", "qp_iters", "T_all", "X_all"]}
 for i in range(12):
     x = x0.copy(); vh = np.zeros(30); t = 0.0
     if i:
@@ -45,6 +45,8 @@ for i in range(12):
     for k in KEYS: dumps[k].append(d[k])
     dumps["Ha"].append(d["H"][:30, :30]); dumps["a"].append(d["x"][:30])
     dumps["k_index"].append(d["k_index"]); dumps["qp_iters"].append(d["qp_iters"])
+    Tall, Xall = s.frames()                       # Robot::getT / getX: every world transform and parent-relative motion transform
+    dumps["T_all"].append(Tall); dumps["X_all"].append(Xall)
 out.update(stage_x=np.array(X), stage_vh=np.array(VH), stage_t=np.array(T))
 for k, v in dumps.items(): out["stage_" + k] = np.array(v)
 

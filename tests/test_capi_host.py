@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     assert api.STAGE_DTYPE.itemsize == 8 * n_dbl + 16
     assert api.STEPLOG_DTYPE.itemsize == 8 * (3 + 3 + 3 + 24) + 4 * 14
     assert api.STATS_DTYPE.itemsize == 8 * 3 + 4 * 6
-    assert C.sizeof(api.LmhConfig) == 8 * (3 + 3 + 6 + 6 + 3) + 4 * 6
+    assert C.sizeof(api.LmhConfig) == 8 * (3 + 3 + 6 + 6 + 3) + 4 * 6 + 8
 
 
 def test_default_config_is_the_reference_scenario():

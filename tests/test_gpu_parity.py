@@ -459,3 +459,98 @@ def test_grid_shape_changes_nothing():
             assert info["blocks"] == 151
         else:
             assert np.array_equal(x, ref[0][:E]) and np.array_equal(vh, ref[1][:E]) and np.array_equal(t, ref[2][:E])
+
+
+def test_kinematics_all_frames(golden, oracle):
+    """Robot::updateState on the device for a batch of postures (lmh_kinematics): EVERY world transform T_i and
+    parent-relative motion transform X_i (28 frames) against the reference vectors and, on further postures, the oracle"""
+    q = golden["stage_x"][:, :30]
+    b = lmh.Batch(2)
+    T, X, com = b.kinematics(q)
+    assert scalederr(T, golden["stage_T_all"]) < 1e-13 and scalederr(X, golden["stage_X_all"]) < 1e-13
+    assert np.abs(com - golden["stage_CoM"]).max() < 1e-14
+    assert (T[:, :, 3] == [0, 0, 0, 1]).all()
+    rng = np.random.default_rng(5)
+    q2 = golden["x0"][:30] + 0.3 * rng.standard_normal((7, 30))
+    T2, X2, com2 = b.kinematics(q2)
+    so = oracle.sim()
+    for i in range(7):
+        d = so.stage(np.concatenate([q2[i], np.zeros(30)]), 0.0)
+        To, Xo = so.frames()
+        assert scalederr(T2[i], To) < 1e-13 and scalederr(X2[i], Xo) < 1e-13 and np.abs(com2[i] - d["CoM"]).max() < 1e-14
+
+
+def test_mpc_dense_solver_on_the_device(oracle):
+    """N2: Mpc3dLip::compute as a DENSE solve per problem (gradient by a dense product, shared Cholesky factor, forward and
+    back substitution), FP64 FMA and FP64 tensor-core (DMMA) builds, against numpy's dense solve of the reference's own
+    formulation (Px, Pu from Mpc3dLip::initialize), against the oracle's Mpc3dLip, and against the gain-vector form the
+    closed-loop kernel uses.  Horizons of BASELINE configs[4] (16, 32, 64) plus the app's 50."""
+    rng = np.random.default_rng(11)
+    for N in (16, 32, 50, 64):
+        hz = N * 0.01 * (1.0 + 1e-9)                      # (int)(horizon / dt) == N as mpcLinearPendulum.hpp:49 computes it
+        b = lmh.Batch(2, time_horizon=hz)
+        Px, Pu = b.mpc_tables()
+        assert Px.shape == (N + 1, 2)
+        n = 37                                            # not a multiple of the 16 / 32 problems a block takes
+        com, vel = 0.05 * rng.standard_normal((n, 2)), 0.2 * rng.standard_normal((n, 2))
+        zx, zy = 0.03 * rng.standard_normal((n, N + 1)), 0.03 * rng.standard_normal((n, N + 1))
+        H = 1e-3 * np.eye(N + 1) + Pu.T @ Pu
+        A, B = np.array([[1, 0.01], [0, 1]]), np.array([0.01 ** 2 / 2, 0.01])
+        ref = np.zeros((2, n, 3))
+        for ax, z in enumerate((zx, zy)):
+            for i in range(n):
+                xk = np.array([com[i, ax], vel[i, ax]])
+                u = np.linalg.solve(H, -(Pu.T @ (Px @ xk - z[i])))
+                ref[ax, i] = np.concatenate([A @ xk + B * u[0], [u[0]]])
+        for dmma in (False, True):
+            xr, yr, ms = b.mpc_solve(com, vel, zx, zy, use_dmma=dmma)
+            assert np.abs(xr - ref[0]).max() < 1e-10 and np.abs(yr - ref[1]).max() < 1e-10, (N, dmma)
+            xr2, yr2, _ = b.mpc_solve(com, vel, zx, zy, use_dmma=dmma, repeats=3)     # repeats recompute from scratch
+            assert np.array_equal(xr, xr2) and np.array_equal(yr, yr2) and ms > 0
+        # the oracle's Mpc3dLip (dense factorisation at this horizon) through a stage evaluation at constant ZMP reference
+        so = oracle.sim(time_horizon=hz)
+        x0 = so.get_state()[0]
+        d = so.stage(x0, 0.0)
+        c0 = d["CoM"][:2]
+        xr, yr, _ = b.mpc_solve([c0], [[0.0, 0.0]], np.zeros((1, N + 1)), np.zeros((1, N + 1)), use_dmma=True)
+        assert np.abs(xr[0] - d["xRef"]).max() < 1e-10 and np.abs(yr[0] - d["yRef"]).max() < 1e-10
+        dg = b.stage()                                    # gain-vector form inside the closed-loop kernel
+        assert np.abs(dg["xRef"][0] - xr[0]).max() < 1e-10 and np.abs(dg["yRef"][0] - yr[0]).max() < 1e-10
+        b.close()
+    with pytest.raises(lmh.LmhError):
+        lmh.Batch(1).mpc_solve([[0, 0]], [[0, 0]], np.zeros((1, 7)), np.zeros((1, 7)))
+
+
+def test_general_inverse_kinematics_entry(ik_golden):
+    """lmh_ik_solve: full operational targets and per-target starting postures (Kinematics::desiredOperationalState +
+    compute as the class surface calls them)"""
+    g = ik_golden
+    n = len(g["q"])
+    b = lmh.Batch(1)
+    q0 = b.nominal()[0]
+    des = np.zeros((n, 30))
+    des[:, 0:6], des[:, 6:12], des[:, 12:24], des[:, 27:30] = g["rf"], g["lf"], q0[18:30], g["com"]
+    r = b.ik_solve(des)
+    assert (r["status"] == 0).all() and np.abs(r["q"] - g["q"]).max() < 2e-8
+    qi = np.array([-0.0185, 0, 0.282, 0, 0, 0, 0, 0, -0.5, 0.8, -0.3, 0, 0, 0, -0.5, 0.8, -0.3, 0, 1.6, 0, 0, 0, 0, -1.6, 0, 0, 0, 0, 0, 0])
+    r2 = b.ik_solve(des[:3], q_start=qi)                 # from Robot's initialConfiguration (Robot.cpp:242-251), as upstream does
+    assert (r2["status"] == 0).all() and np.abs(r2["q"] - g["q"][:3]).max() < 2e-8 and (r2["iters"] > 0).all()
+    des2 = des[:2].copy(); des2[:, 12] += 0.2             # a different arm target is honoured
+    r3 = b.ik_solve(des2)
+    assert (r3["status"] == 0).all() and np.abs(r3["q"][:, 18] - des2[:, 12]).max() < 1e-10
+
+
+def test_walk_plans_generated_inside_the_library(oracle):
+    """lmh_make_walk_plans (ZMP::walkZMP + per-phase foot plans behind the C ABI, keyed by the global environment id)
+    installs exactly what lmh_walk_plan returns: same rollouts bit for bit, for a shard that does not start at id 0"""
+    E, lo, S = 24, 1000, 60
+    wp = lmh.walk_plan(range(lo, lo + E), seed=0x5EED0003)
+    a = lmh.Batch(E, time_horizon=1.6)
+    a.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"], plan_ids=np.arange(E))
+    b = lmh.Batch(E, time_horizon=1.6)
+    b.make_walk_plans(first_env_id=lo, seed=0x5EED0003)
+    a.step(S); b.step(S)
+    assert np.array_equal(a.get_state()[0], b.get_state()[0])
+    assert not np.array_equal(a.get_state()[0][0], a.get_state()[0][1])          # the plans differ per environment
+    ws = lmh.walk_plan([7], fixed_len=0.035)                                       # ZMP(Task::Walk, ...): one nominal step length
+    assert ws["step_len"][0] == 0.035 and ws["zmp_x"][0].max() > 0.06
