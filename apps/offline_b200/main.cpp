@@ -1,61 +1,85 @@
-// The reference's offline app (apps/offline/main.cpp:12-122) rebuilt against the facade classes of
-// include/linearMpcHumanoid_b200/facade.hpp: same objects, same call order, same printed stream (CoM x per step,
-// main.cpp:86), every number computed on the GPU.  With "--fused N" the stand loop is replaced by the fused
-// batched rollout (one launch for all steps of N environments) -- what the library is for.
+// The offline app on the B200 library.  The reference's own apps/offline/main.cpp compiles UNCHANGED against
+// include/linearMpcHumanoid/** (tests/test_class_surface.py does exactly that); this file is the same program plus
+// what the reference does not have: "--fused N" replaces the host-driven stand loop (4 launches per RK4 step) by the
+// fused batched rollout -- one launch for all 500 steps of N environments -- and "--walk" runs the walking extension
+// (ZMP::walkZMP) through the same class surface.
 //
-//   g++ -O2 -std=c++17 -Iinclude apps/offline_b200/main.cpp -Llinearmpchumanoid_b200 -llmh_b200 -Wl,-rpath,$PWD/linearmpchumanoid_b200 -o offline_b200
-#include "linearMpcHumanoid_b200/facade.hpp"
+//   g++ -O2 -std=c++17 -Iinclude apps/offline_b200/main.cpp -Llinearmpchumanoid_b200 -llmh_b200
+//       -Wl,-rpath,$PWD/linearmpchumanoid_b200 -o offline_b200
+#include "linearMpcHumanoid/robotInfo/Robot.hpp"
+#include "linearMpcHumanoid/controller/controller.hpp"
+#include "linearMpcHumanoid/controller/invKinematics.hpp"
+#include "linearMpcHumanoid/controller/mpcLinearPendulum.hpp"
+#include "linearMpcHumanoid/general/Clock.hpp"
+#include "linearMpcHumanoid/general/Task.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-using namespace lmhb;
 
-static Vec dynamics(const Vec& state, double t, Robot& robot, Controller& controller) {   // main.cpp:91-122
+// the dynamics() closure of apps/offline/main.cpp:91-122
+static Eigen::VectorXd dynamics(const Eigen::VectorXd& state, double t, Robot& robot, Controller& controller) {
     const int n = robot.getNumJoints();
-    Vec q = state.segment(0, n), qD = state.segment(n, n);
+    Eigen::VectorXd q = state.segment(0, n), qD = state.segment(n, n);
     ControllerInput in;
     in.q = q; in.dq = qD; in.time = t;
     controller.standStep(in);
     WBCOutput out = controller.WBC(t);
-    Vec wxp = crossTimes(qD.segment(3, 3), q.segment(0, 3));
-    for (int k = 0; k < 3; ++k) qD[k] += wxp[k];
-    qD.setSegment(3, eulerRates(q.segment(3, 3), qD.segment(3, 3)));
-    Vec xp(2 * n);
-    xp.setSegment(0, qD);
-    xp.setSegment(n, out.qpp);
+    qD.segment(0, 3) += crossMatrix(qD.segment(3, 3)) * q.segment(0, 3);            // spatial -> classical linear velocity
+    qD.segment(3, 3) = matrixAngularVelToEulerDot(q.segment(3, 3)) * qD.segment(3, 3);   // angular velocity -> Euler rates
+    Eigen::VectorXd xp(2 * n);
+    xp.head(n) = qD;
+    xp.tail(n) = out.qpp;
     return xp;
 }
 
 int main(int argc, char** argv) {
-    double simulationTime = 5, timeStep = 0.01;
+    int fused = 0;
+    bool walk = false;
+    for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--fused") && i + 1 < argc) fused = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--walk")) walk = true;
+    }
+    const double simulationTime = walk ? 2.4 : 5, timeStep = 0.01;
     Robot nao;
     Kinematics ik;
     Clock clock(timeStep, simulationTime);
-    ZMP zmp(Task::Stand, simulationTime, timeStep, SupportFoot::Double);
-    Vec Rf = Vec::Zero(6), Lf = Vec::Zero(6), com{-0.02, 0.0, 0.26};
-    Rf[1] = -0.05; Lf[1] = 0.05;
-    Vec desOp = ik.desiredOperationalState(nao, Rf, Lf, com);
-    ik.compute(nao, desOp);
-    Mpc3dLip mpc(clock.getTimeStep(), 0.5, nao.getCoM()(2));
-    std::vector<Vec> rF = footCoeffTrajectory(Vec{0, -0.05, 0}, Vec{0, -0.05, 0}, 0, simulationTime);
-    std::vector<Vec> lF = footCoeffTrajectory(Vec{0, 0.05, 0}, Vec{0, 0.05, 0}, 0, simulationTime);
-    int fused = 0;
-    for (int i = 1; i + 1 < argc; ++i) if (!std::strcmp(argv[i], "--fused")) fused = std::atoi(argv[i + 1]);
-    Controller controller(nao, mpc, zmp, rF, lF, fused > 0 ? fused : 1);
+    ZMP zmp = walk ? ZMP(Task::Walk, 4, 0.4, simulationTime) : ZMP(Task::Stand, simulationTime, timeStep, SupportFoot::Double);
+    if (walk) zmp.walkZMP();
+    Eigen::VectorXd Rf = Eigen::VectorXd::Zero(6), Lf = Eigen::VectorXd::Zero(6);
+    Rf(1) = -0.05; Lf(1) = 0.05;
+    Eigen::Vector3d com(-0.02, 0.0, 0.26);
+    ik.compute(nao, ik.desiredOperationalState(nao, Rf, Lf, com));
+    Mpc3dLip mpc(clock.getTimeStep(), walk ? 1.6 : 0.5, nao.getCoM()(2));
+    std::vector<Eigen::VectorXd> rF = footCoeffTrajectory(Eigen::Vector3d(0, -0.05, 0), Eigen::Vector3d(0, -0.05, 0), 0, simulationTime);
+    std::vector<Eigen::VectorXd> lF = footCoeffTrajectory(Eigen::Vector3d(0, 0.05, 0), Eigen::Vector3d(0, 0.05, 0), 0, simulationTime);
     if (fused > 0) {
-        controller.rollout(500);
-        std::vector<double> c(3 * fused);
-        lmh_get_com(controller.batch(), c.data());
-        std::printf("%.6g\n", c[0]);
+        // the batched path: N environments, every one the scenario above, all steps in one launch
+        LmhConfig c;
+        lmh_default_config(&c);
+        c.time_horizon = mpc.getTimeHorizon(); c.mpc_zcom = mpc.getZCom();
+        LmhBatch* h = nullptr;
+        lmhf::check(lmh_create(&c, fused, &h), "offline_b200");
+        if (walk) {
+            LmhWalkSpec ws;
+            lmh_default_walk_spec(&ws);
+            lmhf::check(lmh_make_walk_plans(h, &ws, 0, 0x5EED0003), "offline_b200");
+        }
+        const int steps = (int)(simulationTime / timeStep + 0.5);
+        lmhf::check(lmh_step(h, steps), "offline_b200");
+        std::vector<double> cm(3 * (size_t)fused);
+        lmhf::check(lmh_get_com(h, cm.data()), "offline_b200");
+        std::printf("%.6g\n", cm[0]);
+        lmh_destroy(h);
         return 0;
     }
+    Controller controller(nao, mpc, zmp, rF, lF);
     const int n = nao.getNumJoints();
-    Vec state(2 * n);
-    state.setSegment(0, nao.getJoints());
-    state.setSegment(n, nao.getJointsVelocity());
-    while (std::fabs(clock.getTime() - clock.getSimulationTime()) > 0.01) {            // main.cpp:74
-        state = rk4Step([&](const Vec& x, double t) { return dynamics(x, t, nao, controller); }, state, clock.getTime(),
-                        clock.getTimeStep());
+    Eigen::VectorXd state(2 * n);
+    state.segment(0, n) = nao.getJoints();
+    state.segment(n, n) = nao.getJointsVelocity();
+    while (std::abs(clock.getTime() - clock.getSimulationTime()) > 0.01) {            // main.cpp:74
+        state = rk4Step([&](const Eigen::VectorXd& x, double t) { return dynamics(x, t, nao, controller); }, state,
+                        clock.getTime(), clock.getTimeStep());
         std::printf("%.6g\n\n", nao.getCoM()(0));                                        // main.cpp:86
         clock.step();
     }

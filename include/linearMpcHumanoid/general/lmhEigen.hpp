@@ -34,6 +34,7 @@ class Dense;
 class Block {
 public:
     Block(Dense& m, Index r0, Index c0, Index nr, Index nc) : m_(&m), r0_(r0), c0_(c0), nr_(nr), nc_(nc) {}
+    Block(const Block&) = default;
     Index rows() const { return nr_; }
     Index cols() const { return nc_; }
     Index size() const { return nr_ * nc_; }
