@@ -39,6 +39,9 @@ WORKLOADS = {"qp": "QP microbenchmark on frozen states (BASELINE configs[4])",
              "push": "NAO balance under random push perturbations (BASELINE configs[1])",
              "walk": "NAO LIPM-MPC walking, random footstep plans, 1.6 s horizon (BASELINE configs[2]; extension: upstream has no walking)",
              "sweep": "NAO walking robustness Monte Carlo: footstep plans + pushes (BASELINE configs[3]; extension)"}
+# per workload: environments per GPU, RK4 steps per rollout, scenario seed, MPC horizon in samples
+DEFAULTS = {"push": (4096, 200, 0x5EED0002, 50), "walk": (16384, 240, 0x5EED0003, 160), "sweep": (32768, 240, 0x5EED0004, 160),
+            "qp": (4096, 50, 0x5EED0002, 50)}
 FLOP_PER_ENV_STEP = 0.51e6          # SURVEY.md 8(d) / App. C, active-set changes k = 0 (conservative)
 STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 48 + 24   # state read+write, stats, CoM per launch
 # dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel from the committed ncu --set full capture (E = 4096;
@@ -220,7 +223,8 @@ def run_qp_microbench(args):
     cpu_stage_rate = n / (time.perf_counter() - t0)
     # condensed LIPM-MPC over the horizons BASELINE names (16-64 samples) on the same frozen states: evaluations/s and the
     # MPC outputs [pos+, vel+, u0] of both axes against the oracle's Mpc3dLip (dense Hessian solve) at that horizon
-    mpc_sweep = {}
+    mpc_sweep, RM = {}, 200
+    fp64_tf, _, _ = lmh.measure_fp64_peak(0)
     for N in (16, 32, 64):
         hz = N * b.cfg.dt * (1.0 + 1e-9)            # (int)(horizon / dt) == N, as mpcLinearPendulum.hpp:49 computes it
         bn = lmh.Batch(E, threads_per_env=args.threads_per_env, time_horizon=hz)
@@ -234,18 +238,31 @@ def run_qp_microbench(args):
             son.set_state(X[e], float(T[e]), VH[e])
             do = son.stage(X[e], float(T[e]))
             err = max(err, float(np.abs(dn["xRef"][e] - do["xRef"]).max()), float(np.abs(dn["yRef"][e] - do["yRef"]).max()))
-        mpc_sweep[str(N)] = {"evaluations_per_s": E * 4 * R / ((ms_m1 - ms_m0) * 1e-3) if ms_m1 > ms_m0 else float("nan"),
-                             "max_abs_err_refs_vs_oracle": err}
+        # the dense solver on the device (lmh_mpc_solve: gradient by a dense product, shared Cholesky factor, forward and
+        # back substitution per problem), FP64 FMA build and FP64 tensor-core (DMMA m8n8k4) build of the same algorithm
+        com, vel = np.ascontiguousarray(dn["CoM"][:, :2]), np.ascontiguousarray(dn["comVel"][:, :2])
+        zwin = np.zeros((E, N + 1))
+        dense = {}
+        for name, dm in (("dfma", False), ("dmma", True)):
+            bn.mpc_solve(com, vel, zwin, zwin, use_dmma=dm, repeats=2)
+            xr, yr, ms_d = bn.mpc_solve(com, vel, zwin, zwin, use_dmma=dm, repeats=RM)
+            _, _, ms_1 = bn.mpc_solve(com, vel, zwin, zwin, use_dmma=dm, repeats=1)
+            rate = E * (RM - 1) / ((ms_d - ms_1) * 1e-3)
+            flop = 8.0 * (N + 1) ** 2 + 8.0 * (N + 1)            # two axes, shared factor
+            dense[name] = {"qps_per_s": rate, "tflops": rate * flop / 1e12, "frac_of_fp64_peak": rate * flop / 1e12 / fp64_tf,
+                           "max_abs_err_vs_gain_form": float(max(np.abs(xr - dn["xRef"]).max(), np.abs(yr - dn["yRef"]).max()))}
+        mpc_sweep[str(N)] = {"gain_form_evaluations_per_s": E * 4 * R / ((ms_m1 - ms_m0) * 1e-3) if ms_m1 > ms_m0 else float("nan"),
+                             "dense_solve": dense, "max_abs_err_refs_vs_oracle": err}
         bn.close()
     line = {"metric": "WBC QP solves/sec (74 var, 18 eq, 32 ineq; cold start, frozen states)", "value": qps, "unit": "QPs/s",
             "n_gpus": 1, "steps": R, "warmup": 2, "ms_per_step": (ms_qp - ms_model) / (R - 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "QP microbenchmark on frozen states (BASELINE configs[4])", "envs": E,
                        "states": "config 2 at step 50", "repeats": R},
-            "mpc_evaluations_per_s": mpcs, "mpc_horizon_sweep": mpc_sweep, "max_rel_err_a_f_vs_oracle": worst, "oracle_sample_envs": n,
+            "mpc_gain_form_evaluations_per_s": mpcs, "mpc_horizon_sweep": mpc_sweep, "fp64_peak_tflops_builder_measured": fp64_tf, "max_rel_err_a_f_vs_oracle": worst, "oracle_sample_envs": n,
             "cpu_baseline": {"value": cpu_stage_rate, "unit": "stage evaluations/s (model + MPC + QP)", "cores": 1, "kind": "port",
                              "sample": f"{n} frozen states, oracle stage evaluation (its QP is ~85% of a stage)"},
-            "gpu_launches": 4 + 3 * 3}
+            "gpu_launches": 4 + 3 * (3 + 6)}
     _emit(line)
     b.close()
     return 0
@@ -269,15 +286,15 @@ def run_ours(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
 
     E, S, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 0)
+    seed = DEFAULTS[args.workload][2]
     lo = rank * E                                             # weak scaling: E envs per GPU, global ids lo..lo+E
     walk = args.workload in ("walk", "sweep")
     b = lmh.Batch(E, device=local_rank, threads_per_env=args.threads_per_env, **({"time_horizon": 1.6} if walk else {}))
     q0, zcom, mass, _ = b.nominal()
-    if walk:      # configs 3-4 (EXTENSION: the reference has no walking): per-env footstep plans, 1.6 s MPC horizon
-        wp = lmh.walk_plan(range(lo, lo + E))
-        b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"], plan_ids=np.arange(E))
+    if walk:      # configs 3-4 (EXTENSION: the reference has no walking): per-env footstep plans, 1.6 s MPC horizon,
+        b.make_walk_plans(first_env_id=lo, seed=seed)          # generated inside the library, keyed by the global env id
     if args.workload in ("push", "sweep"):
-        push_step, push_dv = lmh.push_plan(range(lo, lo + E), seed=0x5EED0002 if args.workload == "push" else 0x5EED0004)
+        push_step, push_dv = lmh.push_plan(range(lo, lo + E), seed=seed)
     else:
         push_step, push_dv = np.full(E, -1, np.int32), np.zeros((E, 6))
     b.set_pushes(push_step, push_dv)
@@ -375,7 +392,8 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         total_env_steps = world * E * S * K
         value = total_env_steps / (ms_total * 1e-3)
-        e2e_value = total_env_steps / (e2e_ms * 1e-3)
+        # end to end = host copies + rollouts + (N > 1) the final gather of the statistics, once per K rollouts' worth of work
+        e2e_value = total_env_steps / ((e2e_ms + (K * gather_ms if world > 1 else 0.0)) * 1e-3)
         ach_tf = FLOP_PER_ENV_STEP * E * S / (kern * 1e-3) / 1e12
         ach_gbs = STATE_BYTES_PER_ENV * E / (kern * 1e-3) / 1e9
         info = b.launch_info()
@@ -384,22 +402,24 @@ def run_ours(args):
             "steps": K, "warmup": max(W, 3), "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload],
-                       "envs_per_gpu": E, "rk4_steps_per_rollout": S, "stage_evals_per_env_step": 4, "seed": "0x5EED0002",
+                       "envs_per_gpu": E, "rk4_steps_per_rollout": S, "stage_evals_per_env_step": 4, "seed": hex(seed).upper().replace("X", "x"),
                        "push": "U(0,0.25) m/s on base v_xy at step U{0..50}" if args.workload != "walk" else "none",
                        "mpc_horizon": 160 if walk else 50, "dt": 0.01,
                        "threads_per_env": info["threads_per_env"], "smem_bytes_per_env": info["smem_bytes"],
                        "l2": "flushed (256 MiB write) before every timed rollout; working set is on-chip"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / K},
+                    "ms_per_step": e2e_ms / K + (gather_ms if world > 1 else 0.0),
+                    "includes_gather_ms": gather_ms if world > 1 else 0.0},
             "gpu_launches": launches,
             "batch1_step_latency_us": lat_us,
             "wall_ms_timed_region": wall_ms,
             "gather_ms": gather_ms,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE, "kernel": "rollout_kernel", "kernel_ms_per_launch": kern,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE, "kernel": "rollout_kernel_multi" if info["envs_per_block"] > 1 else "rollout_kernel", "kernel_ms_per_launch": kern,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
-                         "peak_source": "FP64 FMA micro-kernel measured in this run (lmh_measure_fp64_peak); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "peak_source": "BUILDER-MEASURED: FP64 FMA micro-kernel run in this process (lmh_measure_fp64_peak; "
+                                        "97 % of the nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2 TFLOP/s); "
+                                        "MEASURED_PEAKS.json has no FP64 entry and the profiling guide states no FP64 fallback",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"}},
             "clocks": clocks,
@@ -407,25 +427,40 @@ def run_ours(args):
                               "qp_iters_per_stage": float(all_stats[:, 3].sum() / (all_stats[:, 5].sum() * 4.0)),
                               "max_abs_tau": float(all_stats[:, 0].max()), "max_com_err": float(all_stats[:, 1].max())},
         }
-        if world == 1 and not args.no_cpu_baseline and args.workload == "push":
+        if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import orc_py
             orc_py.build()
             lib = orc_py.oracle()
             cores = os.cpu_count() or 1
-            n_cpu, s_cpu = 16 * cores, S          # a bounded sample: the first 16*cores envs, full rollout length
-            rate, dtc, x_cpu = cpu_rollout_rate(lib, "port", n_cpu, s_cpu, cores)
+            # a bounded sample of the SAME workload: the first n_cpu envs, full rollout length (the 1.6 s horizon makes an
+            # oracle stage about three times dearer, hence fewer envs for the walking workloads)
+            n_cpu, s_cpu = (16 if not walk else 4) * cores, S
+            wp = lmh.walk_plan(range(n_cpu), seed=seed) if walk else None
+            ps, dv = push_step[:n_cpu], push_dv[:n_cpu]
+            cfg = lib.default_config(second_wbc=0, mpc_rebuild_hessian=0, **({"time_horizon": 1.6} if walk else {}))
+            t0 = time.perf_counter()
+            r = lib.batch_rollout_ex(cfg, n_cpu, s_cpu, push_step=ps, push_dv=dv, walk=wp, n_threads=cores)
+            dtc = time.perf_counter() - t0
+            so = r["stats"]
+            rate = float(so["steps"].sum()) / dtc
             # the same envs on the GPU for the same number of steps: a live parity check beside the timing
-            b2 = lmh.Batch(n_cpu, device=local_rank, threads_per_env=args.threads_per_env)
-            ps, dv = lmh.push_plan(range(n_cpu))
+            b2 = lmh.Batch(n_cpu, device=local_rank, threads_per_env=args.threads_per_env, **({"time_horizon": 1.6} if walk else {}))
+            if walk:
+                b2.make_walk_plans(first_env_id=0, seed=seed)
             b2.set_pushes(ps, dv)
             b2.step(s_cpu)
             xg, _, _ = b2.get_state()
+            sg = b2.stats()
             b2.close()
+            both = (sg["alive"] == 1) & (so["alive"] == 1)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n_cpu} envs of the workload x {s_cpu} RK4 steps, {cores} host threads, {dtc:.1f} s",
                                     "note": "oracle port: one WBC solve per stage, cached MPC factor, -O2, no sanitizers",
-                                    "max_abs_state_diff_vs_gpu": float(np.abs(xg - x_cpu).max())}
+                                    "max_abs_state_diff_vs_gpu": float(np.abs(xg - r["x"])[both].max()) if both.any() else None,
+                                    "integer_stats_equal": bool(np.array_equal(sg["alive"], so["alive"]) and np.array_equal(sg["steps"], so["steps"])
+                                                                and np.array_equal(sg["qp_fail"], so["qp_fail"])),
+                                    "alive_in_sample": int(so["alive"].sum())}
         _emit(line)
     b.close()
     if world > 1:
@@ -451,12 +486,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
-    ap.add_argument("--rollout", type=int, default=200, help="RK4 steps per rollout (= per bench step)")
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: the workload's BASELINE size)")
+    ap.add_argument("--rollout", type=int, default=0, help="RK4 steps per rollout = per bench step (default: the workload's)")
     ap.add_argument("--threads-per-env", type=int, default=0)
     ap.add_argument("--workload", default="push", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.envs = args.envs or DEFAULTS[args.workload][0]
+    args.rollout = args.rollout or DEFAULTS[args.workload][1]
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_qp_microbench(args) if args.workload == "qp" else run_ours(args)

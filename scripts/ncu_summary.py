@@ -21,6 +21,11 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed_op_shared_ld.sum",
+        "smsp__inst_executed_op_shared_st.sum", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_fp64.sum", "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_op_dmma.sum", "smsp__inst_executed_pipe_tensor_op_dmma.sum",
         "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -47,11 +52,14 @@ for si, start in enumerate(sections):
     if "# Samples" not in h:
         continue
     iS, iI = h.index("# Samples"), h.index("Instructions Executed")
+    iW = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else None
+    iE = h.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in h else None
     lines = []
     for r in src[base:end]:
         if r and r[0].isdigit():
             try:
-                lines.append((int(r[0]), r[1], int(r[iS]), int(r[iI])))
+                lines.append((int(r[0]), r[1], int(r[iS]), int(r[iI]), int(r[iW] or 0) if iW is not None else 0,
+                              int(r[iE] or 0) if iE is not None else 0))
             except ValueError:
                 pass
     if not lines:
@@ -61,7 +69,7 @@ for si, start in enumerate(sections):
     funcs = [(n, m.group(1)) for n, l in enumerate(text, 1)
              for m in [re.match(r"(?:LMH_HDN?|__global__|__device__(?: __forceinline__)?)\s+.*?(\w+)\(", l)] if m]
     agg = {}
-    for ln, _, s, i in lines:
+    for ln, _, s, i, _w, _e in lines:
         k = bisect.bisect_right([f[0] for f in funcs], ln) - 1
         a = agg.setdefault(funcs[k][1] if k >= 0 else "?", [0, 0])
         a[0] += s; a[1] += i
@@ -69,5 +77,12 @@ for si, start in enumerate(sections):
     for name, (s, i) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         print(f"   {name:30s} samples {100 * s / ts:5.1f}%   instructions {100 * i / ti:5.1f}%", file=out)
     print("   hottest lines:", file=out)
-    for ln, t, s, i in sorted(lines, key=lambda l: -l[2])[:25]:
+    for ln, t, s, i, _w, _e in sorted(lines, key=lambda l: -l[2])[:25]:
         print(f"   {ln:5d} {100 * s / ts:5.1f}% {100 * i / ti:5.1f}%  {t.strip()[:100]}", file=out)
+    tw = sum(l[4] for l in lines)
+    if tw:
+        te = sum(l[5] for l in lines)
+        print(f"   shared-memory wavefronts: {tw} ({te} = {100 * te / tw:.1f}% excessive, i.e. bank conflicts); lines with the most:", file=out)
+        print("    line  wavefronts  of which excessive (bank conflicts)", file=out)
+        for ln, t, s, i, w_, e_ in sorted(lines, key=lambda l: -l[4])[:25]:
+            print(f"   {ln:5d} {100 * w_ / tw:5.1f}% {100 * e_ / tw:5.1f}%  {t.strip()[:100]}", file=out)

@@ -34,7 +34,7 @@ int main() {
     put("T7", nao.getT()[7]);
     put("T27", nao.getT()[27]);
     put("X5", nao.getX()[5]);
-    std::printf("parent14 %d actuated13 %d vertices %zu\n", nao.parentFrame()[14], nao.actuatedFrames()[13], nao.getFootVertices().size());
+    std::printf("tree %d %d %zu\n", nao.parentFrame()[14], nao.actuatedFrames()[13], nao.getFootVertices().size());
 
     Dynamics dyn;                                        // Dynamics.hpp:13-20 at the IK posture, zero velocity
     dyn.computeAll(nao);
@@ -93,7 +93,7 @@ int main() {
     std::printf("\n");
     // errors are exceptions, not silence
     int caught = 0;
-    try { ZMP tiny(Task::Stand, 0.1, 0.01, SupportFoot::Double); Controller bad(nao, mpc, tiny, rF, lF); } catch (const std::exception&) { ++caught; }
+    try { ZMP tiny(Task::Stand, 0.0, 0.01, SupportFoot::Double);   /* 50 samples < horizon + 1 */ Controller bad(nao, mpc, tiny, rF, lF); } catch (const std::exception&) { ++caught; }
     try { std::vector<Eigen::VectorXd> two(2); Controller bad(nao, mpc, zmp, two, lF); } catch (const std::exception&) { ++caught; }
     try { mpc.compute(pc, vc, zmp.getZmpXRef(), zmp.getZmpYRef(), 5.2); } catch (const std::exception&) { ++caught; }
     std::printf("caught %d\n", caught);

@@ -110,7 +110,7 @@ def test_class_surface_numbers(golden, probe):
     assert np.abs(p["com0"] - g["stage_CoM"][0]).max() < 1e-10
     assert scalederr(p["T7"].reshape(4, 4), g["stage_T_all"][0][7]) < 1e-9 and scalederr(p["T27"].reshape(4, 4), g["stage_T_all"][0][27]) < 1e-9
     assert scalederr(p["X5"].reshape(6, 6), g["stage_X_all"][0][5]) < 1e-9
-    assert list(p["parent14"]) == [13] or p["parent14"][0] == 13
+    assert list(p["tree"]) == [13, 12, 4]
     # Dynamics / Kinematics getters at the IK posture (the posture itself agrees to 1e-9, so do the terms)
     for k, shape in (("M", (30, 30)), ("C", 30), ("Cg", 30), ("AG", (6, 30)), ("AGpqp", 6), ("Jpqp", 12), ("JFeet", (12, 30))):
         assert scalederr(p[k].reshape(shape), g["stage_" + k][0]) < 1e-8, k
