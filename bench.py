@@ -378,11 +378,15 @@ def run_ours(args):
     gather_ms = 1e3 * (time.perf_counter() - tg)
 
     if rank == 0:
-        # batch-1 step latency (BASELINE metric, config 1): one environment, fused rollout, device time per RK4 step
-        b1 = lmh.Batch(1, device=local_rank, threads_per_env=args.threads_per_env)
-        b1.step(20)
-        lat_us = min(b1.step_timed(200) for _ in range(3)) / 200 * 1e3
-        b1.close()
+        # batch-1 step latency (BASELINE metric, config 1): one environment, fused rollout, device time per RK4 step, for
+        # the one-warp kernel (the default) and the generic 64- and 128-thread-per-environment kernels
+        lat = {}
+        for nt in (32, 64, 128):
+            b1 = lmh.Batch(1, device=local_rank, threads_per_env=nt)
+            b1.step(20)
+            lat[str(nt)] = min(b1.step_timed(200) for _ in range(3)) / 200 * 1e3
+            b1.close()
+        lat_us = lat[str(args.threads_per_env or 32)]
         fp64_tf, sm_mhz_attr, sms = lmh.measure_fp64_peak(local_rank)
         peaks = {}
         try:
@@ -411,7 +415,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / K + (gather_ms if world > 1 else 0.0),
                     "includes_gather_ms": gather_ms if world > 1 else 0.0},
             "gpu_launches": launches,
-            "batch1_step_latency_us": lat_us,
+            "batch1_step_latency_us": lat_us, "batch1_step_latency_us_by_threads_per_env": lat,
             "wall_ms_timed_region": wall_ms,
             "gather_ms": gather_ms,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,

@@ -44,6 +44,9 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+#ifndef LMH_GRAM_DMMA
+#define LMH_GRAM_DMMA 1     // 1: the 10 x 30 x 10 Gram product of the QP front end on the FP64 tensor cores (one-warp path)
+#endif
 #ifndef LMH_WARP_WRENCH
 #define LMH_WARP_WRENCH 1
 #endif
@@ -988,6 +991,30 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         }
     }
     // Gram matrix of the rows: Gm[r][c] = [.]_r D^-1 [.]_c'
+#if defined(__CUDA_ARCH__) && LMH_GRAM_DMMA
+    if (Cx::NT == 32) {
+        // 10 x 30 times 30 x 10 on the FP64 tensor cores: three 8 x 8 tiles (the lower triangle of the 16 x 16 padded
+        // product), eight k-steps of mma.sync m8n8k4 each.  Yt serves as A (row-major) and, read the same way, as B (= Yt').
+        const int lane = cx.tid, fr = lane >> 2, fk = lane & 3;
+        double t00a = 0, t00b = 0, t10a = 0, t10b = 0, t11a = 0, t11b = 0;
+        LMH_UNROLL
+        for (int kt = 0; kt < 8; ++kt) {
+            const int m = 4 * kt + fk;
+            const double y0 = m < NQ ? Yt[NQ * fr + m] : 0.0;
+            const double y1 = (m < NQ && fr < NYR - 8) ? Yt[NQ * (8 + fr) + m] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t00a), "+d"(t00b) : "d"(y0), "d"(y0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t10a), "+d"(t10b) : "d"(y1), "d"(y0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t11a), "+d"(t11b) : "d"(y1), "d"(y1));
+        }
+        const int c0 = 2 * fk;
+        Gm[NYR * fr + c0] = t00a; Gm[NYR * fr + c0 + 1] = t00b;
+        if (fr < NYR - 8) {
+            Gm[NYR * (8 + fr) + c0] = t10a; Gm[NYR * (8 + fr) + c0 + 1] = t10b;
+            Gm[NYR * c0 + 8 + fr] = t10a; Gm[NYR * (c0 + 1) + 8 + fr] = t10b;
+            if (fk == 0) { Gm[NYR * (8 + fr) + 8] = t11a; Gm[NYR * (8 + fr) + 9] = t11b; }
+        }
+    } else
+#endif
     LMH_FOR(it, NYR * (NYR + 1) / 2) {
         // unrank the lower-triangular index (55 entries): 8 it + 1 = (2r + 1)^2 at the start of row r, exact in float
         const int r = (int)((sqrtf(8.0f * (float)it + 1.0f) - 1.0f) * 0.5f);

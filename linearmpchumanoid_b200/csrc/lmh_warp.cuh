@@ -53,6 +53,9 @@ __device__ __forceinline__ double cross3_sel(const double* a, const double* b, i
 #define LMH_XSTRIDE 6      // doubles between the chains' slots in the exchange buffers: 6 = lane order (lane 6c + r writes word
                            // 6c + r: no bank conflicts), 8 = one 64-byte line per chain
 #endif
+#ifndef LMH_JTJ_DMMA
+#define LMH_JTJ_DMMA 1     // 1: J'J of the sole Jacobians (the J'W_F J term of the QP Hessian) on the FP64 tensor cores
+#endif
 #ifndef LMH_BCAST64
 #define LMH_BCAST64 0      // 1: chain-broadcast six-vectors / transforms through LDS.64 (one wavefront each) instead of LDS.128
 #endif
@@ -556,6 +559,72 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
     const bool isbase = lane >= 12 && lane < ND1;
 #pragma unroll
     for (int j = 0; j < ND1; ++j) h[j] = 0.0;
+#if LMH_JTJ_DMMA
+    {
+        // J_f'J_f of both feet on the FP64 tensor cores (controller.cpp:94-123: the J'W_F J term of the Hessian).  J_f is
+        // 6 x 12 in compact columns [base 0..5 | that leg's joints 6..11]; the 12 x 12 product is three 8 x 8 tiles of the
+        // lower triangle (k = 6 -> two k-steps of m8n8k4), J_f serving as A (transposed on the fly) and as B.  The tiles
+        // go to shared memory and every row owner then picks its row of D1 in factor order.
+        double* Gs = w.u.s.Bm;                            // [2][12][12] (Bm | Pm | Wb | Ay are contiguous and free here)
+        const int fr = lane >> 2, fk = lane & 3, c0 = 2 * fk;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const double* J = w.JFc + 72 * f;
+            double t00a = 0, t00b = 0, t10a = 0, t10b = 0, t11a = 0, t11b = 0;
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const int k = 4 * kt + fk;
+                const double a0 = k < 6 ? J[12 * k + fr] : 0.0;
+                const double a1 = (k < 6 && fr < 4) ? J[12 * k + 8 + fr] : 0.0;
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t00a), "+d"(t00b) : "d"(a0), "d"(a0));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t10a), "+d"(t10b) : "d"(a1), "d"(a0));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t11a), "+d"(t11b) : "d"(a1), "d"(a1));
+            }
+            double* G = Gs + 144 * f;
+            G[12 * fr + c0] = t00a; G[12 * fr + c0 + 1] = t00b;
+            if (fr < 4) {
+                G[12 * (8 + fr) + c0] = t10a; G[12 * (8 + fr) + c0 + 1] = t10b;
+                G[12 * c0 + 8 + fr] = t10a; G[12 * (c0 + 1) + 8 + fr] = t10b;
+                if (fk < 2) { G[12 * (8 + fr) + 8 + c0] = t11a; G[12 * (8 + fr) + 8 + c0 + 1] = t11b; }
+            }
+        }
+        __syncwarp();
+        if (mrow) {
+            const double wF = K.wFoot;
+            if (!isbase) {                                  // leg rows: the leg-leg block of that foot
+                const int f = lane < 6 ? 0 : 1;
+                const double* Gr = Gs + 144 * f + 12 * (6 + lane - 6 * f) + 6;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const double v = wF * Gr[c];
+                    h[c] = dsel(lane < 6, v, 0.0);
+                    h[6 + c] = v;                           // read by the left-leg rows only
+                }
+            } else {                                        // base rows: base-leg blocks of both feet, base-base block summed
+                const int b = lane - 12;
+                const double* G0 = Gs + 12 * b;
+                const double* G1 = Gs + 144 + 12 * b;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    h[c] = wF * G0[6 + c];
+                    h[6 + c] = wF * G1[6 + c];
+                    h[12 + c] = wF * (G0[c] + G1[c]);
+                }
+            }
+        }
+    }
+    if (!mrow && yrow) {
+        // row yr of [M6; ga'; U]: a pointer and a scale per lane, no per-entry branching
+        const double* src = yr < 6 ? w.M6 + NQ * yr : yr == 6 ? w.ga : w.AG + NQ * (yr - 4);
+        const double sc = yr < 7 ? 1.0 : K.sq_wCoML;
+        const double sc2 = sc * K.isq_wJoints;
+#pragma unroll
+        for (int j = 0; j < ND1; ++j) h[j] = sc * src[j < 12 ? j + 6 : j - 12];
+#pragma unroll
+        for (int j = ND1; j < NQ; ++j) Yt[NQ * yr + j] = sc2 * src[j];     // the arm/head part needs no solve
+    }
+    __syncwarp();
+#else
     if (mrow) {
         // Only the lower triangle is ever read (row p: columns <= p).  Two passes of 6 columns x 6 terms per lane:
         // pass 0 against the base block of a foot (a leg row's result is its piece of the base-leg block, which the
@@ -611,6 +680,7 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
 #pragma unroll
         for (int c = 0; c < 12; ++c) h[c] = Xbl[6 * c + bcol];
     }
+#endif
     if (mrow) {
         const int o = qp_orig(lane);
         const double wj = o < 3 ? K.wBasePos : o < 6 ? K.wBaseAng : K.wJoints;
