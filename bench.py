@@ -381,12 +381,13 @@ def run_ours(args):
         # batch-1 step latency (BASELINE metric, config 1): one environment, fused rollout, device time per RK4 step, for
         # the one-warp kernel (the default) and the generic 64- and 128-thread-per-environment kernels
         lat = {}
-        for nt in (32, 64, 128):
-            b1 = lmh.Batch(1, device=local_rank, threads_per_env=nt)
+        for name, kw in (("32", dict(threads_per_env=32)), ("64", dict(threads_per_env=64)), ("128", dict(threads_per_env=128)),
+                         ("32+2 helper warps (latency mode)", dict(threads_per_env=32, envs_per_block=-1))):
+            b1 = lmh.Batch(1, device=local_rank, **kw)
             b1.step(20)
-            lat[str(nt)] = min(b1.step_timed(200) for _ in range(3)) / 200 * 1e3
+            lat[name] = min(b1.step_timed(200) for _ in range(3)) / 200 * 1e3
             b1.close()
-        lat_us = lat[str(args.threads_per_env or 32)]
+        lat_us = lat["32+2 helper warps (latency mode)"]
         fp64_tf, sm_mhz_attr, sms = lmh.measure_fp64_peak(local_rank)
         peaks = {}
         try:

@@ -46,7 +46,11 @@ typedef struct {
     int32_t device;        /* CUDA device ordinal */
     int32_t log_steps;     /* capacity of the per-step log (0 = no log) */
     int32_t envs_per_block;/* one-warp environments per thread block of the fused rollout (threads_per_env = 32 only):
-                              0 = as many as the shared memory holds (the default), else 1..that many */
+                              0 = as many as the shared memory holds (the default: the throughput kernel, results
+                              independent of batch size and sharding bit for bit), 1..that many = fewer;
+                              -1 = LATENCY MODE for a handful of environments: one environment per block plus two helper
+                              warps (RNEA, CRBA and the sole Jacobians side by side): 64 instead of 77 us per RK4 step
+                              at one environment; agrees with the default to rounding, not bit for bit */
     int32_t placement;     /* 0 = lmh_set_pushes places environments that are pushed at the same step in the same
                               block (default; results do not depend on it), 1 = keep the index order */
     double mpc_zcom;       /* Mpc3dLip's zCoM argument (mpcLinearPendulum.hpp:13-16); 0 = the CoM height after the inverse

@@ -171,6 +171,80 @@ __global__ void __launch_bounds__(32 * kMaxEpb, 1) rollout_kernel_multi(Params p
     }
 }
 
+// Latency mode (LmhConfig.envs_per_block = -1, meant for a handful of environments): one environment per block of three
+// warps.  Warp 0 is the environment's warp and runs the whole step; while it runs the RNEA, warp 1 computes the CRBA and
+// warp 2 the sole Jacobians (the three only read the transforms; their outputs and scratch are disjoint): 64 us instead
+// of 77 us per RK4 step of a single environment.  Every phase is the same source on the same data, but this is another
+// kernel: the compiler contracts a few sums of products differently, so results agree with the throughput kernel to
+// rounding (1e-12 after 50 pushed steps), not bit for bit -- which is why it is opt-in and the default path is one kernel
+// for every batch size (sharding invariance is bit exact).
+__global__ void __launch_bounds__(96, 1) rollout_kernel_helpers(Params p, int env_bytes, int tab_doubles) {
+    extern __shared__ double smem[];
+    EnvWS& w = *reinterpret_cast<EnvWS*>(smem);
+    double* x = smem + (sizeof(EnvWS) + 7) / 8;
+    double* kacc = x + 60;
+    const int env = blockIdx.x;
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (env >= p.n_env) return;
+    const Consts& K = *p.K;
+    // the same block-shared tables as the throughput kernel, so that both run the same instantiation of every phase
+    // (Ctx<32, true>): identical arithmetic, bit for bit
+    double* tab = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + env_bytes);
+    for (int i = threadIdx.x; i < 28 * 36; i += blockDim.x) tab[i] = K.Isp[i];
+    for (int i = threadIdx.x; i < 120; i += blockDim.x) tab[kTabDh + i] = K.th_off[i];
+    for (int i = threadIdx.x; i < tab_doubles - kTabMpc; i += blockDim.x) tab[kTabMpc + i] = K.mpc_r[i];
+    __syncthreads();
+    if (wid != 0) {
+        const LaneRole L = lane_role(lane);
+        for (int s = 0; s < p.n_steps; ++s) {
+            asm volatile("bar.sync 1, 96;" ::: "memory");
+            if (w.dead != 0) continue;
+            for (int stage = 0; stage < 4; ++stage) {
+                asm volatile("bar.sync 2, 96;" ::: "memory");
+                if (wid == 1) crba_warp(w, K, tab, L, lane); else jacobian_warp(w, lane);
+                asm volatile("bar.sync 3, 96;" ::: "memory");
+            }
+        }
+        return;
+    }
+    Ctx<32, true> cx{lane, 0};
+    cx.isp = tab; cx.dh = tab + kTabDh;
+    if (tab_doubles > kTabMpc) cx.mpc_r = tab + kTabMpc;
+    ws_reset(cx, w);
+    for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
+    for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
+    double t = p.t[env];
+    const int plan_id = p.plan_id ? p.plan_id[env] : 0;
+    const int push_at = p.push_step ? p.push_step[env] : -1;
+    StatsAcc st;
+    {
+        const LmhStats& s0 = p.stats[env];
+        st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
+        st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
+        if (lane == 0) w.dead = s0.alive ? 0 : 1;
+    }
+    cx.sync();
+    cx.helpers = 96;
+    for (int s = 0; s < p.n_steps; ++s) {
+        const int gstep = p.step0 + s;
+        if (gstep == push_at && w.dead == 0) {
+            for (int k = lane; k < 6; k += 32) x[30 + k] += p.push_dv[(size_t)env * 6 + k];
+            cx.sync();
+        }
+        LmhStepLog* lg = (p.log && gstep < p.log_cap) ? p.log + (size_t)gstep * p.n_env + env : nullptr;
+        rk4_step(cx, w, x, kacc, t, K, p.plan, plan_id, lg, &st);
+    }
+    for (int i = lane; i < 60; i += 32) p.x[(size_t)env * 60 + i] = x[i];
+    for (int i = lane; i < 30; i += 32) p.vh[(size_t)env * 30 + i] = w.vh[i];
+    for (int i = lane; i < 3; i += 32) p.com[(size_t)env * 3 + i] = w.com[i];
+    if (lane == 0) {
+        p.t[env] = t;
+        LmhStats& s1 = p.stats[env];
+        s1.max_abs_tau = st.max_tau; s1.max_com_err = st.max_err; s1.max_abs_qpp = st.max_qpp;
+        s1.qp_iters = st.qp_iters; s1.qp_fail = st.qp_fail; s1.steps = st.steps; s1.alive = st.alive; s1.qp_fallback = st.qp_fallback; s1.pad = 0;
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) stage_kernel(Params p) {
     extern __shared__ double smem[];
@@ -326,6 +400,7 @@ struct LmhBatch {
     std::vector<double> h_zmp_x, h_zmp_y, h_foot;
     std::vector<int32_t> h_contact;
     bool has_pushes = false, has_plan_ids = false, has_order = false;
+    bool small_batch = false;           // latency mode: one block of three warps per environment
     double* d_mpc = nullptr;            // dense MPC tables (PuT | L | LT | Dinv | DinvT | Px | rdiag), uploaded on first use
     // scratch of lmh_ik_batch / lmh_qp_bench / lmh_kinematics / lmh_mpc_solve, kept between calls (grown on demand)
     double* d_scratch = nullptr;
@@ -392,13 +467,15 @@ int32_t launch_rollout(LmhBatch* h, int32_t n_steps) {
     Params p = make_params(h);
     p.n_steps = n_steps;
     dim3 grid(h->n_env), block(h->nt);
-    if (h->nt == 32 && h->epb > 1) {
+    if (h->nt == 32 && h->small_batch) {
+        rollout_kernel_helpers<<<grid, 96, (size_t)h->smem + (size_t)h->tab_doubles * sizeof(double), h->stream>>>(p, h->smem, h->tab_doubles);
+    } else
+    if (h->nt == 32) {
         int n_full = 0;
         const int nblk = multi_grid(h, &n_full);
         rollout_kernel_multi<<<nblk, 32 * h->epb, (size_t)h->smem * h->epb + (size_t)h->tab_doubles * sizeof(double), h->stream>>>(p, h->epb, h->smem, h->tab_doubles, n_full);
     } else
-    if (h->nt == 32) rollout_kernel<32><<<grid, block, h->smem, h->stream>>>(p);
-    else if (h->nt == 64) rollout_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
+    if (h->nt == 64) rollout_kernel<64><<<grid, block, h->smem, h->stream>>>(p);
     else rollout_kernel<128><<<grid, block, h->smem, h->stream>>>(p);
     CU(cudaGetLastError());
     h->step_counter += n_steps;
@@ -431,8 +508,11 @@ static int32_t create_on_device(LmhBatch* h, const LmhConfig* cfg, int32_t n_env
     const int epb_max = std::min(kMaxEpb, (kMaxDynSmem - kTabMpc * 8) / h->smem);
     h->epb = cfg->envs_per_block > 0 ? cfg->envs_per_block : epb_max;
     if (h->nt != 32) h->epb = 1;
+    // latency mode (envs_per_block = -1): one environment per block, two helper warps
+    h->small_batch = h->nt == 32 && cfg->envs_per_block == -1;
+    if (h->small_batch) CU(cudaFuncSetAttribute(rollout_kernel_helpers, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     if (h->epb > epb_max) return fail(LMH_EINVAL, "lmh_create: envs_per_block exceeds what the shared memory holds");
-    if (h->epb > 1) {
+    if (h->nt == 32) {
         // block-shared constant tables behind the slices, as far as the 227 KB allow: Isp + DH (9 KB), then the MPC gains
         const int64_t slices = (int64_t)h->smem * h->epb;
         const int n1 = h->hm->K.mpc_n1;
@@ -477,7 +557,7 @@ int32_t lmh_create(const LmhConfig* cfg, int32_t n_env, LmhBatch** out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(LMH_EINVAL, "lmh_create: device ordinal out of range");
     const int nt = cfg->threads_per_env == 0 ? 32 : cfg->threads_per_env;
     if (nt != 32 && nt != 64 && nt != 128) return fail(LMH_EINVAL, "lmh_create: threads_per_env must be 32, 64 or 128");
-    if (cfg->envs_per_block < 0 || cfg->placement < 0 || cfg->placement > 1 || cfg->log_steps < 0)
+    if (cfg->envs_per_block < -1 || cfg->placement < 0 || cfg->placement > 1 || cfg->log_steps < 0)
         return fail(LMH_EINVAL, "lmh_create: envs_per_block / placement / log_steps out of range");
     CU(cudaSetDevice(cfg->device));
     LmhBatch* h = new LmhBatch;
@@ -1145,7 +1225,7 @@ int32_t lmh_launch_info(const LmhBatch* h, int32_t* nt, int32_t* epb, int32_t* s
     if (nt) *nt = h->nt;
     if (epb) *epb = h->epb;
     if (smem) *smem = h->smem;
-    if (blocks) *blocks = (h->nt == 32 && h->epb > 1) ? multi_grid(h, nullptr) : h->n_env;
+    if (blocks) *blocks = (h->nt == 32 && !h->small_batch) ? multi_grid(h, nullptr) : h->n_env;
     if (launches) *launches = h->launches;
     return LMH_OK;
 }

@@ -44,6 +44,13 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+#ifndef LMH_QP_GENERAL_NOINLINE
+#define LMH_QP_GENERAL_NOINLINE 0     // measured: as a real call it costs 5 % (spills around the call); inlined, the split
+                                      // of qp_phase into hot path + general iteration removed the kernel's last spills
+#endif
+#ifndef LMH_STAGE_NOINLINE
+#define LMH_STAGE_NOINLINE 0     // 1: the whole stage as one non-inlined function (measured: -14 % throughput)
+#endif
 #ifndef LMH_GRAM_DMMA
 #define LMH_GRAM_DMMA 1     // 1: the 10 x 30 x 10 Gram product of the QP front end on the FP64 tensor cores (one-warp path)
 #endif
@@ -199,6 +206,17 @@ struct Ctx {
     const double* isp = nullptr;
     const double* dh = nullptr;
     const double* mpc_r = nullptr;
+    // Latency mode (rollout_kernel_helpers): the environment's warp is joined by two helper warps that take the CRBA
+    // and the sole Jacobians while it runs the RNEA (the three only read the transforms); helpers = threads of the block
+    // taking part in the hand-over barriers, 0 = no helpers
+    int helpers = 0;
+    LMH_HD void handover(int id) const {
+#if defined(__CUDA_ARCH__)
+        if (helpers) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(helpers) : "memory");
+#else
+        (void)id;
+#endif
+    }
     LMH_HD void align() const {
 #if defined(__CUDA_ARCH__)
         if (NT == 32) {
@@ -712,7 +730,7 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
     }
     bool jac_done = false;
 #if defined(__CUDA_ARCH__)
-    if (Cx::NT == 32) { jacobian_warp(w, cx.tid); jac_done = true; }
+    if (Cx::NT == 32) { if (!cx.helpers) jacobian_warp(w, cx.tid); jac_done = true; }
 #endif
     if (!jac_done) {
     // running sole_X_j = (E, B) for both feet, starting from the sole frame
@@ -952,242 +970,23 @@ __device__ void jacobian_warp(EnvWS& w, int lane);
 __device__ void qp_backsolve_warp(EnvWS& w, int lane);
 #endif
 
-// ================================================================================================
-// Phase 7: the WBC QP (controller.cpp:388-479) in reduced form.
-//   variables a (30), c (32);  f12 = G c eliminated (controller.cpp:156-294 rows 6..17)
-//   min 1/2 a'Ha a + ga'a + 1/2 wF |G c|^2 + 1/2 eps |c|^2   s.t.  M6 a - Jb' G c = -C6,  c >= 0
-// a is eliminated through the Cholesky factor of Ha and the 6x6 Schur complement Sa = M6 Ha^-1 M6',
-// leaving   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I,
-// which a primal active-set method solves exactly (masked Cholesky of Q per working set).
-template <class Cx>
-LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done) {
-    double* L1 = w.u.s.L1;
-    double* Yt = w.u.s.Yt;
-    double* Gm = w.u.s.Gm;
-    if (!factor_done) {
-        // left-looking Cholesky of D1 (18 columns); the 10 right-hand-side rows ride along and come out as L1^-1 [.]
-        for (int k = 0; k < ND1; ++k) {
-            LMH_FOR(i0, ND1 + NYR - k) {
-                int i = k + i0;
-                double* ri = i < ND1 ? L1 + LD1 * i : Yt + NQ * (i - ND1);
-                const double* rk = L1 + LD1 * k;
-                double s0 = ri[k], s1 = 0.0;
-                int m = 0;
-                for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
-                if (m < k) s0 -= ri[m] * rk[m];
-                ri[k] = s0 + s1;
-            }
-            cx.sync();
-            double dk = sqrt(L1[LD1 * k + k]);     // nobody writes the pivot in the next loop
-            LMH_FOR(i0, ND1 + NYR - k) {
-                int i = k + i0;
-                if (i == k) w.ladiag[k] = dk;
-                else {
-                    double* ri = i < ND1 ? L1 + LD1 * i : Yt + NQ * (i - ND1);
-                    ri[k] = ri[k] / dk;
-                }
-            }
-            cx.sync();
-        }
-    }
-    // Gram matrix of the rows: Gm[r][c] = [.]_r D^-1 [.]_c'
-#if defined(__CUDA_ARCH__) && LMH_GRAM_DMMA
-    if (Cx::NT == 32) {
-        // 10 x 30 times 30 x 10 on the FP64 tensor cores: three 8 x 8 tiles (the lower triangle of the 16 x 16 padded
-        // product), eight k-steps of mma.sync m8n8k4 each.  Yt serves as A (row-major) and, read the same way, as B (= Yt').
-        const int lane = cx.tid, fr = lane >> 2, fk = lane & 3;
-        double t00a = 0, t00b = 0, t10a = 0, t10b = 0, t11a = 0, t11b = 0;
-        LMH_UNROLL
-        for (int kt = 0; kt < 8; ++kt) {
-            const int m = 4 * kt + fk;
-            const double y0 = m < NQ ? Yt[NQ * fr + m] : 0.0;
-            const double y1 = (m < NQ && fr < NYR - 8) ? Yt[NQ * (8 + fr) + m] : 0.0;
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t00a), "+d"(t00b) : "d"(y0), "d"(y0));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t10a), "+d"(t10b) : "d"(y1), "d"(y0));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t11a), "+d"(t11b) : "d"(y1), "d"(y1));
-        }
-        const int c0 = 2 * fk;
-        Gm[NYR * fr + c0] = t00a; Gm[NYR * fr + c0 + 1] = t00b;
-        if (fr < NYR - 8) {
-            Gm[NYR * (8 + fr) + c0] = t10a; Gm[NYR * (8 + fr) + c0 + 1] = t10b;
-            Gm[NYR * c0 + 8 + fr] = t10a; Gm[NYR * (c0 + 1) + 8 + fr] = t10b;
-            if (fk == 0) { Gm[NYR * (8 + fr) + 8] = t11a; Gm[NYR * (8 + fr) + 9] = t11b; }
-        }
-    } else
-#endif
-    LMH_FOR(it, NYR * (NYR + 1) / 2) {
-        // unrank the lower-triangular index (55 entries): 8 it + 1 = (2r + 1)^2 at the start of row r, exact in float
-        const int r = (int)((sqrtf(8.0f * (float)it + 1.0f) - 1.0f) * 0.5f);
-        const int c = it - r * (r + 1) / 2;
-        {
-            double s0 = 0.0, s1 = 0.0;
-            const double* yr = Yt + NQ * r;
-            const double* yc = Yt + NQ * c;
-            LMH_UNROLL
-            for (int m = 0; m < NQ; m += 2) {
-#if defined(__CUDA_ARCH__)
-                const double2 a = *reinterpret_cast<const double2*>(yr + m), b = *reinterpret_cast<const double2*>(yc + m);
-                s0 += a.x * b.x; s1 += a.y * b.y;
+// The general primal active-set iteration of the WBC QP (see qp_phase) and the multiplier of its solution, kept apart
+// from the hot path of qp_phase (it runs in 2 % of the stages of a balancing robot).  In: the projected starting point / warm-started working set in w.c, w.free_mask;
+// out: w.c, w.f12 = G c, w.lam = Sa^-1 (rhs - Jb'f12), iteration count and status.
+#if defined(__CUDACC__) && LMH_QP_GENERAL_NOINLINE
+#define LMH_NOINLINE __noinline__
 #else
-                s0 += yr[m] * yc[m]; s1 += yr[m + 1] * yc[m + 1];
+#define LMH_NOINLINE
 #endif
-            }
-            Gm[NYR * r + c] = s0 + s1;
-            Gm[NYR * c + r] = s0 + s1;
-        }
-    }
-    cx.sync();
-    // Ci = (I3 + U D^-1 U')^-1 in every thread; Sa = M6 Ha^-1 M6', rhs = C6 - M6 Ha^-1 ga
-    double Ci[9];
-    {
-        double c00 = 1.0 + Gm[NYR * 7 + 7], c01 = Gm[NYR * 7 + 8], c02 = Gm[NYR * 7 + 9];
-        double c11 = 1.0 + Gm[NYR * 8 + 8], c12 = Gm[NYR * 8 + 9], c22 = 1.0 + Gm[NYR * 9 + 9];
-        double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
-        double a11 = c00 * c22 - c02 * c02, a12 = c01 * c02 - c00 * c12, a22 = c00 * c11 - c01 * c01;
-        double det = c00 * a00 + c01 * a01 + c02 * a02;
-        const double rdet = 1.0 / det;
-        Ci[0] = a00 * rdet; Ci[1] = a01 * rdet; Ci[2] = a02 * rdet;
-        Ci[3] = Ci[1];      Ci[4] = a11 * rdet; Ci[5] = a12 * rdet;
-        Ci[6] = Ci[2];      Ci[7] = Ci[5];      Ci[8] = a22 * rdet;
-    }
-    LMH_FOR(it, 42) {
-        int r = it / 6, c = it % 6;          // r == 6: the ga row
-        const int rr = r < 6 ? r : c, cc = r < 6 ? c : 6;
-        double g0 = Gm[NYR * rr + 7], g1 = Gm[NYR * rr + 8], g2 = Gm[NYR * rr + 9];
-        double h0 = Gm[NYR * 7 + cc], h1 = Gm[NYR * 8 + cc], h2 = Gm[NYR * 9 + cc];
-        double t0 = Ci[0] * h0 + Ci[1] * h1 + Ci[2] * h2, t1 = Ci[3] * h0 + Ci[4] * h1 + Ci[5] * h2, t2 = Ci[6] * h0 + Ci[7] * h1 + Ci[8] * h2;
-        double v = Gm[NYR * rr + cc] - (g0 * t0 + g1 * t1 + g2 * t2);
-        if (r < 6) w.Sa[it] = v; else w.rhs[c] = w.C[c] - v;
-    }
-    cx.sync();
-    // ---- primal active set on c >= 0, every working set solved in the wrench space of the feet.
-    // For a free set F let P_F = G_F G_F' = B B' (B: 12 x 12, block diagonal per foot, from a diagonally pivoted
-    // Cholesky that stops at the numerical rank: columns beyond the rank are zero).  With f = B zeta the
-    // equality-constrained problem on F is
-    //     (B'K B + eps I) zeta = B'd,   K = wF I + Jb Sa^-1 Jb',  d = Jb Sa^-1 rhs,
-    // c_F = G_F' B (B'B)^-1 zeta, and the multipliers of the clipped coefficients are mu_i = g_i'(wF f - Jb lam),
-    // lam = Sa^-1 (rhs - Jb'f).  Well conditioned for ANY contact pattern (a foot on an edge, on one vertex, or
-    // unloaded only shortens B), which a c-space or a full 12 x 12 wrench-space system is not.
+template <class Cx>
+LMH_NOINLINE LMH_HDN void qp_general_active_set(const Cx& cx, EnvWS& w, const Consts& K, int contact, bool have_point, int& iters, int& status) {
     double* Bm = w.u.s.Bm;            // [12][6] : row 6f+i, basis column k of foot f
     double* Pm = w.u.s.Pm;            // [2][36] : residual of the pivoted Cholesky, then T = B'B
     double* Wb = w.u.s.Wb;            // [6][12] : Ls^-1 Jb' B
     double* Ay = w.u.s.Ay;            // 13 x 13 : lower triangle factorised in place, row 12 = rhs / zeta
     double* vv = w.u.s.vv;            // [36]   : (12 unused), y with B'y = zeta (12), r = wF f - Jb lam (12)
-    const int contact = w.contact;     // bit f: foot f may carry force (both set in the reference's stand task)
-    // Warm start: consecutive stage evaluations of an environment nearly always share their working set, and any
-    // c >= 0 is a feasible starting point, so the previous solution (w.c, w.free_mask) seeds the iteration when it
-    // has clipped coefficients and the contact phase is the same.  The minimiser is unique: only the path changes.
-    bool have_point = false;
-    if (w.warm_contact == contact) {
-#if defined(__CUDA_ARCH__)
-        if (Cx::NT == 32) have_point = __any_sync(0xffffffffu, ((contact >> (cx.tid / 16)) & 1) && !w.free_mask[cx.tid]);
-        else
-#endif
-        {
-        int nclip = 0;
-        for (int i = 0; i < NC; ++i) nclip += (((contact >> (i / 16)) & 1) && !w.free_mask[i]) ? 1 : 0;
-        have_point = nclip > 0;
-        }
-    }
-    cx.sync();
-    if (!have_point) {
-        LMH_FOR(i, NC) { w.free_mask[i] = (contact >> (i / 16)) & 1; w.c[i] = 0.0; }
-    }
-    LMH_FOR(i, 1) w.warm_contact = contact;
-    cx.sync();
-    // ---- all-free shortcut (no stored working set, at least one foot in contact: 98 % of the stages of a balancing robot).
-    // With every coefficient free, f ranges over all of R^12 and c is its minimum-norm preimage, so the problem in f is
-    //     min 1/2 f'D f  s.t.  Sa lam = rhs - Jb'f,   D = wF I + eps (G G')^-1  (constant, block diagonal per foot),
-    // whose multiplier solves the 6 x 6 system (Sa + Jb' D^-1 Jb) lam = rhs, f = D^-1 Jb lam, c = G'(G G')^-1 f.
-    // One 6 x 6 factorisation instead of chol(Sa) plus the 12 x 12 wrench-space system; if some c comes out negative
-    // the general iteration below starts from scratch.
-    int iters = 0, status = 0;
-    bool fast_done = false;
-    double lfast[6] = {0, 0, 0, 0, 0, 0};
-    if (!have_point && contact != 0) {     // a swing foot (walking extension) carries no force: its block of D^-1 is zero
-        double* U = Wb;                // [2][6][6] : D^-1 Jb_f
-        double* S6 = Ay;               // [6][6]    : lower triangle of Sa + Jb' D^-1 Jb
-        LMH_FOR(it, 72) {
-            const int f = it / 36, k = (it % 36) / 6, sidx = it % 6;
-            double sd = 0.0;
-            for (int l = 0; l < 6; ++l) sd += K.Dinv[6 * k + l] * w.JFc[72 * f + 12 * l + sidx];
-            U[it] = ((contact >> f) & 1) ? sd : 0.0;
-        }
-        cx.sync();
-        LMH_FOR(it, 36) {
-            const int r = it / 6, sidx = it % 6;
-            if (sidx <= r) {
-                double sd = w.Sa[it];
-                for (int k = 0; k < 12; ++k) sd += w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * U[36 * (k / 6) + 6 * (k % 6) + sidx];
-                S6[it] = sd;
-            }
-        }
-        cx.sync();
-        {
-            double A[36], Ainv[6];
-            LMH_UNROLL
-            for (int e = 0; e < 36; ++e) A[e] = (e % 6 <= e / 6) ? S6[e] : 0.0;
-            chol6(A, Ainv);
-            LMH_UNROLL
-            for (int r = 0; r < 6; ++r) {
-                double sd = w.rhs[r];
-                LMH_UNROLL
-                for (int m = 0; m < 6; ++m) if (m < r) sd -= A[6 * r + m] * lfast[m];
-                lfast[r] = sd * Ainv[r];
-            }
-            LMH_UNROLL
-            for (int r = 5; r >= 0; --r) {
-                double sd = lfast[r];
-                LMH_UNROLL
-                for (int m = 0; m < 6; ++m) if (m > r) sd -= A[6 * m + r] * lfast[m];
-                lfast[r] = sd * Ainv[r];
-            }
-        }
-        LMH_FOR(it, 12) {              // f = D^-1 Jb lam
-            double sd = 0.0;
-            for (int q = 0; q < 6; ++q) sd += U[6 * it + q] * lfast[q];
-            w.f12[it] = sd;
-        }
-        cx.sync();
-        LMH_FOR(it, 12) {              // y = (G G')^-1 f per foot
-            const int f = it / 6, k = it % 6;
-            double sy = 0.0;
-            for (int l = 0; l < 6; ++l) sy += K.Pinv[6 * k + l] * w.f12[6 * f + l];
-            vv[12 + it] = sy;
-        }
-        cx.sync();
-        double cmin = 0.0;
-#if defined(__CUDA_ARCH__)
-        if (Cx::NT == 32) {
-            const int i = cx.tid, foot = i / 16, gi = i % 16;
-            double sc = 0.0;
-            for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k];
-            cmin = warp_min(sc);
-            // feasible: optimal.  Otherwise project onto the orthant, as the first pass of the general iteration
-            // would: the clipped coefficients are the working set it starts from
-            w.c[i] = sc > 0.0 ? sc : 0.0;
-            w.free_mask[i] = (((contact >> foot) & 1) && (cmin >= 0.0 || sc > 0.0)) ? 1 : 0;
-            w.cs[i] = sc; w.mu[i] = 0.0;
-        } else
-#endif
-        {
-            LMH_FOR(i, NC) {
-                const int foot = i / 16, gi = i % 16;
-                double sc = 0.0;
-                for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k];
-                w.cs[i] = sc; w.mu[i] = 0.0;
-            }
-            cx.sync();
-            for (int i = 0; i < NC; ++i) cmin = w.cs[i] < cmin ? w.cs[i] : cmin;
-            LMH_FOR(i, NC) { w.c[i] = w.cs[i] > 0.0 ? w.cs[i] : 0.0; w.free_mask[i] = (((contact >> (i / 16)) & 1) && (cmin >= 0.0 || w.cs[i] > 0.0)) ? 1 : 0; }
-        }
-        cx.sync();
-        iters = 1;
-        have_point = true;
-        if (cmin >= 0.0) fast_done = true;
-    }
     // Ls = chol(Sa): 6x6, every thread redundantly in registers, then parked in shared memory (general iteration only)
-    if (!fast_done) {
+    {
         double A[36];
         LMH_UNROLL
         for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
@@ -1203,7 +1002,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     const double* Ls = w.Ls;
     const double* Lsi = w.Lsi;
     bool first_pass = true;            // of the general iteration in this stage
-    while (!fast_done) {
+    for (;;) {
         ++iters;
         {
             LMH_FOR(it, 72) {         // P_F per foot
@@ -1481,12 +1280,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         if (done) break;
         if (iters >= K.qp_max_iter) { status = 1; break; }
     }
-    w.qp_fallback = iters > 1 ? 1 : 0;     // stages whose all-free solution was infeasible (contact-limited)
-    w.qp_iters = iters;
-    w.qp_status = status;
-    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12).  After the shortcut both are already there: f12 = D^-1 Jb lam is the
-    // wrench whose minimum-norm preimage c is (G c = f12 up to rounding), and lam came out of the 6 x 6 system.
-    if (!fast_done) {
+    // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12)
     LMH_FOR(r, 12) {
         int foot = r / 6, k = r % 6;
         double s = 0.0;
@@ -1494,21 +1288,18 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         w.f12[r] = s;
     }
     cx.sync();
-    }
-    {
-        double l[6] = {0, 0, 0, 0, 0, 0};
+    double l[6] = {0, 0, 0, 0, 0, 0};
 #if defined(__CUDA_ARCH__)
-        if (fast_done) {
-        } else if (Cx::NT == 32) {       // lane r < 6 forms its own entry, then every lane collects the six
-            const int r = cx.tid < 6 ? cx.tid : 0;
-            double s = w.rhs[r];
-            LMH_UNROLL
-            for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
-            LMH_UNROLL
-            for (int q = 0; q < 6; ++q) l[q] = __shfl_sync(0xffffffffu, s, q);
-        } else
+    if (Cx::NT == 32) {       // lane r < 6 forms its own entry, then every lane collects the six
+        const int r = cx.tid < 6 ? cx.tid : 0;
+        double s = w.rhs[r];
+        LMH_UNROLL
+        for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
+        LMH_UNROLL
+        for (int q = 0; q < 6; ++q) l[q] = __shfl_sync(0xffffffffu, s, q);
+    } else
 #endif
-        if (!fast_done) {
+    {
         LMH_UNROLL
         for (int r = 0; r < 6; ++r) {
             double s = w.rhs[r];
@@ -1516,26 +1307,271 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             for (int k = 0; k < 12; ++k) s -= w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * w.f12[k];
             l[r] = s;
         }
-        }
-        if (fast_done) {
-            LMH_UNROLL
-            for (int r = 0; r < 6; ++r) l[r] = lfast[r];
-        } else {
+    }
+    LMH_UNROLL
+    for (int r = 0; r < 6; ++r) {
+        double s = l[r];
         LMH_UNROLL
-        for (int r = 0; r < 6; ++r) {
-            double s = l[r];
-            LMH_UNROLL
-            for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m];
-            l[r] = s * Lsi[r];
-        }
+        for (int m = 0; m < r; ++m) s -= Ls[6 * r + m] * l[m];
+        l[r] = s * Lsi[r];
+    }
+    LMH_UNROLL
+    for (int r = 5; r >= 0; --r) {
+        double s = l[r];
         LMH_UNROLL
-        for (int r = 5; r >= 0; --r) {
-            double s = l[r];
+        for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m];
+        l[r] = s * Lsi[r];
+    }
+    LMH_FOR(r, 6) w.lam[r] = l[r];
+    cx.sync();
+}
+
+// ================================================================================================
+// Phase 7: the WBC QP (controller.cpp:388-479) in reduced form.
+//   variables a (30), c (32);  f12 = G c eliminated (controller.cpp:156-294 rows 6..17)
+//   min 1/2 a'Ha a + ga'a + 1/2 wF |G c|^2 + 1/2 eps |c|^2   s.t.  M6 a - Jb' G c = -C6,  c >= 0
+// a is eliminated through the Cholesky factor of Ha and the 6x6 Schur complement Sa = M6 Ha^-1 M6',
+// leaving   min 1/2 c'Q c - p'c, c >= 0,  Q = wF G'G + (Ls^-1 Jb'G)'(Ls^-1 Jb'G) + eps I,
+// which a primal active-set method solves exactly (masked Cholesky of Q per working set).
+template <class Cx>
+LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done) {
+    double* L1 = w.u.s.L1;
+    double* Yt = w.u.s.Yt;
+    double* Gm = w.u.s.Gm;
+    if (!factor_done) {
+        // left-looking Cholesky of D1 (18 columns); the 10 right-hand-side rows ride along and come out as L1^-1 [.]
+        for (int k = 0; k < ND1; ++k) {
+            LMH_FOR(i0, ND1 + NYR - k) {
+                int i = k + i0;
+                double* ri = i < ND1 ? L1 + LD1 * i : Yt + NQ * (i - ND1);
+                const double* rk = L1 + LD1 * k;
+                double s0 = ri[k], s1 = 0.0;
+                int m = 0;
+                for (; m + 1 < k; m += 2) { s0 -= ri[m] * rk[m]; s1 -= ri[m + 1] * rk[m + 1]; }
+                if (m < k) s0 -= ri[m] * rk[m];
+                ri[k] = s0 + s1;
+            }
+            cx.sync();
+            double dk = sqrt(L1[LD1 * k + k]);     // nobody writes the pivot in the next loop
+            LMH_FOR(i0, ND1 + NYR - k) {
+                int i = k + i0;
+                if (i == k) w.ladiag[k] = dk;
+                else {
+                    double* ri = i < ND1 ? L1 + LD1 * i : Yt + NQ * (i - ND1);
+                    ri[k] = ri[k] / dk;
+                }
+            }
+            cx.sync();
+        }
+    }
+    // Gram matrix of the rows: Gm[r][c] = [.]_r D^-1 [.]_c'
+#if defined(__CUDA_ARCH__) && LMH_GRAM_DMMA
+    if (Cx::NT == 32) {
+        // 10 x 30 times 30 x 10 on the FP64 tensor cores: three 8 x 8 tiles (the lower triangle of the 16 x 16 padded
+        // product), eight k-steps of mma.sync m8n8k4 each.  Yt serves as A (row-major) and, read the same way, as B (= Yt').
+        const int lane = cx.tid, fr = lane >> 2, fk = lane & 3;
+        double t00a = 0, t00b = 0, t10a = 0, t10b = 0, t11a = 0, t11b = 0;
+        LMH_UNROLL
+        for (int kt = 0; kt < 8; ++kt) {
+            const int m = 4 * kt + fk;
+            const double y0 = m < NQ ? Yt[NQ * fr + m] : 0.0;
+            const double y1 = (m < NQ && fr < NYR - 8) ? Yt[NQ * (8 + fr) + m] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t00a), "+d"(t00b) : "d"(y0), "d"(y0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t10a), "+d"(t10b) : "d"(y1), "d"(y0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(t11a), "+d"(t11b) : "d"(y1), "d"(y1));
+        }
+        const int c0 = 2 * fk;
+        Gm[NYR * fr + c0] = t00a; Gm[NYR * fr + c0 + 1] = t00b;
+        if (fr < NYR - 8) {
+            Gm[NYR * (8 + fr) + c0] = t10a; Gm[NYR * (8 + fr) + c0 + 1] = t10b;
+            Gm[NYR * c0 + 8 + fr] = t10a; Gm[NYR * (c0 + 1) + 8 + fr] = t10b;
+            if (fk == 0) { Gm[NYR * (8 + fr) + 8] = t11a; Gm[NYR * (8 + fr) + 9] = t11b; }
+        }
+    } else
+#endif
+    LMH_FOR(it, NYR * (NYR + 1) / 2) {
+        // unrank the lower-triangular index (55 entries): 8 it + 1 = (2r + 1)^2 at the start of row r, exact in float
+        const int r = (int)((sqrtf(8.0f * (float)it + 1.0f) - 1.0f) * 0.5f);
+        const int c = it - r * (r + 1) / 2;
+        {
+            double s0 = 0.0, s1 = 0.0;
+            const double* yr = Yt + NQ * r;
+            const double* yc = Yt + NQ * c;
             LMH_UNROLL
-            for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m];
-            l[r] = s * Lsi[r];
+            for (int m = 0; m < NQ; m += 2) {
+#if defined(__CUDA_ARCH__)
+                const double2 a = *reinterpret_cast<const double2*>(yr + m), b = *reinterpret_cast<const double2*>(yc + m);
+                s0 += a.x * b.x; s1 += a.y * b.y;
+#else
+                s0 += yr[m] * yc[m]; s1 += yr[m + 1] * yc[m + 1];
+#endif
+            }
+            Gm[NYR * r + c] = s0 + s1;
+            Gm[NYR * c + r] = s0 + s1;
         }
+    }
+    cx.sync();
+    // Ci = (I3 + U D^-1 U')^-1 in every thread; Sa = M6 Ha^-1 M6', rhs = C6 - M6 Ha^-1 ga
+    double Ci[9];
+    {
+        double c00 = 1.0 + Gm[NYR * 7 + 7], c01 = Gm[NYR * 7 + 8], c02 = Gm[NYR * 7 + 9];
+        double c11 = 1.0 + Gm[NYR * 8 + 8], c12 = Gm[NYR * 8 + 9], c22 = 1.0 + Gm[NYR * 9 + 9];
+        double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
+        double a11 = c00 * c22 - c02 * c02, a12 = c01 * c02 - c00 * c12, a22 = c00 * c11 - c01 * c01;
+        double det = c00 * a00 + c01 * a01 + c02 * a02;
+        const double rdet = 1.0 / det;
+        Ci[0] = a00 * rdet; Ci[1] = a01 * rdet; Ci[2] = a02 * rdet;
+        Ci[3] = Ci[1];      Ci[4] = a11 * rdet; Ci[5] = a12 * rdet;
+        Ci[6] = Ci[2];      Ci[7] = Ci[5];      Ci[8] = a22 * rdet;
+    }
+    LMH_FOR(it, 42) {
+        int r = it / 6, c = it % 6;          // r == 6: the ga row
+        const int rr = r < 6 ? r : c, cc = r < 6 ? c : 6;
+        double g0 = Gm[NYR * rr + 7], g1 = Gm[NYR * rr + 8], g2 = Gm[NYR * rr + 9];
+        double h0 = Gm[NYR * 7 + cc], h1 = Gm[NYR * 8 + cc], h2 = Gm[NYR * 9 + cc];
+        double t0 = Ci[0] * h0 + Ci[1] * h1 + Ci[2] * h2, t1 = Ci[3] * h0 + Ci[4] * h1 + Ci[5] * h2, t2 = Ci[6] * h0 + Ci[7] * h1 + Ci[8] * h2;
+        double v = Gm[NYR * rr + cc] - (g0 * t0 + g1 * t1 + g2 * t2);
+        if (r < 6) w.Sa[it] = v; else w.rhs[c] = w.C[c] - v;
+    }
+    cx.sync();
+    // ---- primal active set on c >= 0, every working set solved in the wrench space of the feet.
+    // For a free set F let P_F = G_F G_F' = B B' (B: 12 x 12, block diagonal per foot, from a diagonally pivoted
+    // Cholesky that stops at the numerical rank: columns beyond the rank are zero).  With f = B zeta the
+    // equality-constrained problem on F is
+    //     (B'K B + eps I) zeta = B'd,   K = wF I + Jb Sa^-1 Jb',  d = Jb Sa^-1 rhs,
+    // c_F = G_F' B (B'B)^-1 zeta, and the multipliers of the clipped coefficients are mu_i = g_i'(wF f - Jb lam),
+    // lam = Sa^-1 (rhs - Jb'f).  Well conditioned for ANY contact pattern (a foot on an edge, on one vertex, or
+    // unloaded only shortens B), which a c-space or a full 12 x 12 wrench-space system is not.
+    double* Bm = w.u.s.Bm;            // [12][6] : row 6f+i, basis column k of foot f
+    double* Pm = w.u.s.Pm;            // [2][36] : residual of the pivoted Cholesky, then T = B'B
+    double* Wb = w.u.s.Wb;            // [6][12] : Ls^-1 Jb' B
+    double* Ay = w.u.s.Ay;            // 13 x 13 : lower triangle factorised in place, row 12 = rhs / zeta
+    double* vv = w.u.s.vv;            // [36]   : (12 unused), y with B'y = zeta (12), r = wF f - Jb lam (12)
+    const int contact = w.contact;     // bit f: foot f may carry force (both set in the reference's stand task)
+    // Warm start: consecutive stage evaluations of an environment nearly always share their working set, and any
+    // c >= 0 is a feasible starting point, so the previous solution (w.c, w.free_mask) seeds the iteration when it
+    // has clipped coefficients and the contact phase is the same.  The minimiser is unique: only the path changes.
+    bool have_point = false;
+    if (w.warm_contact == contact) {
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) have_point = __any_sync(0xffffffffu, ((contact >> (cx.tid / 16)) & 1) && !w.free_mask[cx.tid]);
+        else
+#endif
+        {
+        int nclip = 0;
+        for (int i = 0; i < NC; ++i) nclip += (((contact >> (i / 16)) & 1) && !w.free_mask[i]) ? 1 : 0;
+        have_point = nclip > 0;
         }
+    }
+    cx.sync();
+    if (!have_point) {
+        LMH_FOR(i, NC) { w.free_mask[i] = (contact >> (i / 16)) & 1; w.c[i] = 0.0; }
+    }
+    LMH_FOR(i, 1) w.warm_contact = contact;
+    cx.sync();
+    // ---- all-free shortcut (no stored working set, at least one foot in contact: 98 % of the stages of a balancing robot).
+    // With every coefficient free, f ranges over all of R^12 and c is its minimum-norm preimage, so the problem in f is
+    //     min 1/2 f'D f  s.t.  Sa lam = rhs - Jb'f,   D = wF I + eps (G G')^-1  (constant, block diagonal per foot),
+    // whose multiplier solves the 6 x 6 system (Sa + Jb' D^-1 Jb) lam = rhs, f = D^-1 Jb lam, c = G'(G G')^-1 f.
+    // One 6 x 6 factorisation instead of chol(Sa) plus the 12 x 12 wrench-space system; if some c comes out negative
+    // the general iteration below starts from scratch.
+    int iters = 0, status = 0;
+    bool fast_done = false;
+    double lfast[6] = {0, 0, 0, 0, 0, 0};
+    if (!have_point && contact != 0) {     // a swing foot (walking extension) carries no force: its block of D^-1 is zero
+        double* U = Wb;                // [2][6][6] : D^-1 Jb_f
+        double* S6 = Ay;               // [6][6]    : lower triangle of Sa + Jb' D^-1 Jb
+        LMH_FOR(it, 72) {
+            const int f = it / 36, k = (it % 36) / 6, sidx = it % 6;
+            double sd = 0.0;
+            for (int l = 0; l < 6; ++l) sd += K.Dinv[6 * k + l] * w.JFc[72 * f + 12 * l + sidx];
+            U[it] = ((contact >> f) & 1) ? sd : 0.0;
+        }
+        cx.sync();
+        LMH_FOR(it, 36) {
+            const int r = it / 6, sidx = it % 6;
+            if (sidx <= r) {
+                double sd = w.Sa[it];
+                for (int k = 0; k < 12; ++k) sd += w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * U[36 * (k / 6) + 6 * (k % 6) + sidx];
+                S6[it] = sd;
+            }
+        }
+        cx.sync();
+        {
+            double A[36], Ainv[6];
+            LMH_UNROLL
+            for (int e = 0; e < 36; ++e) A[e] = (e % 6 <= e / 6) ? S6[e] : 0.0;
+            chol6(A, Ainv);
+            LMH_UNROLL
+            for (int r = 0; r < 6; ++r) {
+                double sd = w.rhs[r];
+                LMH_UNROLL
+                for (int m = 0; m < 6; ++m) if (m < r) sd -= A[6 * r + m] * lfast[m];
+                lfast[r] = sd * Ainv[r];
+            }
+            LMH_UNROLL
+            for (int r = 5; r >= 0; --r) {
+                double sd = lfast[r];
+                LMH_UNROLL
+                for (int m = 0; m < 6; ++m) if (m > r) sd -= A[6 * m + r] * lfast[m];
+                lfast[r] = sd * Ainv[r];
+            }
+        }
+        LMH_FOR(it, 12) {              // f = D^-1 Jb lam
+            double sd = 0.0;
+            for (int q = 0; q < 6; ++q) sd += U[6 * it + q] * lfast[q];
+            w.f12[it] = sd;
+        }
+        cx.sync();
+        LMH_FOR(it, 12) {              // y = (G G')^-1 f per foot
+            const int f = it / 6, k = it % 6;
+            double sy = 0.0;
+            for (int l = 0; l < 6; ++l) sy += K.Pinv[6 * k + l] * w.f12[6 * f + l];
+            vv[12 + it] = sy;
+        }
+        cx.sync();
+        double cmin = 0.0;
+#if defined(__CUDA_ARCH__)
+        if (Cx::NT == 32) {
+            const int i = cx.tid, foot = i / 16, gi = i % 16;
+            double sc = 0.0;
+            for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k];
+            cmin = warp_min(sc);
+            // feasible: optimal.  Otherwise project onto the orthant, as the first pass of the general iteration
+            // would: the clipped coefficients are the working set it starts from
+            w.c[i] = sc > 0.0 ? sc : 0.0;
+            w.free_mask[i] = (((contact >> foot) & 1) && (cmin >= 0.0 || sc > 0.0)) ? 1 : 0;
+            w.cs[i] = sc; w.mu[i] = 0.0;
+        } else
+#endif
+        {
+            LMH_FOR(i, NC) {
+                const int foot = i / 16, gi = i % 16;
+                double sc = 0.0;
+                for (int k = 0; k < 6; ++k) sc += K.Gf[16 * k + gi] * vv[12 + 6 * foot + k];
+                w.cs[i] = sc; w.mu[i] = 0.0;
+            }
+            cx.sync();
+            for (int i = 0; i < NC; ++i) cmin = w.cs[i] < cmin ? w.cs[i] : cmin;
+            LMH_FOR(i, NC) { w.c[i] = w.cs[i] > 0.0 ? w.cs[i] : 0.0; w.free_mask[i] = (((contact >> (i / 16)) & 1) && (cmin >= 0.0 || w.cs[i] > 0.0)) ? 1 : 0; }
+        }
+        cx.sync();
+        iters = 1;
+        have_point = true;
+        if (cmin >= 0.0) fast_done = true;
+    }
+    if (!fast_done) qp_general_active_set(cx, w, K, contact, have_point, iters, status);
+    w.qp_fallback = iters > 1 ? 1 : 0;     // stages whose all-free solution was infeasible (contact-limited)
+    w.qp_iters = iters;
+    w.qp_status = status;
+    // lam = Sa^-1 (rhs - Jb' f12), f12 = G c.  After the shortcut both are already there: f12 = D^-1 Jb lam is the wrench
+    // whose minimum-norm preimage c is (G c = f12 up to rounding), and lam came out of the 6 x 6 system; the general
+    // iteration leaves them in w.f12, w.lam.
+    {
+        double l[6];
+        LMH_UNROLL
+        for (int r = 0; r < 6; ++r) l[r] = fast_done ? lfast[r] : w.lam[r];
+
         // a = -Ha^-1 (ga + M6' lam) through the same Woodbury pieces
         double coef[7] = {l[0], l[1], l[2], l[3], l[4], l[5], 1.0};
         double z[3] = {0, 0, 0};
@@ -1652,8 +1688,10 @@ LMH_HDN void model_phases(const Cx& cx, EnvWS& w, const Consts& K) {
         const LaneRole L = lane_role(cx.tid);
         const double* Isp = Cx::TAB ? cx.isp : K.Isp;
         if (Cx::TAB) __builtin_assume(__isShared(Isp));
+        cx.handover(2);                             // transforms and base twists are ready: the helper warps start
         rnea_warp(w, K, Isp, L, cx.tid);
-        crba_warp(w, K, Isp, L, cx.tid);
+        if (!cx.helpers) crba_warp(w, K, Isp, L, cx.tid);
+        cx.handover(3);                             // mass matrix and sole Jacobians are there
     } else
 #endif
     {
@@ -1682,8 +1720,17 @@ LMH_HDN void qp_stage(const Cx& cx, EnvWS& w, const Consts& K, LmhStageDump* dum
     qp_phase(cx, w, K, factor_done);
 }
 
+// Not inlined on the device: the throughput kernel and the latency kernel then execute ONE compiled body of the stage
+// (the same instructions, the same FMA contractions), which is what makes their results identical bit for bit.  (Inlined
+// separately, the compiler contracted a few sums of products of the general active-set iteration differently in the two
+// kernels: 1-ulp differences a few steps after a push.)
+#if defined(__CUDACC__) && LMH_STAGE_NOINLINE
+#define LMH_STAGE_ATTR __noinline__
+#else
+#define LMH_STAGE_ATTR
+#endif
 template <class Cx>
-LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, LmhStageDump* dump = nullptr) {
+LMH_STAGE_ATTR LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, LmhStageDump* dump = nullptr) {
     model_phases(cx, w, K);
     mpc_pd_phase(cx, w, K, P, plan_id);
     qp_stage(cx, w, K, dump);
@@ -1714,6 +1761,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
                       int plan_id, LmhStepLog* log, StatsAcc* st) {
     const double dt = K.dt;
     const double half = 0.5 * dt;
+    cx.handover(1);                                 // helper warps learn here whether the environment is still alive
     if (w.dead != 0) {
         // a fallen environment evaluates nothing; it only keeps its appointments with the warps it shares a block with,
         // and its log record repeats the last evaluated stage

@@ -24,6 +24,13 @@ def nt(request):
     return request.param
 
 
+@pytest.fixture(scope="module", params=["throughput", "latency"])
+def kern(request):
+    """the default (throughput) kernel: ten one-warp environments per block; and the opt-in latency kernel
+    (envs_per_block = -1): one environment per block with two helper warps.  Both must pass every parity test."""
+    return {} if request.param == "throughput" else {"envs_per_block": -1}
+
+
 def test_native_library_is_the_thing_running():
     info = lmh.Batch(2).launch_info()
     assert info["threads_per_env"] in (32, 64, 128) and info["smem_bytes"] > 16000
@@ -96,7 +103,7 @@ def test_qp_against_exact_solutions(qp_exact):
 
 
 def test_closed_loop_1s_against_reference_vectors(golden, nt):
-    b = lmh.Batch(4, threads_per_env=nt, log_steps=100)
+    b = lmh.Batch(4, threads_per_env=nt, log_steps=100)          # (nt = 32, four environments: the helper-warp kernel)
     b.step(100)
     lg = b.log(0, 100)
     x, vh, t = b.get_state()
@@ -114,9 +121,9 @@ def test_closed_loop_1s_against_reference_vectors(golden, nt):
     assert t[0] == tt                                                                  # the clock accumulates like Clock::step
 
 
-def test_stand_5s_stream(golden):
+def test_stand_5s_stream(golden, kern):
     """config 1: the reference run, 500 steps; CoM x as printed by main.cpp:86"""
-    b = lmh.Batch(1, log_steps=500)
+    b = lmh.Batch(1, log_steps=500, **kern)
     b.step(500)
     cx = b.log(0, 500)["com_k4"][:, 0, 0]
     assert np.abs(cx - golden["stand_comx"]).max() < 5e-8                              # stream has 6 printed digits
@@ -124,11 +131,11 @@ def test_stand_5s_stream(golden):
     assert st["steps"] == 500 and st["qp_fail"] == 0 and st["alive"] == 1
 
 
-def test_pushed_rollout_against_oracle(oracle):
+def test_pushed_rollout_against_oracle(oracle, kern):
     """config 2 in small: per-env pushes, 60 steps, every env against the CPU oracle"""
     E, S = 48, 60
     step, dv = lmh.push_plan(range(E), max_step=20)
-    b = lmh.Batch(E)
+    b = lmh.Batch(E, **kern)
     b.set_pushes(step, dv)
     b.step(25)
     b.step(S - 25)                                                                     # split launches: same result
@@ -172,6 +179,32 @@ def test_full_size_properties():
     b3.step(40)
     c = b3.com()
     assert abs(c[0, 0] - c[1, 0]) < 1e-6 and abs(c[0, 1] + c[1, 1]) < 1e-6
+
+
+def test_latency_and_throughput_kernels():
+    """the throughput kernel gives the same bits whatever the block shape (1, 3 or 10 environments per block); the latency
+    kernel (one environment per block with two helper warps: RNEA || CRBA || Jacobians) is deterministic and agrees with
+    it to rounding -- it is another kernel, the compiler contracts a few sums of products differently"""
+    E, S = 40, 50
+    step, dv = lmh.push_plan(range(E), max_speed=0.5, max_step=20)
+    out = []
+    for kw in ({}, {"envs_per_block": 1}, {"envs_per_block": 3}, {"envs_per_block": -1}, {"envs_per_block": -1}):
+        b = lmh.Batch(E, **kw)
+        b.set_pushes(step, dv)
+        b.step(S)
+        x, vh, t = b.get_state()
+        st = b.stats()
+        out.append((x, vh, t, st["max_abs_tau"], st["qp_iters"], st["steps"], st["alive"]))
+        b.close()
+    for other in out[1:3]:
+        for a, c in zip(out[0], other):
+            assert np.array_equal(a, c)
+    for a, c in zip(out[3], out[4]):
+        assert np.array_equal(a, c)                                   # deterministic
+    assert np.abs(out[3][0] - out[0][0]).max() < 1e-10 and np.array_equal(out[3][2], out[0][2])
+    assert np.array_equal(out[3][4], out[0][4]) and np.array_equal(out[3][5], out[0][5])     # same iteration counts, same steps
+    with pytest.raises(lmh.LmhError):
+        lmh.Batch(4, envs_per_block=-2)
 
 
 def test_thread_geometries_agree():
@@ -226,13 +259,13 @@ def test_plans_and_edge_cases():
         assert np.array_equal(b.get_state()[0][3], x_frozen) and np.isfinite(b.stats()["max_abs_tau"]).all()
 
 
-def test_walking_extension_against_oracle(oracle):
+def test_walking_extension_against_oracle(oracle, kern):
     """EXTENSION (BASELINE configs 3-4): per-environment walking plans, 1.6 s MPC horizon, contact
     switching.  Defined in the oracle first; the GPU must agree env by env over 1.2 s of closed loop (north star: 1 s),
     and the contact-phase index / contact mask of every stage of every step must match as a SEQUENCE, bit exact."""
     E, n = 6, 120
     wp = lmh.walk_plan(range(E))
-    b = lmh.Batch(E, time_horizon=1.6, log_steps=n)
+    b = lmh.Batch(E, time_horizon=1.6, log_steps=n, **kern)
     b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"], plan_ids=np.arange(E))
     b.step(n)
     lg = b.log(0, n)
@@ -259,7 +292,7 @@ def test_walking_extension_against_oracle(oracle):
         b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"] + 4, plan_ids=np.arange(E))
 
 
-def test_config4_walk_and_push_against_oracle(oracle):
+def test_config4_walk_and_push_against_oracle(oracle, kern):
     """BASELINE configs[3] in small: walking plans + pushes (seed 0x5EED0004) strong enough that some environments
     fall, 200 steps, every environment against the oracle.  Integer work -- alive, committed steps, QP failures, the
     contact-phase / contact-mask / ZMP-window sequences -- bit exact; survivors' states 1e-7, CoM and feet 1e-9 m;
@@ -267,7 +300,7 @@ def test_config4_walk_and_push_against_oracle(oracle):
     E, S = 32, 200
     wp = lmh.walk_plan(range(E), seed=0x5EED0004)
     step, dv = lmh.push_plan(range(E), seed=0x5EED0004, max_speed=0.6, max_step=120)
-    b = lmh.Batch(E, time_horizon=1.6, log_steps=S)
+    b = lmh.Batch(E, time_horizon=1.6, log_steps=S, **kern)
     b.set_walk_plans(wp["zmp_x"], wp["zmp_y"], wp["phase_T"], wp["foot_coef"], wp["contact"], plan_ids=np.arange(E))
     b.set_pushes(step, dv)
     b.step(90)

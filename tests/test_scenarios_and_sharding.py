@@ -59,3 +59,48 @@ def test_two_rank_gather_with_gloo(tmp_path):
     step, dv = lmh.push_plan(range(100))
     assert np.array_equal(g[:, 0], np.arange(100.0)) and np.array_equal(g[:, 1], step) and np.array_equal(g[:, 2:], dv[:, :2])
     assert ms == 11.0                                  # max over ranks
+
+
+def test_walk_plan_is_keyed_by_global_env_id_and_matches_its_definition():
+    """the walking-plan generator behind the C ABI (ZMP::walkZMP + per-phase foot polynomials + contact masks)"""
+    wp = lmh.walk_plan(range(40), seed=0x5EED0003)
+    P, per = 6, 40
+    assert wp["contact"].shape == (40, P) and (wp["contact"] == [3, 2, 1, 2, 1, 3]).all()      # right foot swings first
+    assert wp["zmp_x"].shape[1] == P * per + 40 + 160 + 2 and wp["phase_T"] == 0.4
+    assert (wp["step_len"] >= 0.02).all() and (wp["step_len"] <= 0.05).all() and len(np.unique(wp["step_len"])) == 40
+    for world in (2, 4, 8):                          # any sharding reproduces the same per-env integers and doubles
+        parts = [lmh.walk_plan(range(*lmh.shard_range(40, r, world)), seed=0x5EED0003) for r in range(world)]
+        for k in ("zmp_x", "zmp_y", "foot_coef", "contact", "step_len"):
+            assert np.array_equal(np.concatenate([p[k] for p in parts]), wp[k]), k
+    # definition, environment 5: ZMP under the stance foot in single support, between the feet in double support;
+    # swing polynomials start at the foot's place, end one step ahead of the other foot, peak at step_height
+    L = wp["step_len"][5]
+    zx, zy, fc = wp["zmp_x"][5], wp["zmp_y"][5], wp["foot_coef"][5]
+    assert (zx[:per] == 0).all() and (zy[:per] == 0).all()                       # double support at the start
+    assert (zy[per:2 * per] == 0.05).all() and (zx[per:2 * per] == 0).all()      # right foot swings: ZMP under the left foot
+    assert (zy[2 * per:3 * per] == -0.05).all() and np.allclose(zx[2 * per:3 * per], L)
+    pv = lambda c, t: np.polyval(c[::-1], t)
+    rx, rz = fc[1, 0, 0:6], fc[1, 0, 12:20]                                      # phase 1, right foot
+    assert abs(pv(rx, 0.0)) < 1e-14 and abs(pv(rx, 0.4) - L) < 1e-12 and abs(pv(rz, 0.2) - 0.02) < 1e-12 and abs(pv(rz, 0.4)) < 1e-12
+    assert np.abs(fc[1, 1, 0:6] - [0, 0, 0, 0, 0, 0]).max() == 0 and fc[1, 1, 6] == 0.05        # the left foot stays put
+    fixed = lmh.walk_plan([3, 9], fixed_len=0.03)
+    assert (fixed["step_len"] == 0.03).all() and np.array_equal(fixed["zmp_x"][0], fixed["zmp_x"][1])
+
+
+def test_foot_coefficients_against_numpy():
+    """lmh_foot_coeff / lmh_poly_fit (findPolyCoeff, generalizedFunctions.cpp:103-163) against numpy's solve of the same
+    boundary-value system, and against the reference's stand-task coefficients"""
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    c = np.concatenate([lmh.foot_coefficients([0, -0.05, 0], [0, -0.05, 0], 0.0, 5.0), lmh.foot_coefficients([0, 0.05, 0], [0, 0.05, 0], 0.0, 5.0)])
+    assert np.abs(c - golden["foot_coef"]).max() < 1e-12
+    T, cur, des, hgt = 0.4, [0.01, -0.05, 0.0], [0.05, -0.04, 0.0], 0.02
+    got = lmh.foot_coefficients(cur, des, hgt, T)
+
+    def fit(pt, pv, vt, vv, at, av):
+        n = len(pt) + len(vt) + len(at)
+        A = np.array([[t ** j for j in range(n)] for t in pt] + [[j * t ** (j - 1) if j else 0.0 for j in range(n)] for t in vt]
+                     + [[j * (j - 1) * t ** (j - 2) if j > 1 else 0.0 for j in range(n)] for t in at])
+        return np.linalg.solve(A, np.array(list(pv) + list(vv) + list(av), float))
+    x = fit([0, T], [cur[0], des[0]], [0, T], [0, 0], [0, T], [0, 0])
+    z = fit([0, T / 2, T], [cur[2], hgt, des[2]], [0, T / 2, T], [0, 0, 0], [0, T], [0, 0])
+    assert np.abs(got[:6] - x).max() < 1e-9 * np.abs(x).max() and np.abs(got[12:] - z).max() < 1e-9 * np.abs(z).max()
