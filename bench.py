@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E] [--rollout S]
 
-Workload (config.workload): BASELINE.json configs[1] = NAO balance under random push perturbations, E = 4096
+Workload (config.workload), default: BASELINE.json configs[1] = NAO balance under random push perturbations, E = 4096
 environments per GPU, one push per env (seed 0x5EED0002, keyed by the global env id), S = 200
 RK4 steps per rollout.  One bench "step" = one whole rollout of the batch: restore the initial state, run S
 fused RK4 steps per env (4 stage evaluations each: kinematics + dynamics + LIPM-MPC + WBC QP + inverse
-dynamics), read the statistics back.
+dynamics), read the statistics back.  --workload walk = configs[2] (16384 envs x 240 steps, 1.6 s horizon, seed
+0x5EED0003), sweep = configs[3] (32768 envs per GPU x 240 steps, walking + pushes, seed 0x5EED0004), qp = configs[4]
+(cold WBC QPs and dense LIPM-MPC solves on frozen states); --envs / --rollout override the sizes.
 
   value : env-steps/s, whole job over all N GPUs, initial state resident in HBM (device-to-device restore),
           timed with CUDA events on the launching stream, max over ranks.
@@ -154,8 +156,10 @@ def run_reference_arm(args):
     except Exception:
         lib = None
     if lib is not None:
-        note = ("upstream src/*.cpp + apps/offline/main.cpp compiled unmodified (-O2) against shim Eigen/qpOASES headers "
-                "(oracle/refbuild); solves each stage's WBC QP twice and rebuilds the MPC Hessian per call, as upstream does")
+        note = ("reference sources + NAIVE shims: upstream src/*.cpp + apps/offline/main.cpp compiled unmodified (-O2) against "
+                "this repository's stand-ins for Eigen (eager, heap-allocating) and qpOASES (oracle/refbuild; the real "
+                "libraries are absent and would be faster); solves each stage's WBC QP twice and rebuilds the MPC Hessian "
+                "per call, as upstream does.  The tighter CPU baseline is the oracle port (cpu_baseline of the GPU arm).")
     else:
         orc_py.build()
         lib, kind = orc_py.oracle(), "port"
