@@ -190,3 +190,27 @@ def test_inverse_kinematics_matches_reference_vectors(oracle, ik_golden):
     for i in range(len(g["q"])):
         s = oracle.sim(com=g["com"][i], rf=g["rf"][i], lf=g["lf"][i])
         assert np.abs(s.get_state()[0][:30] - g["q"][i]).max() < 1e-12 and s.ik_iterations == g["iters"][i]
+
+
+def test_health_rule_definition(oracle):
+    """EXTENSION (orc_capi.h): a step is committed only if healthy; a fallen environment is frozen at its last healthy state
+    with its clock and statistics closed, and a healthy one is untouched by the rule"""
+    cfg = oracle.default_config()
+    E, S = 3, 80
+    step = np.array([5, 5, -1], np.int32)
+    dv = np.zeros((E, 6)); dv[0, 0] = 2.5; dv[1, 0] = 0.05                      # env 0 is thrown over, env 1 nudged, env 2 left alone
+    r = oracle.batch_rollout_ex(cfg, E, S, push_step=step, push_dv=dv, n_threads=3, log=True)
+    st = r["stats"]
+    assert list(st["alive"]) == [0, 1, 1] and st["steps"][0] < S and list(st["steps"][1:]) == [S, S]
+    n0 = int(st["steps"][0])
+    tt = 0.0
+    for _ in range(n0):
+        tt += 0.01
+    assert st["t"][0] == tt and np.isfinite(r["x"][0]).all()                     # clock stopped with the environment
+    assert np.array_equal(r["log"][0]["x"][n0 - 1], r["x"][0])                   # frozen at the last committed state
+    assert np.array_equal(r["log"][0]["x"][S - 1], r["x"][0])                    # ... and still there at the end
+    assert st["max_abs_tau"][0] < 100.0 and st["max_com_err"][0] < 0.5          # the failing step never reached the statistics
+    # a healthy environment equals the plain rollout bit for bit (the rule only decides, it does not compute)
+    x2, _, _, _ = oracle.batch_rollout(cfg, 1, S)
+    assert np.array_equal(r["x"][2], x2[0])
+    assert (r["log"][2]["phase"] == 0).all() and (r["log"][2]["contact"] == 3).all()      # stand task: one phase, both feet
