@@ -46,12 +46,17 @@ DEFAULTS = {"push": (4096, 200, 0x5EED0002, 50), "walk": (16384, 240, 0x5EED0003
             "qp": (4096, 50, 0x5EED0002, 50)}
 FLOP_PER_ENV_STEP = 0.51e6          # SURVEY.md 8(d) / App. C, active-set changes k = 0 (conservative)
 STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 48 + 24   # state read+write, stats, CoM per launch
-# dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel from the committed ncu --set full capture (E = 4096;
-# the traffic of a launch does not depend on the number of steps it fuses: the state stays on chip)
-NCU_DRAM_BYTES_PER_LAUNCH = 3339264 + 13568
-NCU_TRAFFIC_SOURCE = ("profiles/r01_rollout_v16_settled.txt: dram read 3.34 MB + write 0.01 MB for a 10-step launch of "
-                      "4096 envs (algorithmic: 6.3 MB of state and statistics per launch, independent of the step count; the "
-                      "written state was still in the 126 MB L2 when the kernel ended)")
+# dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel_multi from the committed ncu --set full captures (the
+# traffic of a launch does not depend on the number of steps it fuses: the state stays on chip).  Walking reads each
+# environment's own plan (ZMP reference + per-phase foot polynomials) as well.
+NCU_DRAM_BYTES_PER_LAUNCH = {"push": 3474688 + 0, "walk": 68428800 + 4722688, "sweep": None}
+NCU_TRAFFIC_SOURCE = {"push": "profiles/r02_rollout_push.txt: dram read 3.47 MB + write 0 for a 10-step launch of 4096 envs "
+                              "(algorithmic: 6.3 MB of state and statistics per launch, independent of the step count; the "
+                              "written state was still in the 126 MB L2 when the kernel ended)",
+                      "walk": "profiles/r02_rollout_walk.txt: dram read 68.4 MB + write 4.7 MB for a 10-step launch of 16384 envs "
+                              "(algorithmic: 25 MB of state and statistics + 16384 plans x 9 KB = 147 MB if every plan were read whole; "
+                              "a 10-step launch touches only the current ZMP window and phase)",
+                      "sweep": "no capture of the 32768-environment sweep launch (same kernel and plan layout as the walking workload)"}
 
 
 # ---------------------------------------------------------------- distributed helpers (also unit-tested with gloo)
@@ -425,7 +430,7 @@ def run_ours(args):
             "wall_ms_timed_region": wall_ms,
             "gather_ms": gather_ms,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE, "kernel": "rollout_kernel_multi" if info["envs_per_block"] > 1 else "rollout_kernel", "kernel_ms_per_launch": kern,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH[args.workload], "traffic_source": NCU_TRAFFIC_SOURCE[args.workload], "kernel": "rollout_kernel_multi" if info["envs_per_block"] > 1 else "rollout_kernel", "kernel_ms_per_launch": kern,
                          "flop_per_env_step": FLOP_PER_ENV_STEP,
                          "peak_source": "BUILDER-MEASURED: FP64 FMA micro-kernel run in this process (lmh_measure_fp64_peak; "
                                         "97 % of the nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2 TFLOP/s); "

@@ -499,9 +499,9 @@ def test_mpc_dense_solver_on_the_device(oracle):
     """N2: Mpc3dLip::compute as a DENSE solve per problem (gradient by a dense product, shared Cholesky factor, forward and
     back substitution), FP64 FMA and FP64 tensor-core (DMMA) builds, against numpy's dense solve of the reference's own
     formulation (Px, Pu from Mpc3dLip::initialize), against the oracle's Mpc3dLip, and against the gain-vector form the
-    closed-loop kernel uses.  Horizons of BASELINE configs[4] (16, 32, 64) plus the app's 50."""
+    closed-loop kernel uses.  Horizons of BASELINE configs[4] (16, 32, 64) plus the app's 50 and the walking workloads' 160."""
     rng = np.random.default_rng(11)
-    for N in (16, 32, 50, 64):
+    for N in (16, 32, 50, 64, 160):                    # 160 = the walking workloads' 1.6 s horizon
         hz = N * 0.01 * (1.0 + 1e-9)                      # (int)(horizon / dt) == N as mpcLinearPendulum.hpp:49 computes it
         b = lmh.Batch(2, time_horizon=hz)
         Px, Pu = b.mpc_tables()
