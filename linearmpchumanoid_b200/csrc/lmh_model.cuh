@@ -44,6 +44,12 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+#ifndef LMH_RSQRT_CUBIC
+#define LMH_RSQRT_CUBIC 1
+#endif
+#ifndef LMH_LOGMAP_SERIES
+#define LMH_LOGMAP_SERIES 1
+#endif
 #ifndef LMH_QP_GENERAL_NOINLINE
 #define LMH_QP_GENERAL_NOINLINE 0     // measured: as a real call it costs 5 % (spills around the call); inlined, the split
                                       // of qp_phase into hot path + general iteration removed the kernel's last spills
@@ -268,12 +274,22 @@ LMH_HD double lmh_rsqrt(double x) {
     // library's special-case path (a branch and a call) has nothing to do here
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if LMH_RSQRT_CUBIC
+    // one third-order step, y (1 + e/2 + 3 e^2/8) with e = 1 - x y^2: from a 2^-22 seed the error term (5/16) e^3 is below
+    // 2^-66, so this is as exact as two Newton steps at five dependent operations instead of eight (the factorisations
+    // call this eighteen times in a row per stage, each waiting for the one before)
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double q = e * fma(0.375, e, 0.5);
+    return fma(y, q, y);
+#else
     double t = x * y;
     double e = fma(-t, y, 1.0);
     y = fma(0.5 * y, e, y);
     t = x * y;
     e = fma(-t, y, 1.0);
     return fma(0.5 * y, e, y);
+#endif
 #else
     return 1.0 / sqrt(x);
 #endif
@@ -856,7 +872,7 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
         }
     }
     // walking extension: phase of this stage (integer work, same FP64 expression as the oracle)
-    int ph = (int)(w.t / P.phase_T);
+    int ph = P.n_phases > 1 ? (int)(w.t / P.phase_T) : 0;      // (one phase: the clamp below gives 0 whatever t is; no division)
     ph = ph < 0 ? 0 : (ph >= P.n_phases ? P.n_phases - 1 : ph);
     const double tl = mul_then_add(w.t, -(double)ph, P.phase_T);
     LMH_FOR(i, 1) { w.phase = ph; w.contact = P.contact[(size_t)plan_id * P.n_phases + ph]; }
@@ -877,9 +893,25 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
                 for (int c = 0; c < 3; ++c) E[3 * r + c] = K.Rdes[r] * w.Rs[s][c] + K.Rdes[3 + r] * w.Rs[s][3 + c] + K.Rdes[6 + r] * w.Rs[s][6 + c];
             double tr = E[0] + E[4] + E[8];
             double cth = fmax(-1.0, fmin(1.0, (tr - 1.0) / 2.0));
-            double phi = acos(cth);
             double ax[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
-            double sc = phi < 1e-6 ? 0.5 : phi / (2.0 * sin(phi));
+            double sc;
+#if defined(__CUDA_ARCH__) && LMH_LOGMAP_SERIES
+            // phi / (2 sin phi) as a function of x = 1 - cos phi, exactly: acos(1 - x) = sqrt(2x) P(x/2), sin phi = sqrt(2x)
+            // sqrt(1 - x/2), P(y) = sum (2n)! / (4^n n!^2 (2n+1)) y^n (the arcsine series).  Below x = 1/64 (10 degrees: a
+            // foot in or near contact) eight terms are exact to 3e-17 and replace acos, sin and a division -- library
+            // routines with slow paths -- by a dozen FMAs; 1 - cth is exact there (Sterbenz).  Same function, same value to
+            // the last bits; beyond that angle the library path is taken.
+            const double xs = 1.0 - cth;
+            if (xs < 1.0 / 64.0) {
+                const double Ps = 1.0 + xs * (1.0 / 12 + xs * (3.0 / 160 + xs * (5.0 / 896 + xs * (35.0 / 18432 + xs * (63.0 / 90112
+                                + xs * (231.0 / 851968 + xs * (143.0 / 1310720)))))));
+                sc = xs < 5e-13 ? 0.5 : 0.5 * Ps * lmh_rsqrt(1.0 - 0.5 * xs);       // (phi < 1e-6: upstream's small-angle branch)
+            } else
+#endif
+            {
+                double phi = acos(cth);
+                sc = phi < 1e-6 ? 0.5 : phi / (2.0 * sin(phi));
+            }
             double l[3] = {sc * ax[0], sc * ax[1], sc * ax[2]};
             double eo = -rot_row(K.Rdes, k, l);
             out = K.KpF * eo + K.KdF * (0.0 - velk) + 0.0;
