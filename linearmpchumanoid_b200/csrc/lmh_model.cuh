@@ -919,10 +919,23 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
             int j = k - 3;
             const double* cf = P.foot_coef + (((size_t)plan_id * P.n_phases + ph) * 2 + s) * 20 + (j == 0 ? 0 : j == 1 ? 6 : 12);
             int nc = j == 2 ? 8 : 6;
-            double pos = 0.0, vr = 0.0, ar = 0.0, tp = 1.0, tv = 1.0, ta = 1.0;
-            for (int i = 0; i < nc; ++i) { pos += cf[i] * tp; tp *= tl; }
-            for (int i = 1; i < nc; ++i) { vr += (double)i * cf[i] * tv; tv *= tl; }
-            for (int i = 2; i < nc; ++i) { ar += (double)(i - 1) * ((double)i * cf[i]) * ta; ta *= tl; }
+            // polyval of the polynomial, of its derivative and of its second derivative (generalizedFunctions.cpp:165-193) in
+            // the same order of operations, with ONE chain of powers serving the three sums (upstream's three chains hold the
+            // same products) and coefficients beyond the degree read as zero (adding +0 changes nothing): three independent
+            // accumulations of fixed length instead of three dependent loops of variable length
+            double pw[8], c[8];
+            pw[0] = 1.0;
+            LMH_UNROLL
+            for (int i = 1; i < 8; ++i) pw[i] = pw[i - 1] * tl;
+            LMH_UNROLL
+            for (int i = 0; i < 8; ++i) c[i] = i < nc ? cf[i] : 0.0;
+            double pos = 0.0, vr = 0.0, ar = 0.0;
+            LMH_UNROLL
+            for (int i = 0; i < 8; ++i) pos += c[i] * pw[i];
+            LMH_UNROLL
+            for (int i = 1; i < 8; ++i) vr += ((double)i * c[i]) * pw[i - 1];
+            LMH_UNROLL
+            for (int i = 2; i < 8; ++i) ar += ((double)(i - 1) * ((double)i * c[i])) * pw[i - 2];
             out = K.KpF * (pos - w.ps[s][j]) + K.KdF * (vr - velk) + ar;
         }
         w.footAccRef[it] = out;

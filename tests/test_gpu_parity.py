@@ -569,3 +569,38 @@ def test_walk_plans_generated_inside_the_library(oracle):
     assert not np.array_equal(a.get_state()[0][0], a.get_state()[0][1])          # the plans differ per environment
     ws = lmh.walk_plan([7], fixed_len=0.035)                                       # ZMP(Task::Walk, ...): one nominal step length
     assert ws["step_len"][0] == 0.035 and ws["zmp_x"][0].max() > 0.06
+
+
+def test_full_size_walking_sweep_properties(oracle):
+    """BASELINE sizes of configs 3-4 (16384 and 32768 environments per GPU): properties that need no oracle at that size --
+    clean per-environment statistics, determinism, sharding invariance of a shard that does not start at 0 -- plus the
+    oracle on a handful of environments picked out of the big batch"""
+    E, S, lo = 32768, 30, 5000
+    step, dv = lmh.push_plan(range(E), seed=0x5EED0004, max_speed=0.6, max_step=20)
+    b = lmh.Batch(E, time_horizon=1.6)
+    b.make_walk_plans(first_env_id=0, seed=0x5EED0004)
+    b.set_pushes(step, dv)
+    b.step(S)
+    x, vh, t = b.get_state()
+    st = b.stats()
+    assert np.isfinite(x).all() and (st["qp_fail"] == 0).all()
+    assert (st["max_abs_tau"] < lmh.TAU_LIMIT).all() and (st["max_com_err"] < lmh.COM_ERR_LIMIT).all()   # no garbage maxima
+    assert ((st["steps"] == S) == (st["alive"] == 1)).all() and st["alive"].mean() > 0.9
+    b.close()
+    # a shard of 16384 environments starting at global id 5000 reproduces its slice bit for bit
+    b2 = lmh.Batch(16384, time_horizon=1.6)
+    b2.make_walk_plans(first_env_id=lo, seed=0x5EED0004)
+    b2.set_pushes(step[lo:lo + 16384], dv[lo:lo + 16384])
+    b2.step(S)
+    x2 = b2.get_state()[0]
+    st2 = b2.stats()
+    assert np.array_equal(x2, x[lo:lo + 16384]) and np.array_equal(st2["steps"], st["steps"][lo:lo + 16384])
+    b2.close()
+    # ... and eight environments of the big batch against the oracle
+    ids = [0, 4097, 9999, 16383, 16384, 20000, 31111, 32767]
+    wp = lmh.walk_plan(ids, seed=0x5EED0004)
+    r = oracle.batch_rollout_ex(oracle.default_config(time_horizon=1.6), len(ids), S, push_step=step[ids], push_dv=dv[ids], walk=wp,
+                                n_threads=8)
+    assert np.array_equal(r["stats"]["alive"], st["alive"][ids]) and np.array_equal(r["stats"]["steps"], st["steps"][ids])
+    ok = st["alive"][ids] == 1
+    assert scalederr(x[ids][ok], r["x"][ok]) < 1e-8
