@@ -44,6 +44,9 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+#ifndef LMH_SHORTCUT_DMMA
+#define LMH_SHORTCUT_DMMA 1     // 1: the 6 x 6 system of the all-free QP shortcut (D^-1 Jb, Sa + Jb'D^-1 Jb) on the FP64 tensor cores
+#endif
 #ifndef LMH_RSQRT_CUBIC
 #define LMH_RSQRT_CUBIC 1
 #endif
@@ -1526,6 +1529,43 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     if (!have_point && contact != 0) {     // a swing foot (walking extension) carries no force: its block of D^-1 is zero
         double* U = Wb;                // [2][6][6] : D^-1 Jb_f
         double* S6 = Ay;               // [6][6]    : lower triangle of Sa + Jb' D^-1 Jb
+#if defined(__CUDA_ARCH__) && LMH_SHORTCUT_DMMA
+        if (Cx::NT == 32) {
+            // the two 6 x 6 x 6 products per foot on the FP64 tensor cores (m8n8k4, two k-steps each): U_f = D^-1 Jb_f with
+            // Jb_f as B, then S6 = Sa + sum_f Jb_f' U_f with the SAME fragments of Jb_f as A (transposed on the fly) and
+            // U_f read back from shared memory as B (it is needed there anyway for f = D^-1 Jb lam)
+            const int lane = cx.tid, fr = lane >> 2, fk = lane & 3, c0 = 2 * fk;
+            const bool inr = fr < 6, inc = c0 < 6;
+            double jb[2][2];           // [foot][k-step]: Jb_f[k = 4 kt + fk][fr]
+            double s6a = (inr && inc) ? w.Sa[6 * fr + c0] : 0.0, s6b = (inr && inc) ? w.Sa[6 * fr + c0 + 1] : 0.0;
+            LMH_UNROLL
+            for (int f = 0; f < 2; ++f) {
+                double ua = 0.0, ub = 0.0;
+                LMH_UNROLL
+                for (int kt = 0; kt < 2; ++kt) {
+                    const int k = 4 * kt + fk;
+                    jb[f][kt] = (k < 6 && inr) ? w.JFc[72 * f + 12 * k + fr] : 0.0;
+                    const double di = (k < 6 && inr) ? K.Dinv[6 * fr + k] : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(ua), "+d"(ub) : "d"(di), "d"(jb[f][kt]));
+                }
+                const bool on = (contact >> f) & 1;
+                if (inr && inc) { U[36 * f + 6 * fr + c0] = on ? ua : 0.0; U[36 * f + 6 * fr + c0 + 1] = on ? ub : 0.0; }
+            }
+            __syncwarp();
+            LMH_UNROLL
+            for (int f = 0; f < 2; ++f) {
+                LMH_UNROLL
+                for (int kt = 0; kt < 2; ++kt) {
+                    const int k = 4 * kt + fk;
+                    const double ub = (k < 6 && inr) ? U[36 * f + 6 * k + fr] : 0.0;      // B fragment: U_f[k][n = fr]
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(s6a), "+d"(s6b) : "d"(jb[f][kt]), "d"(ub));
+                }
+            }
+            if (inr && inc) { S6[6 * fr + c0] = s6a; S6[6 * fr + c0 + 1] = s6b; }
+            __syncwarp();
+        } else
+#endif
+        {
         LMH_FOR(it, 72) {
             const int f = it / 36, k = (it % 36) / 6, sidx = it % 6;
             double sd = 0.0;
@@ -1542,6 +1582,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
             }
         }
         cx.sync();
+        }
         {
             double A[36], Ainv[6];
             LMH_UNROLL
