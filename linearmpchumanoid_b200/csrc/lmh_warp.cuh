@@ -53,6 +53,9 @@ __device__ __forceinline__ double cross3_sel(const double* a, const double* b, i
 #define LMH_XSTRIDE 6      // doubles between the chains' slots in the exchange buffers: 6 = lane order (lane 6c + r writes word
                            // 6c + r: no bank conflicts), 8 = one 64-byte line per chain
 #endif
+#ifndef LMH_FACTOR_DMMA
+#define LMH_FACTOR_DMMA 1  // 1: Schur complement of the leg blocks in the 18 x 18 factorisation on the FP64 tensor cores
+#endif
 #ifndef LMH_JTJ_DMMA
 #define LMH_JTJ_DMMA 1     // 1: J'J of the sole Jacobians (the J'W_F J term of the QP Hessian) on the FP64 tensor cores
 #endif
@@ -708,13 +711,47 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
         if (lane == 6 + k) { w.ladiag[6 + k] = likb; w.ladinv[6 + k] = rsb; }
         __syncwarp();
     }
+#if LMH_FACTOR_DMMA
+    // Schur complement of the two leg blocks on the base block and on the right-hand-side rows, as one product on the FP64
+    // tensor cores: rows 12..27 (six base rows, ten right-hand-side rows) times the base rows' leg part,
+    // (16 x 12) (12 x 6): two 8 x 8 tiles, three k-steps each, instead of 72 broadcast loads and 72 FMAs per lane
+    {
+        if (yrow) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) Yt[NQ * yr + j] = h[j];          // (stored at the end otherwise)
+        }
+        __syncwarp();
+        const int fr = lane >> 2, fk = lane & 3, c0 = 2 * fk;
+        double d0a = 0, d0b = 0, d1a = 0, d1b = 0;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            const int m = 4 * kt + fk;
+            const int p0 = 12 + fr, p1 = 20 + fr;                          // rows of the two tiles
+            const double a0 = p0 < ND1 ? L1[LD1 * p0 + m] : Yt[NQ * (p0 - ND1) + m];
+            const double a1 = Yt[NQ * (p1 - ND1) + m];
+            const double b = fr < 6 ? L1[LD1 * (12 + fr) + m] : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0a), "+d"(d0b) : "d"(a0), "d"(b));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d1a), "+d"(d1b) : "d"(a1), "d"(b));
+        }
+        double* Ts = w.u.s.Bm;                                             // [16][6] (free again: the rows have their J'J entries)
+        if (c0 < 6) {
+            Ts[6 * fr + c0] = d0a; Ts[6 * fr + c0 + 1] = d0b;
+            Ts[6 * (8 + fr) + c0] = d1a; Ts[6 * (8 + fr) + c0 + 1] = d1b;
+        }
+        __syncwarp();
+        if (lane >= 12 && lane < ND1 + NYR) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) h[12 + c] -= Ts[6 * (lane - 12) + c];
+        }
+    }
+#endif
     // the base block
 #pragma unroll
     for (int k = 12; k < ND1; ++k) {
         double s = h[k], t = 0.0;
         const double* Lk = L1 + LD1 * k;
 #pragma unroll
-        for (int m = 0; m < k; ++m) {
+        for (int m = LMH_FACTOR_DMMA ? 12 : 0; m < k; ++m) {
             const double l = Lk[m];
             if (m & 1) t -= h[m] * l; else s -= h[m] * l;
         }
@@ -729,7 +766,7 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
     }
     if (yrow) {
 #pragma unroll
-        for (int j = 0; j < ND1; ++j) Yt[NQ * yr + j] = h[j];
+        for (int j = LMH_FACTOR_DMMA ? 12 : 0; j < ND1; ++j) Yt[NQ * yr + j] = h[j];
     }
     __syncwarp();
 }
