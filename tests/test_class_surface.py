@@ -57,6 +57,17 @@ def test_our_app_and_probe_compile_and_refuse_to_run_without_a_gpu(tmp_path, pro
         assert out.returncode != 0 and "no CUDA device" in out.stderr          # loud, not a fallback
 
 
+def test_host_side_types_and_helpers(tmp_path):
+    """CPU only: the Eigen-API subset the headers fall back to without Eigen3 (comma initialiser, segment / head / tail views,
+    the aliasing assignments of main.cpp:111-116, the arithmetic of rk4Step) and the generalizedFunctions helpers against
+    their definitions; findPolyCoeff goes through the library's host-only entry point"""
+    exe = str(tmp_path / "eigen_lite_probe")
+    r = _compile(os.path.join(ROOT, "tests", "cpp", "eigen_lite_probe.cpp"), exe, extra=("-Wextra",))
+    assert r.returncode == 0 and "warning" not in r.stderr, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
 def test_class_surface_has_the_reference_headers():
     want = ["robotInfo/Robot.hpp", "robotInfo/linkInertia.hpp", "robotInfo/robotParameters.hpp", "controller/controller.hpp",
             "controller/Dynamics.hpp", "controller/invKinematics.hpp", "controller/mpcLinearPendulum.hpp",
