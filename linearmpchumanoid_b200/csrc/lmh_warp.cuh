@@ -53,6 +53,9 @@ __device__ __forceinline__ double cross3_sel(const double* a, const double* b, i
 #define LMH_XSTRIDE 6      // doubles between the chains' slots in the exchange buffers: 6 = lane order (lane 6c + r writes word
                            // 6c + r: no bank conflicts), 8 = one 64-byte line per chain
 #endif
+#ifndef LMH_FK_UNROLL
+#define LMH_FK_UNROLL 1
+#endif
 #ifndef LMH_FACTOR_DMMA
 #define LMH_FACTOR_DMMA 1  // 1: Schur complement of the leg blocks in the 18 x 18 factorisation on the FP64 tensor cores
 #endif
@@ -176,8 +179,15 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
             pp = R0 * P[9] + R1 * P[10] + R2 * P[11] + pp;
             R0 = n0; R1 = n1; R2 = n2;
         }
+        // (unrolled: the local transforms of all levels are there already, so their loads can be issued ahead of the recurrence)
+#if LMH_FK_UNROLL
+#pragma unroll
+        for (int d = 0; d < MAXDEPTH; ++d) {
+            if (d >= len) break;
+#else
 #pragma unroll 1
         for (int d = 0; d < len; ++d) {
+#endif
             const double* L = Xl + 12 * (first + d);
             double* O = Tw + 12 * (first + d);
             const double n0 = R0 * L[0] + R1 * L[3] + R2 * L[6];
