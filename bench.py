@@ -450,7 +450,7 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             # a bounded sample of the SAME workload: the first n_cpu envs, full rollout length (the 1.6 s horizon makes an
             # oracle stage about three times dearer, hence fewer envs for the walking workloads)
-            n_cpu, s_cpu = (16 if not walk else 4) * cores, S
+            n_cpu, s_cpu = (32 if not walk else 12) * cores, S      # about 10 s of CPU work on the box's 16 threads
             wp = lmh.walk_plan(range(n_cpu), seed=seed) if walk else None
             ps, dv = push_step[:n_cpu], push_dv[:n_cpu]
             cfg = lib.default_config(second_wbc=0, mpc_rebuild_hessian=0, **({"time_horizon": 1.6} if walk else {}))
