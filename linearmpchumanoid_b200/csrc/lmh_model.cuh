@@ -47,6 +47,9 @@ constexpr int LDQ = 33;
 #ifndef LMH_SHORTCUT_DMMA
 #define LMH_SHORTCUT_DMMA 1     // 1: the 6 x 6 system of the all-free QP shortcut (D^-1 Jb, Sa + Jb'D^-1 Jb) on the FP64 tensor cores
 #endif
+#ifndef LMH_ALIGN_STAGES
+#define LMH_ALIGN_STAGES 1      // 1: the warps of a block meet at a barrier once per stage (shared instruction fetches)
+#endif
 #ifndef LMH_RSQRT_CUBIC
 #define LMH_RSQRT_CUBIC 1
 #endif
@@ -227,7 +230,7 @@ struct Ctx {
 #endif
     }
     LMH_HD void align() const {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && LMH_ALIGN_STAGES
         if (NT == 32) {
             if (bar_id < 0) __syncthreads();                 // every warp of the block is live
             else if (bar_id > 32) asm volatile("bar.sync 1, %0;" ::"r"(bar_id) : "memory");
