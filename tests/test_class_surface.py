@@ -126,8 +126,12 @@ def test_class_surface_numbers(golden, probe):
     for k, shape in (("M", (30, 30)), ("C", 30), ("Cg", 30), ("AG", (6, 30)), ("AGpqp", 6), ("Jpqp", 12), ("JFeet", (12, 30))):
         assert scalederr(p[k].reshape(shape), g["stage_" + k][0]) < 1e-8, k
     assert np.array_equal(p["JR"], p["JFeet"][:180]) and np.array_equal(p["JL"], p["JFeet"][180:])
-    AG = g["stage_AG"][0]
-    assert np.abs(p["comVel"]).max() > 1e-3 and np.isfinite(p["angMom"]).all() and AG.shape == (6, 30)
+    # Robot::updateVelocityState / computeComMomentum (Robot.cpp:271-274,300-310) at v = 0.01 everywhere, from the reference's
+    # own AG and X_0: swap [v_lin, w] -> [w, v_lin], express in the base frame, h = AG v
+    AG, X0, v = g["stage_AG"][0], g["stage_X_all"][0][0], np.full(30, 0.01)
+    vb = v.copy(); vb[:6] = X0 @ np.concatenate([v[3:6], v[0:3]])
+    h = AG @ vb
+    assert np.abs(p["comVel"] - h[3:] / float(g["mass"])).max() < 1e-9 and np.abs(p["angMom"] - h[:3]).max() < 1e-9
     assert list(p["zmp_sizes"][:2]) == [550, 150] and p["zmp_sizes"][2] == 0.05
     assert np.abs(p["xRef"] - g["stage_xRef"][0]).max() < 1e-9 and np.abs(p["yRef"] - g["stage_yRef"][0]).max() < 1e-9
     assert p["yRef_left"][2] != 0.0 and abs(p["zcom"][0] - float(g["zcom"])) < 1e-9 and p["zcom"][1] == 0.26
