@@ -67,15 +67,16 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 10 : 1) rollout_kernel(Params p
     ws_reset(cx, w);
     for (int i = threadIdx.x; i < 60; i += NT) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = threadIdx.x; i < 30; i += NT) w.vh[i] = p.vh[(size_t)env * 30 + i];
-    double t = p.t[env];
+    double& t = w.t_env;                                    // clock and statistics live in the workspace (shared memory):
+    StatsAcc& st = w.stats;                                 // nothing of the bookkeeping is held in registers across a stage
     const int plan_id = p.plan_id ? p.plan_id[env] : 0;
     const int push_at = p.push_step ? p.push_step[env] : -1;
-    StatsAcc st;
-    {
+    if (cx.tid == 0) {
+        t = p.t[env];
         const LmhStats& s0 = p.stats[env];
         st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
         st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
-        if (cx.tid == 0) w.dead = s0.alive ? 0 : 1;
+        w.dead = s0.alive ? 0 : 1;
     }
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {
@@ -140,15 +141,16 @@ __global__ void __launch_bounds__(32 * kMaxEpb, 1) rollout_kernel_multi(Params p
     ws_reset(cx, w);
     for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
-    double t = p.t[env];
+    double& t = w.t_env;                                    // clock and statistics live in the workspace (shared memory):
+    StatsAcc& st = w.stats;                                 // nothing of the bookkeeping is held in registers across a stage
     const int plan_id = p.plan_id ? p.plan_id[env] : 0;
     const int push_at = p.push_step ? p.push_step[env] : -1;
-    StatsAcc st;
-    {
+    if (cx.tid == 0) {
+        t = p.t[env];
         const LmhStats& s0 = p.stats[env];
         st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
         st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
-        if (cx.tid == 0) w.dead = s0.alive ? 0 : 1;
+        w.dead = s0.alive ? 0 : 1;
     }
     cx.sync();
     for (int s = 0; s < p.n_steps; ++s) {
@@ -213,15 +215,16 @@ __global__ void __launch_bounds__(96, 1) rollout_kernel_helpers(Params p, int en
     ws_reset(cx, w);
     for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
-    double t = p.t[env];
+    double& t = w.t_env;                                    // clock and statistics live in the workspace (shared memory):
+    StatsAcc& st = w.stats;                                 // nothing of the bookkeeping is held in registers across a stage
     const int plan_id = p.plan_id ? p.plan_id[env] : 0;
     const int push_at = p.push_step ? p.push_step[env] : -1;
-    StatsAcc st;
-    {
+    if (cx.tid == 0) {
+        t = p.t[env];
         const LmhStats& s0 = p.stats[env];
         st.max_tau = s0.max_abs_tau; st.max_err = s0.max_com_err; st.max_qpp = s0.max_abs_qpp;
         st.qp_iters = s0.qp_iters; st.qp_fail = s0.qp_fail; st.steps = s0.steps; st.alive = s0.alive; st.qp_fallback = s0.qp_fallback;
-        if (lane == 0) w.dead = s0.alive ? 0 : 1;
+        w.dead = s0.alive ? 0 : 1;
     }
     cx.sync();
     cx.helpers = 96;
@@ -379,6 +382,34 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 
 }  // namespace
 
+// Device copies of the QP working-set table (lmh_setup.hpp: 65536 x 72 doubles = 37.7 MB): one per (device, host table),
+// reference counted, shared by every handle that uses it.
+namespace {
+struct QpTabDev { int device; const void* key; double* d_tab; int refs; };
+std::mutex g_qp_tab_mu;
+std::vector<QpTabDev> g_qp_tabs;
+int32_t qp_table_acquire(int device, const std::shared_ptr<const std::vector<double>>& host, const double** d_out) {
+    std::lock_guard<std::mutex> lock(g_qp_tab_mu);
+    for (QpTabDev& t : g_qp_tabs)
+        if (t.device == device && t.key == host.get()) { ++t.refs; *d_out = t.d_tab; return LMH_OK; }
+    double* d = nullptr;
+    CU(cudaMalloc(&d, host->size() * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d, host->data(), host->size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return fail(LMH_ECUDA, std::string("working-set table upload: ") + cudaGetErrorString(e)); }
+    g_qp_tabs.push_back(QpTabDev{device, host.get(), d, 1});
+    *d_out = d;
+    return LMH_OK;
+}
+void qp_table_release(int device, const void* key) {
+    std::lock_guard<std::mutex> lock(g_qp_tab_mu);
+    for (size_t i = 0; i < g_qp_tabs.size(); ++i)
+        if (g_qp_tabs[i].device == device && g_qp_tabs[i].key == key) {
+            if (--g_qp_tabs[i].refs == 0) { cudaFree(g_qp_tabs[i].d_tab); g_qp_tabs.erase(g_qp_tabs.begin() + i); }
+            return;
+        }
+}
+}  // namespace
+
 struct LmhBatch {
     LmhConfig cfg;
     HostModel* hm = nullptr;
@@ -386,6 +417,7 @@ struct LmhBatch {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Consts* dK = nullptr;
+    const void* qp_tab_key = nullptr;      // which shared device table this handle holds a reference on
     double *d_x = nullptr, *d_vh = nullptr, *d_t = nullptr, *d_push_dv = nullptr, *d_com = nullptr;
     double *d_zmp_x = nullptr, *d_zmp_y = nullptr, *d_foot = nullptr;
     int32_t *d_plan_id = nullptr, *d_push_step = nullptr, *d_order = nullptr;
@@ -527,7 +559,17 @@ static int32_t create_on_device(LmhBatch* h, const LmhConfig* cfg, int32_t n_env
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     size_t E = (size_t)n_env;
     CU(cudaMalloc(&h->dK, sizeof(Consts)));
-    CU(cudaMemcpy(h->dK, &h->hm->K, sizeof(Consts), cudaMemcpyHostToDevice));
+    {
+        // the device copy of the constants points at the device copy of the working-set table (shared by every handle
+        // of this device that uses the same generators)
+        const double* d_tab = nullptr;
+        int32_t rt = qp_table_acquire(h->cfg.device, h->hm->qp_tab, &d_tab);
+        if (rt != LMH_OK) return rt;
+        h->qp_tab_key = h->hm->qp_tab.get();
+        Consts kc = h->hm->K;
+        kc.qp_tab = d_tab;
+        CU(cudaMemcpy(h->dK, &kc, sizeof(Consts), cudaMemcpyHostToDevice));
+    }
     CU(cudaMalloc(&h->d_x, E * 60 * sizeof(double))); CU(cudaMalloc(&h->d_vh, E * 30 * sizeof(double)));
     CU(cudaMalloc(&h->d_t, E * sizeof(double))); CU(cudaMalloc(&h->d_push_dv, E * 6 * sizeof(double)));
     CU(cudaMalloc(&h->d_com, E * 3 * sizeof(double)));
@@ -592,6 +634,7 @@ void lmh_destroy(LmhBatch* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->qp_tab_key) qp_table_release(h->cfg.device, h->qp_tab_key);
     cudaFree(h->dK); cudaFree(h->d_x); cudaFree(h->d_vh); cudaFree(h->d_t); cudaFree(h->d_push_dv); cudaFree(h->d_com);
     cudaFree(h->d_plan_id); cudaFree(h->d_push_step); cudaFree(h->d_order); cudaFree(h->d_stats); cudaFree(h->d_stats0); cudaFree(h->d_dump); cudaFree(h->d_log);
     cudaFree(h->d_zmp_x); cudaFree(h->d_zmp_y); cudaFree(h->d_foot); cudaFree(h->d_contact); cudaFree(h->d_scratch); cudaFree(h->d_mpc);

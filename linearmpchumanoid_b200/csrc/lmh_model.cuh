@@ -44,6 +44,10 @@ constexpr int NC = 32;      // contact coefficients (2 feet x 4 vertices x 4 pyr
 constexpr int MPC_MAXN = 320;
 constexpr int LDM = 31;     // odd leading dimension: conflict-free column walks in shared memory
 constexpr int LDQ = 33;
+#ifndef LMH_QP_TABLE
+#define LMH_QP_TABLE 1          // 1: every pass of the general active-set iteration reads what depends on the working set alone from
+                                // the 65536-row table and solves the 6 x 6 system of the shortcut; 0: pivoted Cholesky + 12 x 12 system per pass
+#endif
 #ifndef LMH_SHORTCUT_DMMA
 #define LMH_SHORTCUT_DMMA 1     // 1: the 6 x 6 system of the all-free QP shortcut (D^-1 Jb, Sa + Jb'D^-1 Jb) on the FP64 tensor cores
 #endif
@@ -112,6 +116,8 @@ struct Consts {
     int32_t qp_max_iter;
     double mpc_r[MPC_MAXN];
     double dt;                // integrator step (Clock.hpp)
+    const double* qp_tab;     // working-set table of the WBC QP: [65536][72] = Kf (36), Yf (36) per subset of a foot's generators
+                              // (lmh_setup.hpp: qp_working_set_table); device pointer in the device copy of this struct
 };
 
 // Per-environment plan data shared through plan ids (global memory).
@@ -123,6 +129,12 @@ struct Plan {
     const int32_t* contact;   // [n_plans][n_phases] : bit 0 right foot, bit 1 left foot may carry force
     double phase_T;           // phase p = min((int)(t/phase_T), n_phases-1).  EXTENSION: upstream has one phase (stand).
     int32_t zmp_len, n_phases;
+};
+
+// Running statistics of one environment (a member of its workspace; thread 0 of the group updates it once per step).
+struct StatsAcc {
+    double max_tau, max_err, max_qpp;
+    int32_t qp_iters, qp_fail, steps, alive, qp_fallback, pad;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -156,6 +168,11 @@ struct EnvWS {
     int32_t phase, contact;        // walking extension: phase index and contact mask of this stage
     int32_t warm_contact, dead;    // contact mask the stored working set (free_mask, c) belongs to (-1 = none);
                                    // dead: the environment fell (state frozen, statistics closed)
+    // ---- bookkeeping of the closed loop, kept here so that nothing of it is live in registers across a stage evaluation
+    double t_env;                  // the environment's clock (rollout kernels)
+    double acc_tau, acc_qpp;       // step in flight: max |tau|, max |qpp| of its first stage
+    StatsAcc stats;                // running statistics (rollout kernels)
+    int32_t acc_iters, acc_fails, acc_nfall, acc_pad;
     // ---- phase-overlaid scratch
     union alignas(16) {
         struct {                       // model phase
@@ -1031,6 +1048,101 @@ __device__ void qp_backsolve_warp(EnvWS& w, int lane);
 #endif
 template <class Cx>
 LMH_NOINLINE LMH_HDN void qp_general_active_set(const Cx& cx, EnvWS& w, const Consts& K, int contact, bool have_point, int& iters, int& status) {
+#if LMH_QP_TABLE
+    // One pass = the equality-constrained problem on the current working set F.  Everything that depends on F alone comes
+    // from the table (Consts::qp_tab, one row per foot); with g = Jb lam the target in wrench space,
+    //     f = Kf g,   (Sa + Jb' Kf Jb) lam = rhs,   c_F = G_F' Yf g,   mu_i = g_i'(wF f - g) on the clipped coefficients:
+    // the same 6 x 6 system as the all-free shortcut of qp_phase, whose Dinv and Pinv Dinv are the row of the full set.
+    double* KY = w.u.s.Ay;            // [2][72] : Kf (36), Yf (36) of each foot's working set
+    double* U = w.u.s.Wb;             // [2][6][6] : Kf Jb_f
+    double* S6 = w.u.s.Pm;            // [6][6]    : lower triangle of Sa + sum_f Jb_f' Kf Jb_f
+    double* vv = w.u.s.vv;            // [36]      : g (12), y = Yf g (12), r = wF f - g (12)
+    bool done = false;
+    for (;;) {
+        ++iters;
+        {
+            double lam[6] = {0, 0, 0, 0, 0, 0};
+            unsigned m0 = 0u, m1 = 0u;
+#if defined(__CUDA_ARCH__)
+            if (Cx::NT == 32) {
+                const unsigned b = __ballot_sync(0xffffffffu, w.free_mask[cx.tid] != 0);
+                m0 = b & 0xffffu; m1 = b >> 16;
+            } else
+#endif
+            {
+                for (int g = 0; g < 16; ++g) { m0 |= w.free_mask[g] ? 1u << g : 0u; m1 |= w.free_mask[16 + g] ? 1u << g : 0u; }
+            }
+            const double* r0 = K.qp_tab + (size_t)m0 * 72;
+            const double* r1 = K.qp_tab + (size_t)m1 * 72;
+            LMH_FOR(it, 144) KY[it] = it < 72 ? r0[it] : r1[it - 72];
+            cx.sync();
+            LMH_FOR(it, 72) {
+                const int f = it / 36, i = (it % 36) / 6, sidx = it % 6;
+                double sd = 0.0;
+                for (int l = 0; l < 6; ++l) sd += KY[72 * f + 6 * i + l] * w.JFc[72 * f + 12 * l + sidx];
+                U[it] = sd;
+            }
+            cx.sync();
+            LMH_FOR(it, 36) {
+                const int r = it / 6, sidx = it % 6;
+                if (sidx <= r) {
+                    double sd = w.Sa[it];
+                    for (int k = 0; k < 12; ++k) sd += w.JFc[72 * (k / 6) + 12 * (k % 6) + r] * U[36 * (k / 6) + 6 * (k % 6) + sidx];
+                    S6[it] = sd;
+                }
+            }
+            cx.sync();
+            {
+                double A[36], Ainv[6];
+                LMH_UNROLL
+                for (int e = 0; e < 36; ++e) A[e] = (e % 6 <= e / 6) ? S6[e] : 0.0;
+                chol6(A, Ainv);
+                LMH_UNROLL
+                for (int r = 0; r < 6; ++r) {
+                    double sd = w.rhs[r];
+                    LMH_UNROLL
+                    for (int m = 0; m < 6; ++m) if (m < r) sd -= A[6 * r + m] * lam[m];
+                    lam[r] = sd * Ainv[r];
+                }
+                LMH_UNROLL
+                for (int r = 5; r >= 0; --r) {
+                    double sd = lam[r];
+                    LMH_UNROLL
+                    for (int m = 0; m < 6; ++m) if (m > r) sd -= A[6 * m + r] * lam[m];
+                    lam[r] = sd * Ainv[r];
+                }
+            }
+            LMH_FOR(i, 1) {                       // every thread holds the same six values; the caller reads them from here
+                LMH_UNROLL
+                for (int r = 0; r < 6; ++r) w.lam[r] = lam[r];
+            }
+            LMH_FOR(it, 24) {
+                if (it < 12) {            // f = Kf Jb lam
+                    double sd = 0.0;
+                    for (int q = 0; q < 6; ++q) sd += U[6 * it + q] * lam[q];
+                    w.f12[it] = sd;
+                } else {                  // g = Jb lam
+                    const int k = it - 12;
+                    double sd = 0.0;
+                    for (int q = 0; q < 6; ++q) sd += w.JFc[72 * (k / 6) + 12 * (k % 6) + q] * lam[q];
+                    vv[k] = sd;
+                }
+            }
+            cx.sync();
+            LMH_FOR(it, 24) {
+                if (it < 12) {            // y = Yf g
+                    const int f = it / 6, k = it % 6;
+                    double sy = 0.0;
+                    for (int l = 0; l < 6; ++l) sy += KY[72 * f + 36 + 6 * k + l] * vv[6 * f + l];
+                    vv[12 + it] = sy;
+                } else {                  // r = wF f - g
+                    const int k = it - 12;
+                    vv[24 + k] = K.wForce * w.f12[k] - vv[k];
+                }
+            }
+            cx.sync();
+        }
+#else
     double* Bm = w.u.s.Bm;            // [12][6] : row 6f+i, basis column k of foot f
     double* Pm = w.u.s.Pm;            // [2][36] : residual of the pivoted Cholesky, then T = B'B
     double* Wb = w.u.s.Wb;            // [6][12] : Ls^-1 Jb' B
@@ -1239,6 +1351,7 @@ LMH_NOINLINE LMH_HDN void qp_general_active_set(const Cx& cx, EnvWS& w, const Co
         }
         cx.sync();
         }
+#endif
         LMH_FOR(i, NC) {
             const int foot = i / 16, gi = i % 16;
             double sc = 0.0, sm = 0.0;
@@ -1248,7 +1361,11 @@ LMH_NOINLINE LMH_HDN void qp_general_active_set(const Cx& cx, EnvWS& w, const Co
         }
         cx.sync();
         // decisions: every thread reaches the same ones (warp reductions for one warp per env, else redundant loops)
+#if LMH_QP_TABLE
+        done = false;
+#else
         bool done = false;
+#endif
         int change = -1, to_free = 0;
         double alpha = 1.0;
         // multipliers come out of the cancellation wF f - Jb lam: anything below the round-off of those two terms is
@@ -1327,10 +1444,30 @@ LMH_NOINLINE LMH_HDN void qp_general_active_set(const Cx& cx, EnvWS& w, const Co
             }
         }
         cx.sync();
+#if !LMH_QP_TABLE
         first_pass = false;
+#endif
         if (done) break;
         if (iters >= K.qp_max_iter) { status = 1; break; }
     }
+#if LMH_QP_TABLE
+    // the last pass took the full step: c = c*, and f12 = Kf g, lam are those of that pass (Sa lam = rhs - Jb' f12 holds by
+    // construction).  Only an iteration that ran out of passes needs them rebuilt from the point it stopped at.
+    if (done) return;
+    {
+        double A[36], Ainv[6];
+        LMH_UNROLL
+        for (int e = 0; e < 36; ++e) A[e] = w.Sa[e];
+        chol6(A, Ainv);
+        LMH_UNROLL
+        for (int e = 0; e < 36; ++e) if (e % 6 <= e / 6) w.Ls[e] = A[e];
+        LMH_UNROLL
+        for (int e = 0; e < 6; ++e) w.Lsi[e] = Ainv[e];
+        cx.sync();
+    }
+    const double* Ls = w.Ls;
+    const double* Lsi = w.Lsi;
+#endif
     // f12 = G c ; lam = Sa^-1 (rhs - Jb' f12)
     LMH_FOR(r, 12) {
         int foot = r / 6, k = r % 6;
@@ -1373,7 +1510,10 @@ LMH_NOINLINE LMH_HDN void qp_general_active_set(const Cx& cx, EnvWS& w, const Co
         for (int m = r + 1; m < 6; ++m) s -= Ls[6 * m + r] * l[m];
         l[r] = s * Lsi[r];
     }
-    LMH_FOR(r, 6) w.lam[r] = l[r];
+    LMH_FOR(i, 1) {
+        LMH_UNROLL
+        for (int r = 0; r < 6; ++r) w.lam[r] = l[r];
+    }
     cx.sync();
 }
 
@@ -1649,7 +1789,11 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         have_point = true;
         if (cmin >= 0.0) fast_done = true;
     }
+#if defined(LMH_GENERAL_UNLIKELY) && defined(__CUDA_ARCH__)
+    if (__builtin_expect(!fast_done, 0)) qp_general_active_set(cx, w, K, contact, have_point, iters, status);
+#else
     if (!fast_done) qp_general_active_set(cx, w, K, contact, have_point, iters, status);
+#endif
     w.qp_fallback = iters > 1 ? 1 : 0;     // stages whose all-free solution was infeasible (contact-limited)
     w.qp_iters = iters;
     w.qp_status = status;
@@ -1664,16 +1808,22 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
         // a = -Ha^-1 (ga + M6' lam) through the same Woodbury pieces
         double coef[7] = {l[0], l[1], l[2], l[3], l[4], l[5], 1.0};
         double z[3] = {0, 0, 0};
+        LMH_UNROLL                     // static indices keep coef in registers (a runtime index would put it in local memory)
         for (int r = 0; r < 7; ++r) { z[0] += Gm[NYR * 7 + r] * coef[r]; z[1] += Gm[NYR * 8 + r] * coef[r]; z[2] += Gm[NYR * 9 + r] * coef[r]; }
         double cu[3] = {-(Ci[0] * z[0] + Ci[1] * z[1] + Ci[2] * z[2]), -(Ci[3] * z[0] + Ci[4] * z[1] + Ci[5] * z[2]),
                         -(Ci[6] * z[0] + Ci[7] * z[1] + Ci[8] * z[2])};
         LMH_FOR(i, NQ) {
             double sy = 0.0;
+            LMH_UNROLL
             for (int r = 0; r < 7; ++r) sy += Yt[NQ * r + i] * coef[r];
+            LMH_UNROLL
             for (int u = 0; u < 3; ++u) sy += Yt[NQ * (7 + u) + i] * cu[u];
             w.a[i] = i < ND1 ? -sy : -sy * K.isq_wJoints;
         }
-        LMH_FOR(r, 6) w.lam[r] = l[r];
+        LMH_FOR(i, 1) {
+            LMH_UNROLL
+            for (int r = 0; r < 6; ++r) w.lam[r] = l[r];
+        }
     }
     cx.sync();
 #if defined(__CUDA_ARCH__)
@@ -1829,12 +1979,6 @@ LMH_STAGE_ATTR LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, 
     cx.sync();
 }
 
-// Running statistics of one environment (every thread of the group holds the same copy).
-struct StatsAcc {
-    double max_tau, max_err, max_qpp;
-    int32_t qp_iters, qp_fail, steps, alive, qp_fallback;
-};
-
 // EXTENSION (the reference has no notion of falling): the health rule of a closed-loop step (the checker restates it
 // independently).  A step is COMMITTED -- state, clock, statistics -- only if, with x+ the state the RK4
 // combination would produce,
@@ -1865,8 +2009,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         }
         return;
     }
-    int iters = 0, fails = 0, nfall = 0;
-    double tau_inf = 0.0, qpp_inf = 0.0;
+    LMH_FOR(i, 1) { w.acc_iters = 0; w.acc_fails = 0; w.acc_nfall = 0; w.acc_tau = 0.0; w.acc_qpp = 0.0; }
     for (int stage = 0; stage < 4; ++stage) {
         const double cstage = stage == 0 ? 0.0 : stage == 3 ? dt : half;
 #if defined(__CUDA_ARCH__)
@@ -1885,9 +2028,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
             double k = w.xdot[i];
             kacc[i] = stage == 0 ? k : stage == 3 ? kacc[i] + k : mul_then_add(kacc[i], 2.0, k);
         }
-        iters += w.qp_iters;
-        fails += w.qp_status != 0;
-        nfall += w.qp_fallback;
+        LMH_FOR(i, 1) { w.acc_iters += w.qp_iters; w.acc_fails += w.qp_status != 0; w.acc_nfall += w.qp_fallback; }
         if (log) {
             LMH_FOR(i, 1) { log->k_index[stage] = w.k_index; log->phase[stage] = w.phase; log->contact[stage] = w.contact; }
             if (stage == 0) { LMH_FOR(i, NJ) log->tau_k1[i] = w.tau[i]; }
@@ -1898,12 +2039,17 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
                 const int i = cx.tid;
                 // NaN-propagating maxima (fmax would drop a NaN torque): a non-finite torque must fail the health test
                 const double ti = i < NJ ? fabs(w.tau[i]) : 0.0, ai = i < NQ ? fabs(w.xdot[NQ + i]) : 0.0;
-                tau_inf = warp_max(ti == ti ? ti : 1e300); qpp_inf = warp_max(ai == ai ? ai : 1e300);
+                const double tm = warp_max(ti == ti ? ti : 1e300), am = warp_max(ai == ai ? ai : 1e300);
+                if (i == 0) { w.acc_tau = tm; w.acc_qpp = am; }
             } else
 #endif
             {
-                for (int j = 0; j < NJ; ++j) { const double v = fabs(w.tau[j]); tau_inf = fmax(tau_inf, v == v ? v : 1e300); }
-                for (int j = 0; j < NQ; ++j) { const double v = fabs(w.xdot[NQ + j]); qpp_inf = fmax(qpp_inf, v == v ? v : 1e300); }
+                LMH_FOR(i, 1) {
+                    double tm = 0.0, am = 0.0;
+                    for (int j = 0; j < NJ; ++j) { const double v = fabs(w.tau[j]); tm = fmax(tm, v == v ? v : 1e300); }
+                    for (int j = 0; j < NQ; ++j) { const double v = fabs(w.xdot[NQ + j]); am = fmax(am, v == v ? v : 1e300); }
+                    w.acc_tau = tm; w.acc_qpp = am;
+                }
             }
         }
         cx.sync();
@@ -1918,6 +2064,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
     const double ex = w.com[0] - P.zmp_x[(size_t)plan_id * P.zmp_len + k0];
     const double ey = w.com[1] - P.zmp_y[(size_t)plan_id * P.zmp_len + k0];
     const double err = sqrt(ex * ex + ey * ey);
+    const double tau_inf = w.acc_tau;
     bool healthy = tau_inf < LMH_TAU_LIMIT && err < LMH_COM_ERR_LIMIT && kacc[2] > LMH_TORSO_MIN;
 #if defined(__CUDA_ARCH__)
     if (Cx::NT == 32) {
@@ -1931,17 +2078,19 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
     }
     if (healthy) {
         LMH_FOR(i, 2 * NQ) x[i] = kacc[i];
-        t = t + dt;
-        if (st) {
-            st->max_tau = fmax(st->max_tau, tau_inf); st->max_qpp = fmax(st->max_qpp, qpp_inf); st->max_err = fmax(st->max_err, err);
-            st->qp_iters += iters; st->qp_fail += fails; st->steps += 1; st->qp_fallback += nfall;
+        LMH_FOR(i, 1) {
+            t = t + dt;
+            if (st) {
+                st->max_tau = fmax(st->max_tau, tau_inf); st->max_qpp = fmax(st->max_qpp, w.acc_qpp); st->max_err = fmax(st->max_err, err);
+                st->qp_iters += w.acc_iters; st->qp_fail += w.acc_fails; st->steps += 1; st->qp_fallback += w.acc_nfall;
+            }
         }
     } else {
-        if (st) st->alive = 0;
+        LMH_FOR(i, 1) { if (st) st->alive = 0; }
     }
     if (log) {
         LMH_FOR(i, 3) { log->com_k4[i] = w.com[i]; log->rfoot[i] = w.ps[0][i]; log->lfoot[i] = w.ps[1][i]; }
-        LMH_FOR(i, 1) { log->qp_iters = iters; log->qp_fail = fails; }
+        LMH_FOR(i, 1) { log->qp_iters = w.acc_iters; log->qp_fail = w.acc_fails; }
     }
     cx.sync();                        // nobody reads kacc / w.dead of this step any more
     if (!healthy) { LMH_FOR(i, 1) w.dead = 1; }

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <vector>
 
@@ -98,9 +99,95 @@ inline void nao_local_transform(int i, double theta, double* T16) {
     std::memcpy(T16, T, sizeof(T));
 }
 
+// Working-set table of the WBC QP (qp_general_active_set, lmh_model.cuh).  A working set fixes which of a foot's 16 wrench
+// generators may carry force; everything that depends on that subset F ALONE is a constant of the robot and is tabulated
+// here for all 2^16 subsets (bit g of the index = generator g free), 72 doubles each:
+//   Kf [6][6] = B (wF B'B + eps I)^-1 B'          the wrench f_F = Kf g that answers the wrench-space target g = Jb lam,
+//   Yf [6][6]                                     y = Yf g with c_F = G_F' y, the coefficients of that wrench,
+// where B is the pivoted (rank-revealing) Cholesky factor of G_F G_F'; columns beyond the numerical rank are dropped, so
+// a foot on an edge, on one vertex or unloaded is as well conditioned as a flat one.  y is the solution of B'y = zeta with
+// zeros on the rows that were never pivoted (any solution gives the same c_F: they differ by null(G_F')).
+// For F = everything, Kf = Consts::Dinv and Yf = Pinv Dinv (the all-free shortcut).
+inline void qp_working_set_entry(const double* Gf, double wF, double eps, unsigned mask, double* out72) {
+    double S[36], B[36], Z[36];
+    int pord[6];
+    bool pdone[6] = {false, false, false, false, false, false};
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double s = 0.0;
+            for (int g = 0; g < 16; ++g) if ((mask >> g) & 1u) s += Gf[16 * i + g] * Gf[16 * j + g];
+            S[6 * i + j] = s; B[6 * i + j] = 0.0;
+        }
+    double dmax0 = 0.0;
+    for (int i = 0; i < 6; ++i) dmax0 = std::fmax(dmax0, S[7 * i]);
+    int rank = 0;
+    for (int k = 0; k < 6; ++k) {
+        int p = -1;
+        double best = 1e-10 * dmax0;
+        for (int j = 0; j < 6; ++j) if (!pdone[j] && S[7 * j] > best) { best = S[7 * j]; p = j; }
+        if (p < 0) break;
+        const double d = std::sqrt(best);
+        for (int i = 0; i < 6; ++i) B[6 * i + k] = pdone[i] ? 0.0 : (i == p ? d : S[6 * i + p] / d);
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) S[6 * i + j] -= B[6 * i + k] * B[6 * j + k];
+        pdone[p] = true; pord[k] = p; rank = k + 1;
+    }
+    for (int e = 0; e < 72; ++e) out72[e] = 0.0;
+    if (rank == 0) return;
+    // Z = (wF B'B + eps I)^-1 B'   (rank x 6)
+    std::vector<double> D((size_t)rank * rank), e(rank), x(rank);
+    for (int k = 0; k < rank; ++k)
+        for (int l = 0; l < rank; ++l) {
+            double t = 0.0;
+            for (int i = 0; i < 6; ++i) t += B[6 * i + k] * B[6 * i + l];
+            D[(size_t)k * rank + l] = wF * t + (k == l ? eps : 0.0);
+        }
+    for (int j = 0; j < 6; ++j) {
+        for (int k = 0; k < rank; ++k) e[k] = B[6 * j + k];
+        if (!dense_solve(rank, D, e, x.data())) throw std::runtime_error("lmh: singular working-set weight");
+        for (int k = 0; k < rank; ++k) Z[6 * k + j] = x[k];
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < rank; ++k) s += B[6 * i + k] * Z[6 * k + j];
+            out72[6 * i + j] = s;
+        }
+    for (int i = 0; i < 6; ++i)        // Kf is symmetric: remove the rounding asymmetry
+        for (int j = 0; j < i; ++j) { const double s = 0.5 * (out72[6 * i + j] + out72[6 * j + i]); out72[6 * i + j] = s; out72[6 * j + i] = s; }
+    for (int j = 0; j < 6; ++j) {      // column j of Yf: back substitution in pivot order
+        double y[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = rank - 1; k >= 0; --k) {
+            const int p = pord[k];
+            double s = Z[6 * k + j];
+            for (int i = 0; i < 6; ++i) s -= B[6 * i + k] * y[i];      // y[p] is still zero here
+            y[p] = s / B[6 * p + k];
+        }
+        for (int i = 0; i < 6; ++i) out72[36 + 6 * i + j] = y[i];
+    }
+}
+
+constexpr int kQpTabRow = 72;                      // doubles per working set
+constexpr size_t kQpTabDoubles = (size_t)65536 * kQpTabRow;
+
+// the whole table, built once per process and set of generators (friction coefficient)
+inline std::shared_ptr<const std::vector<double>> qp_working_set_table(const Consts& K) {
+    struct Entry { std::vector<double> key; std::shared_ptr<const std::vector<double>> tab; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    std::vector<double> key(K.Gf, K.Gf + 96);
+    key.push_back(K.wForce); key.push_back(K.epsC);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& en : cache) if (en.key == key) return en.tab;
+    auto tab = std::make_shared<std::vector<double>>(kQpTabDoubles);
+    for (unsigned m = 0; m < 65536u; ++m) qp_working_set_entry(K.Gf, K.wForce, K.epsC, m, tab->data() + (size_t)m * kQpTabRow);
+    cache.push_back(Entry{key, tab});
+    return tab;
+}
+
 class HostModel {
 public:
     Consts K;
+    std::shared_ptr<const std::vector<double>> qp_tab;     // working-set table of the WBC QP; K.qp_tab points at the HOST copy
     std::vector<double> zmp_x, zmp_y, foot_coef;   // nominal plan 0
     double q0[NQ];
     int ik_iterations = 0;
@@ -118,6 +205,8 @@ public:
         std::memset(ws_.get(), 0, sizeof(EnvWS));
         build_robot_tables();
         build_controller_tables();
+        qp_tab = qp_working_set_table(K);
+        K.qp_tab = qp_tab->data();
         // stand task: constant ZMP in the middle of the support zone (zmpGeneration.cpp:39-60)
         int samples = static_cast<int>((sc.sim_time + 0.5) / sc.dt);
         zmp_x.assign(samples, 0.0);
