@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(96, 1) rollout_kernel_helpers(Params p, int en
     for (int i = threadIdx.x; i < 120; i += blockDim.x) tab[kTabDh + i] = K.th_off[i];
     for (int i = threadIdx.x; i < tab_doubles - kTabMpc; i += blockDim.x) tab[kTabMpc + i] = K.mpc_r[i];
     __syncthreads();
+    const int plan_id = p.plan_id ? p.plan_id[env] : 0;
+    Ctx<32, true> cx{lane, 0};
+    cx.isp = tab; cx.dh = tab + kTabDh;
+    if (tab_doubles > kTabMpc) cx.mpc_r = tab + kTabMpc;
     if (wid != 0) {
         const LaneRole L = lane_role(lane);
         for (int s = 0; s < p.n_steps; ++s) {
@@ -203,21 +207,23 @@ __global__ void __launch_bounds__(96, 1) rollout_kernel_helpers(Params p, int en
             if (w.dead != 0) continue;
             for (int stage = 0; stage < 4; ++stage) {
                 asm volatile("bar.sync 2, 96;" ::: "memory");
-                if (wid == 1) crba_warp(w, K, tab, L, lane); else jacobian_warp(w, lane);
+                if (wid == 1) crba_warp(w, K, tab, L, lane);
+                else {
+                    // the sole Jacobians, then everything of the MPC / PD phase that does not need the dynamics
+                    jacobian_warp(w, lane);
+                    __syncwarp();
+                    mpc_pd_helper(cx, w, K, p.plan, plan_id);
+                }
                 asm volatile("bar.sync 3, 96;" ::: "memory");
             }
         }
         return;
     }
-    Ctx<32, true> cx{lane, 0};
-    cx.isp = tab; cx.dh = tab + kTabDh;
-    if (tab_doubles > kTabMpc) cx.mpc_r = tab + kTabMpc;
     ws_reset(cx, w);
     for (int i = lane; i < 60; i += 32) x[i] = p.x[(size_t)env * 60 + i];
     for (int i = lane; i < 30; i += 32) w.vh[i] = p.vh[(size_t)env * 30 + i];
     double& t = w.t_env;                                    // clock and statistics live in the workspace (shared memory):
     StatsAcc& st = w.stats;                                 // nothing of the bookkeeping is held in registers across a stage
-    const int plan_id = p.plan_id ? p.plan_id[env] : 0;
     const int push_at = p.push_step ? p.push_step[env] : -1;
     if (cx.tid == 0) {
         t = p.t[env];

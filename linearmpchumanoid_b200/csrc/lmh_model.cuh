@@ -850,13 +850,23 @@ LMH_HDN void centroidal_jacobian_phase(const Cx& cx, EnvWS& w, const Consts& K) 
 // ================================================================================================
 // Phase 5: LIPM MPC as a precomputed gain (mpcLinearPendulum.cpp:78-109) + PD references
 // (controller.cpp:296-386).
-template <class Cx>
-LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
+// The pieces of mpc_pd_phase.  In latency mode (rollout_kernel_helpers) the pieces that do not need the dynamics -- the ZMP
+// window sums of the MPC, the joint-space PD and the foot references -- run on the helper warp that computed the sole
+// Jacobians, while the environment's warp is still in the RNEA; the arithmetic is the same source either way.
+LMH_HD int mpc_window_start(const Consts& K, const Plan& P, double t, int& kidx) {
     const int n1 = K.mpc_n1;
-    int kidx = (int)(w.t / K.mpc_dt);                // mpcLinearPendulum.cpp:92 -- same FP64 expression
+    kidx = (int)(t / K.mpc_dt);                      // mpcLinearPendulum.cpp:92 -- same FP64 expression
     int k0 = kidx;
     if (k0 < 0) k0 = 0;
     if (k0 + n1 > P.zmp_len) k0 = P.zmp_len - n1;    // the reference would read out of bounds here; we clamp
+    return k0;
+}
+// sum_i r[i] zmp[k + i] for both axes as 2 x 16 partial sums in w.red; returns the window index k of this stage
+template <class Cx>
+LMH_HDN int mpc_window_sums(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
+    const int n1 = K.mpc_n1;
+    int kidx;
+    const int k0 = mpc_window_start(K, P, w.t, kidx);
     LMH_FOR(it, 32) {
         int ax = it / 16, part = it % 16;
         const double* z = (ax == 0 ? P.zmp_x : P.zmp_y) + (size_t)plan_id * P.zmp_len + k0;
@@ -865,24 +875,35 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
         for (int i = part; i < n1; i += 16) s += mr[i] * z[i];
         w.red[it] = s;
     }
-    cx.sync();
+    return kidx;
+}
+// u0 and the reference CoM state of both axes (mpcLinearPendulum.cpp:89-101).  sums_done: the window sums were left
+// in xRef[2] / yRef[2] (latency mode), else they are the partial sums in w.red
+template <class Cx>
+LMH_HDN void mpc_close(const Cx& cx, EnvWS& w, const Consts& K, int kidx, bool sums_done) {
     LMH_FOR(ax, 2) {
+        double* ref = ax == 0 ? w.xRef : w.yRef;
         double s = 0.0;
-        for (int part = 0; part < 16; ++part) s += w.red[16 * ax + part];
+        if (sums_done) s = ref[2];
+        else for (int part = 0; part < 16; ++part) s += w.red[16 * ax + part];
         double p = w.com[ax], vv = w.comVel[ax];
         double u = s - (K.mpc_rPx[0] * p + K.mpc_rPx[1] * vv);
-        double* ref = ax == 0 ? w.xRef : w.yRef;
         ref[0] = K.mpc_A[0] * p + K.mpc_A[1] * vv + K.mpc_B[0] * u;
         ref[1] = K.mpc_A[2] * p + K.mpc_A[3] * vv + K.mpc_B[1] * u;
         ref[2] = u;
         if (ax == 0) w.k_index = kidx;
     }
+}
+template <class Cx>
+LMH_HDN void pd_joint_refs(const Cx& cx, EnvWS& w, const Consts& K) {
     // joint-space PD (controller.cpp:296-309): world-form errors, 3<->3 swap of the base slots
     LMH_FOR(i, NQ) {
         int src = i < 3 ? i + 3 : i < 6 ? i - 3 : i;
         w.qppRef[i] = K.KpJ * (K.qdes[src] - w.q[src]) + K.KdJ * (0.0 - w.v[src]);
     }
-    cx.sync();
+}
+template <class Cx>
+LMH_HDN void pd_momentum_refs(const Cx& cx, EnvWS& w, const Consts& K) {
     // centroidal momentum rate (controller.cpp:311-327)
     LMH_FOR(k, 6) {
         if (k < 3) w.hGpRef[k] = K.KdM * (0.0 - w.angMom[k]);
@@ -894,6 +915,9 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
             w.hGpRef[k] = K.mass * (K.KpM * (pr - w.com[j]) + K.KdM * (vr - w.comVel[j]) + ar);
         }
     }
+}
+template <class Cx>
+LMH_HDN void pd_foot_refs(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
     // walking extension: phase of this stage (integer work, same FP64 expression as the oracle)
     int ph = P.n_phases > 1 ? (int)(w.t / P.phase_T) : 0;      // (one phase: the clamp below gives 0 whatever t is; no division)
     ph = ph < 0 ? 0 : (ph >= P.n_phases ? P.n_phases - 1 : ph);
@@ -963,6 +987,40 @@ LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
         }
         w.footAccRef[it] = out;
     }
+}
+// what the helper warp of the latency mode computes after the sole Jacobians (see above)
+template <class Cx>
+LMH_HDN void mpc_pd_helper(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
+    (void)mpc_window_sums(cx, w, K, P, plan_id);
+    cx.sync();
+    LMH_FOR(ax, 2) {
+        double s = 0.0;
+        for (int part = 0; part < 16; ++part) s += w.red[16 * ax + part];
+        (ax == 0 ? w.xRef : w.yRef)[2] = s;
+    }
+    pd_joint_refs(cx, w, K);
+    pd_foot_refs(cx, w, K, P, plan_id);
+    cx.sync();
+}
+
+template <class Cx>
+LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
+    if (cx.helpers) {                  // latency mode: the helper warp has left the sums and the references (mpc_pd_helper)
+        int kidx;
+        (void)mpc_window_start(K, P, w.t, kidx);
+        mpc_close(cx, w, K, kidx, true);
+        cx.sync();
+        pd_momentum_refs(cx, w, K);
+        cx.sync();
+        return;
+    }
+    const int kidx = mpc_window_sums(cx, w, K, P, plan_id);
+    cx.sync();
+    mpc_close(cx, w, K, kidx, false);
+    pd_joint_refs(cx, w, K);
+    cx.sync();
+    pd_momentum_refs(cx, w, K);
+    pd_foot_refs(cx, w, K, P, plan_id);
     cx.sync();
 }
 

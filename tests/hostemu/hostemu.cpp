@@ -51,6 +51,13 @@ void emu_tables(void* p, double* mass28, double* com28x3, double* isp28x36, doub
     rPx[0] = e->hm.K.mpc_rPx[0]; rPx[1] = e->hm.K.mpc_rPx[1];
     std::memcpy(foot40, e->hm.foot_coef.data(), sizeof(double) * 40);
 }
+// row `mask` of the QP working-set table (lmh_setup.hpp: Kf 36, Yf 36) and what it was built from
+void emu_qp_table_row(void* p, int32_t mask, double* out72, double* Gf96, double* wf_eps2) {
+    Emu* e = static_cast<Emu*>(p);
+    std::memcpy(out72, e->hm.K.qp_tab + (size_t)mask * 72, sizeof(double) * 72);
+    std::memcpy(Gf96, e->hm.K.Gf, sizeof(double) * 96);
+    wf_eps2[0] = e->hm.K.wForce; wf_eps2[1] = e->hm.K.epsC;
+}
 // one dynamics(x,t) evaluation; vheld is read and advanced
 void emu_stage(void* p, const double* x60, double* vheld30, double t, LmhStageDump* dump) {
     Emu* e = static_cast<Emu*>(p);

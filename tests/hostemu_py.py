@@ -14,6 +14,7 @@ _L.emu_destroy.argtypes = [_vp]
 _L.emu_nominal.argtypes = [_vp] * 5
 _L.emu_tables.argtypes = [_vp] * 8
 _L.emu_stage.argtypes = [_vp, _vp, _vp, _f64, _vp]
+_L.emu_qp_table_row.argtypes = [_vp, _i32, _vp, _vp, _vp]
 _L.emu_set_walk_plan.argtypes = [_vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp]
 _L.emu_step.argtypes = [_vp, _vp, _vp, _vp, _i32, _vp, _vp]
 _L.emu_rollout.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]
@@ -47,6 +48,12 @@ class Emu:
         zx = np.ascontiguousarray(zx, np.float64); zy = np.ascontiguousarray(zy, np.float64)
         fc = np.ascontiguousarray(foot_coef, np.float64); ct = np.ascontiguousarray(contact, np.int32)
         _L.emu_set_walk_plan(self.h, len(zx), _p(zx), _p(zy), len(ct), float(phase_T), _p(fc), _p(ct))
+
+    def qp_table_row(self, mask):
+        """(Kf [6][6], Yf [6][6], Gf [6][16], wForce, epsC) of the working set `mask` (bit g = generator g free)"""
+        row, gf, we = np.zeros(72), np.zeros(96), np.zeros(2)
+        _L.emu_qp_table_row(self.h, int(mask), _p(row), _p(gf), _p(we))
+        return row[:36].reshape(6, 6), row[36:].reshape(6, 6), gf.reshape(6, 16), float(we[0]), float(we[1])
 
     def stage(self, x, v_held, t):
         d = np.zeros(1, STAGE_DTYPE)

@@ -60,6 +60,42 @@ def test_qp_against_exact_solutions(hostemu, qp_exact):
     assert worst < 1e-8, worst
 
 
+def test_qp_working_set_table(hostemu):
+    """Rows of the working-set table against the problem they tabulate: for the free set F of one foot and a target g in
+    wrench space, c_F = argmin 1/2 wF |G_F c|^2 + 1/2 eps |c|^2 - g'G_F c  and  f = G_F c_F.  Checked in extended precision
+    for the full set, flat sub-patterns, an edge, a single vertex, single generators, the empty set and random subsets."""
+    e = hostemu.Emu()
+    rng = np.random.default_rng(5)
+    masks = [0xFFFF, 0x0000, 0x00FF, 0xFF00, 0x0F0F, 0x000F, 0xF000, 0x0001, 0x8000, 0x0101, 0x7FFF, 0xFFFE, 0x1248]
+    masks += [int(m) for m in rng.integers(1, 0xFFFF, 40)]
+    ld = np.longdouble
+    for m in masks:
+        Kf, Yf, Gf, wF, eps = e.qp_table_row(m)
+        free = [g for g in range(16) if (m >> g) & 1]
+        if not free:
+            assert not Kf.any() and not Yf.any()
+            continue
+        G = Gf[:, free].astype(ld)
+        H = ld(wF) * (G.T @ G) + ld(eps) * np.eye(len(free), dtype=ld)
+        # H^-1 G' by Gaussian elimination in extended precision (numpy.linalg has no longdouble)
+        A = np.concatenate([H, G.T], axis=1)
+        n = len(free)
+        for k in range(n):
+            piv = k + int(np.argmax(np.abs(A[k:, k])))
+            A[[k, piv]] = A[[piv, k]]
+            A[k] = A[k] / A[k, k]
+            for i in range(n):
+                if i != k:
+                    A[i] = A[i] - A[i, k] * A[k]
+        C = A[:, n:]                                    # c_F = C g
+        Kx = (G @ C).astype(np.float64)
+        scale = np.abs(Kx).max()
+        assert np.abs(Kf - Kx).max() < 1e-10 * scale, hex(m)
+        assert np.abs(Kf - Kf.T).max() == 0.0
+        cF = (Gf[:, free].T @ Yf)                       # c_F = G_F' Yf g for every g
+        assert np.abs(cF - C.astype(np.float64)).max() < 1e-10 * np.abs(C.astype(np.float64)).max(), hex(m)
+
+
 def test_closed_loop_1s(hostemu, golden):
     e = hostemu.Emu()
     x, vh, t, lg, st = e.step(golden["x0"], np.zeros(30), 0.0, 100)
