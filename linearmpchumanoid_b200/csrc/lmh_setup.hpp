@@ -109,60 +109,81 @@ inline void nao_local_transform(int i, double theta, double* T16) {
 // zeros on the rows that were never pivoted (any solution gives the same c_F: they differ by null(G_F')).
 // For F = everything, Kf = Consts::Dinv and Yf = Pinv Dinv (the all-free shortcut).
 inline void qp_working_set_entry(const double* Gf, double wF, double eps, unsigned mask, double* out72) {
-    double S[36], B[36], Z[36];
+    // extended precision throughout (run once per process): the rows come out correctly rounded to a few ulp, so the
+    // table adds nothing to the error budget of a pass
+    typedef long double real;
+    real S[36], B[36], Z[36], D[36], Kf[36];
     int pord[6];
     bool pdone[6] = {false, false, false, false, false, false};
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) {
-            double s = 0.0;
-            for (int g = 0; g < 16; ++g) if ((mask >> g) & 1u) s += Gf[16 * i + g] * Gf[16 * j + g];
-            S[6 * i + j] = s; B[6 * i + j] = 0.0;
+            real s = 0;
+            for (int g = 0; g < 16; ++g) if ((mask >> g) & 1u) s += (real)Gf[16 * i + g] * (real)Gf[16 * j + g];
+            S[6 * i + j] = s; B[6 * i + j] = 0;
         }
-    double dmax0 = 0.0;
-    for (int i = 0; i < 6; ++i) dmax0 = std::fmax(dmax0, S[7 * i]);
+    real dmax0 = 0;
+    for (int i = 0; i < 6; ++i) dmax0 = S[7 * i] > dmax0 ? S[7 * i] : dmax0;
     int rank = 0;
     for (int k = 0; k < 6; ++k) {
         int p = -1;
-        double best = 1e-10 * dmax0;
+        real best = 1e-10L * dmax0;
         for (int j = 0; j < 6; ++j) if (!pdone[j] && S[7 * j] > best) { best = S[7 * j]; p = j; }
         if (p < 0) break;
-        const double d = std::sqrt(best);
-        for (int i = 0; i < 6; ++i) B[6 * i + k] = pdone[i] ? 0.0 : (i == p ? d : S[6 * i + p] / d);
+        const real d = std::sqrt(best);
+        for (int i = 0; i < 6; ++i) B[6 * i + k] = pdone[i] ? (real)0 : (i == p ? d : S[6 * i + p] / d);
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) S[6 * i + j] -= B[6 * i + k] * B[6 * j + k];
         pdone[p] = true; pord[k] = p; rank = k + 1;
     }
     for (int e = 0; e < 72; ++e) out72[e] = 0.0;
     if (rank == 0) return;
-    // Z = (wF B'B + eps I)^-1 B'   (rank x 6)
-    std::vector<double> D((size_t)rank * rank), e(rank), x(rank);
+    // D = wF B'B + eps I (rank x rank, SPD) = L L'; Z = D^-1 B'   (rank x 6)
     for (int k = 0; k < rank; ++k)
         for (int l = 0; l < rank; ++l) {
-            double t = 0.0;
+            real t = 0;
             for (int i = 0; i < 6; ++i) t += B[6 * i + k] * B[6 * i + l];
-            D[(size_t)k * rank + l] = wF * t + (k == l ? eps : 0.0);
+            D[6 * k + l] = (real)wF * t + (k == l ? (real)eps : (real)0);
         }
+    for (int k = 0; k < rank; ++k) {
+        for (int i = k; i < rank; ++i) {
+            real t = D[6 * i + k];
+            for (int m = 0; m < k; ++m) t -= D[6 * i + m] * D[6 * k + m];
+            if (i == k) {
+                if (!(t > 0)) throw std::runtime_error("lmh: singular working-set weight");
+                D[6 * k + k] = std::sqrt(t);
+            } else D[6 * i + k] = t / D[6 * k + k];
+        }
+    }
     for (int j = 0; j < 6; ++j) {
-        for (int k = 0; k < rank; ++k) e[k] = B[6 * j + k];
-        if (!dense_solve(rank, D, e, x.data())) throw std::runtime_error("lmh: singular working-set weight");
+        real x[6];
+        for (int k = 0; k < rank; ++k) {
+            real t = B[6 * j + k];
+            for (int m = 0; m < k; ++m) t -= D[6 * k + m] * x[m];
+            x[k] = t / D[6 * k + k];
+        }
+        for (int k = rank - 1; k >= 0; --k) {
+            real t = x[k];
+            for (int m = k + 1; m < rank; ++m) t -= D[6 * m + k] * x[m];
+            x[k] = t / D[6 * k + k];
+        }
         for (int k = 0; k < rank; ++k) Z[6 * k + j] = x[k];
     }
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) {
-            double s = 0.0;
+            real s = 0;
             for (int k = 0; k < rank; ++k) s += B[6 * i + k] * Z[6 * k + j];
-            out72[6 * i + j] = s;
+            Kf[6 * i + j] = s;
         }
     for (int i = 0; i < 6; ++i)        // Kf is symmetric: remove the rounding asymmetry
-        for (int j = 0; j < i; ++j) { const double s = 0.5 * (out72[6 * i + j] + out72[6 * j + i]); out72[6 * i + j] = s; out72[6 * j + i] = s; }
+        for (int j = 0; j <= i; ++j) { const double v = (double)(0.5L * (Kf[6 * i + j] + Kf[6 * j + i])); out72[6 * i + j] = v; out72[6 * j + i] = v; }
     for (int j = 0; j < 6; ++j) {      // column j of Yf: back substitution in pivot order
-        double y[6] = {0, 0, 0, 0, 0, 0};
+        real y[6] = {0, 0, 0, 0, 0, 0};
         for (int k = rank - 1; k >= 0; --k) {
             const int p = pord[k];
-            double s = Z[6 * k + j];
-            for (int i = 0; i < 6; ++i) s -= B[6 * i + k] * y[i];      // y[p] is still zero here
-            y[p] = s / B[6 * p + k];
+            real t = Z[6 * k + j];
+            for (int i = 0; i < 6; ++i) t -= B[6 * i + k] * y[i];      // y[p] is still zero here
+            y[p] = t / B[6 * p + k];
         }
-        for (int i = 0; i < 6; ++i) out72[36 + 6 * i + j] = y[i];
+        for (int i = 0; i < 6; ++i) out72[36 + 6 * i + j] = (double)y[i];
     }
 }
 
