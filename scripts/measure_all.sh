@@ -1,3 +1,7 @@
+#!/bin/bash
+# Developer tool: the one-GPU measurement suite of a round, run on the GPU box through gpurun (from the repository root):
+# GPU tests, smoke, the four bench workloads, the reference arm, three ncu captures summarised into gpurun_out/ (the
+# .ncu-rep files are deleted: gpurun_out/ is limited to 64 MiB), the launch list and the latency-mode crossover.
 set -x
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
