@@ -51,6 +51,11 @@ constexpr int LDQ = 33;
 #ifndef LMH_SHORTCUT_DMMA
 #define LMH_SHORTCUT_DMMA 1     // 1: the 6 x 6 system of the all-free QP shortcut (D^-1 Jb, Sa + Jb'D^-1 Jb) on the FP64 tensor cores
 #endif
+#if defined(LMH_TIMELINE) && defined(__CUDA_ARCH__)
+#define LMH_STAMP(i) do { if (cx.tid == 0) w.stamp[(i)] = (double)clock64(); } while (0)
+#else
+#define LMH_STAMP(i) do {} while (0)
+#endif
 #ifndef LMH_ALIGN_STAGES
 #define LMH_ALIGN_STAGES 1      // 1: the warps of a block meet at a barrier once per stage (shared instruction fetches)
 #endif
@@ -173,6 +178,9 @@ struct EnvWS {
     double acc_tau, acc_qpp;       // step in flight: max |tau|, max |qpp| of its first stage
     StatsAcc stats;                // running statistics (rollout kernels)
     int32_t acc_iters, acc_fails, acc_nfall, acc_pad;
+#if defined(LMH_TIMELINE)
+    double stamp[16];              // debug build: clock64 at the phase boundaries of the last stage evaluated
+#endif
     // ---- phase-overlaid scratch
     union alignas(16) {
         struct {                       // model phase
@@ -872,7 +880,13 @@ LMH_HDN int mpc_window_sums(const Cx& cx, EnvWS& w, const Consts& K, const Plan&
         const double* z = (ax == 0 ? P.zmp_x : P.zmp_y) + (size_t)plan_id * P.zmp_len + k0;
         double s = 0.0;
         const double* mr = cx.mpc_r ? cx.mpc_r : K.mpc_r;
-        for (int i = part; i < n1; i += 16) s += mr[i] * z[i];
+        // the sixteen partial sums of an axis take the same number of turns (a short one adds 0 x z[0]): no divergent exit
+        for (int i0 = 0; i0 < n1; i0 += 16) {
+            const int i = i0 + part;
+            const bool on = i < n1;
+            const double r = on ? mr[on ? i : 0] : 0.0;
+            s += r * z[on ? i : 0];
+        }
         w.red[it] = s;
     }
     return kidx;
@@ -891,7 +905,7 @@ LMH_HDN void mpc_close(const Cx& cx, EnvWS& w, const Consts& K, int kidx, bool s
         ref[0] = K.mpc_A[0] * p + K.mpc_A[1] * vv + K.mpc_B[0] * u;
         ref[1] = K.mpc_A[2] * p + K.mpc_A[3] * vv + K.mpc_B[1] * u;
         ref[2] = u;
-        if (ax == 0) w.k_index = kidx;
+        if (ax == 0 && !sums_done) w.k_index = kidx;      // (latency mode: the helper warp has stored it)
     }
 }
 template <class Cx>
@@ -991,12 +1005,13 @@ LMH_HDN void pd_foot_refs(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P
 // what the helper warp of the latency mode computes after the sole Jacobians (see above)
 template <class Cx>
 LMH_HDN void mpc_pd_helper(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
-    (void)mpc_window_sums(cx, w, K, P, plan_id);
+    const int kidx = mpc_window_sums(cx, w, K, P, plan_id);
     cx.sync();
     LMH_FOR(ax, 2) {
         double s = 0.0;
         for (int part = 0; part < 16; ++part) s += w.red[16 * ax + part];
         (ax == 0 ? w.xRef : w.yRef)[2] = s;
+        if (ax == 0) w.k_index = kidx;
     }
     pd_joint_refs(cx, w, K);
     pd_foot_refs(cx, w, K, P, plan_id);
@@ -1006,9 +1021,7 @@ LMH_HDN void mpc_pd_helper(const Cx& cx, EnvWS& w, const Consts& K, const Plan& 
 template <class Cx>
 LMH_HDN void mpc_pd_phase(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id) {
     if (cx.helpers) {                  // latency mode: the helper warp has left the sums and the references (mpc_pd_helper)
-        int kidx;
-        (void)mpc_window_start(K, P, w.t, kidx);
-        mpc_close(cx, w, K, kidx, true);
+        mpc_close(cx, w, K, 0, true);
         cx.sync();
         pd_momentum_refs(cx, w, K);
         cx.sync();
@@ -1031,10 +1044,15 @@ LMH_HDN void assemble_ga_phase(const Cx& cx, EnvWS& w, const Consts& K) {
         double s = 0.0;
         for (int k = 0; k < 6; ++k) s += (k < 3 ? K.wCoMK : K.wCoML) * w.AG[NQ * k + i] * (w.AGpqp[k] - w.hGpRef[k]);
         double sj = 0.0;
-        for (int f = 0; f < 2; ++f) {
-            int ci = jf_col(f, i);
-            if (ci >= 0)
-                for (int k = 0; k < 6; ++k) sj += w.JFc[72 * f + 12 * k + ci] * (w.Jpqp[6 * f + k] - w.footAccRef[6 * f + k]);
+        LMH_UNROLL
+        for (int f = 0; f < 2; ++f) {          // branch-free: a coordinate a foot does not depend on contributes 0 x (...)
+            const int ci = jf_col(f, i);
+            const bool on = ci >= 0;
+            LMH_UNROLL
+            for (int k = 0; k < 6; ++k) {
+                const double jv = on ? w.JFc[72 * f + 12 * k + (on ? ci : 0)] : 0.0;
+                sj += jv * (w.Jpqp[6 * f + k] - w.footAccRef[6 * f + k]);
+            }
         }
         double wj = i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
         w.ga[i] = s - wj * w.qppRef[i] + K.wFoot * sj;
@@ -1885,7 +1903,7 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
     }
     cx.sync();
 #if defined(__CUDA_ARCH__)
-    if (Cx::NT == 32) { qp_backsolve_warp(w, cx.tid); return; }
+    if (Cx::NT == 32) { LMH_STAMP(9); qp_backsolve_warp(w, cx.tid); return; }
 #endif
     for (int k = ND1 - 1; k >= 0; --k) {     // L1' a[0:18] = rhs, column oriented
         double xk = w.a[k] / w.ladiag[k];
@@ -1903,35 +1921,44 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
 // (controller.cpp:137-147, apps/offline/main.cpp:107-121).
 template <class Cx>
 LMH_HDN void output_phase(const Cx& cx, EnvWS& w) {
+    // Branch-free on purpose: the work items of a pass differ (leg / arm / head joints; linear, angular and joint
+    // coordinates) and a divergent branch costs a warp more than the few FMAs it guards.  Terms that do not apply are
+    // multiplied by a zero operand (x + 0 y = x exactly) and indices are clamped to valid ones.
     LMH_FOR(j, NJ) {
         double s = w.C[6 + j];
+        LMH_UNROLL
         for (int k = 0; k < 6; ++k) s += w.M6[NQ * k + 6 + j] * w.a[k];
-        int c = joint_chain(j), j0 = chain_joint0(c), n = chain_nact(c);
-        for (int b = 0; b < n; ++b) s += w.Hc[36 * c + 6 * (j - j0) + b] * w.a[6 + j0 + b];
-        if (j < 12) {
-            const int f = j / 6;
-            for (int k = 0; k < 6; ++k) s -= w.JFc[72 * f + 12 * k + 6 + (j - 6 * f)] * w.f12[6 * f + k];
+        const int c = joint_chain(j), j0 = chain_joint0(c), n = chain_nact(c);
+        LMH_UNROLL
+        for (int b = 0; b < 6; ++b) {
+            const bool on = b < n;
+            const double hv = on ? w.Hc[36 * c + 6 * (j - j0) + b] : 0.0;
+            s += hv * w.a[6 + j0 + (on ? b : 0)];
+        }
+        const bool leg = j < 12;
+        const int f = leg ? j / 6 : 0, col = leg ? 6 + (j - 6 * f) : 6;
+        LMH_UNROLL
+        for (int k = 0; k < 6; ++k) {
+            const double jv = leg ? w.JFc[72 * f + 12 * k + col] : 0.0;
+            s -= jv * w.f12[6 * f + k];
         }
         w.tau[j] = s;
     }
     LMH_FOR(i, NQ) {
-        double x;
-        if (i < 3) {         // linear part of X0^-1 a : R0 a_lin + p0 x (R0 a_ang)
-            double ra[3] = {rot_row(w.R0, 0, w.a), rot_row(w.R0, 1, w.a), rot_row(w.R0, 2, w.a)};
-            x = rot_row(w.R0, i, w.a + 3) + cross_k(w.p0, ra, i);
-        } else if (i < 6) x = rot_row(w.R0, i - 3, w.a);
-        else x = w.a[i];
-        w.xdot[NQ + i] = x;
-        double qd;
-        if (i < 3) qd = w.v[i] + cross_k(w.v + 3, w.q, i);       // v + w x p
-        else if (i < 6) {    // Euler rates (generalizedFunctions.cpp:43-50)
-            const double s2 = w.esc[2], c2 = w.esc[3], ic1 = 1.0 / w.esc[1], t1 = w.esc[0] * ic1;   // tan = sin/cos
-            const double* om = w.v + 3;
-            qd = i == 3 ? (c2 * ic1) * om[0] + (s2 * ic1) * om[1]
-               : i == 4 ? -s2 * om[0] + c2 * om[1]
-                        : c2 * t1 * om[0] + s2 * t1 * om[1] + om[2];
-        } else qd = w.v[i];
-        w.xdot[i] = qd;
+        const int k3 = i < 3 ? i : i < 6 ? i - 3 : 0;
+        // X0^-1 a : linear part R0 a_lin + p0 x (R0 a_ang), angular part R0 a_ang
+        const double ra[3] = {rot_row(w.R0, 0, w.a), rot_row(w.R0, 1, w.a), rot_row(w.R0, 2, w.a)};
+        const double xlin = rot_row(w.R0, k3, w.a + 3) + cross_k(w.p0, ra, k3);
+        const double xang = k3 == 0 ? ra[0] : k3 == 1 ? ra[1] : ra[2];
+        w.xdot[NQ + i] = i < 3 ? xlin : i < 6 ? xang : w.a[i];
+        // state derivative of the configuration: v + w x p, Euler rates (generalizedFunctions.cpp:43-50), joint rates
+        const double qlin = w.v[k3] + cross_k(w.v + 3, w.q, k3);
+        const double s2 = w.esc[2], c2 = w.esc[3], ic1 = 1.0 / w.esc[1], t1 = w.esc[0] * ic1;   // tan = sin/cos
+        const double* om = w.v + 3;
+        const double qe = k3 == 0 ? (c2 * ic1) * om[0] + (s2 * ic1) * om[1]
+                        : k3 == 1 ? -s2 * om[0] + c2 * om[1]
+                                  : c2 * t1 * om[0] + s2 * t1 * om[1] + om[2];
+        w.xdot[i] = i < 3 ? qlin : i < 6 ? qe : w.v[i];
     }
     cx.sync();
 }
@@ -1985,10 +2012,14 @@ LMH_HDN void model_phases(const Cx& cx, EnvWS& w, const Consts& K) {
         const LaneRole L = lane_role(cx.tid);
         const double* Isp = Cx::TAB ? cx.isp : K.Isp;
         if (Cx::TAB) __builtin_assume(__isShared(Isp));
+        LMH_STAMP(1);
         cx.handover(2);                             // transforms and base twists are ready: the helper warps start
+        LMH_STAMP(2);
         rnea_warp(w, K, Isp, L, cx.tid);
+        LMH_STAMP(3);
         if (!cx.helpers) crba_warp(w, K, Isp, L, cx.tid);
         cx.handover(3);                             // mass matrix and sole Jacobians are there
+        LMH_STAMP(4);
     } else
 #endif
     {
@@ -2005,8 +2036,10 @@ LMH_HDN void qp_stage(const Cx& cx, EnvWS& w, const Consts& K, LmhStageDump* dum
 #if defined(__CUDA_ARCH__)
     if (Cx::NT == 32 && K.wCoMK == 0.0) {
         assemble_ga_phase(cx, w, K);
+        LMH_STAMP(7);
         if (dump) dump_assembly(cx, w, K, dump);
         qp_factor_warp(w, K, cx.tid);
+        LMH_STAMP(8);
         factor_done = true;
     } else
 #endif
@@ -2028,10 +2061,15 @@ LMH_HDN void qp_stage(const Cx& cx, EnvWS& w, const Consts& K, LmhStageDump* dum
 #endif
 template <class Cx>
 LMH_STAGE_ATTR LMH_HDN void stage_eval(const Cx& cx, EnvWS& w, const Consts& K, const Plan& P, int plan_id, LmhStageDump* dump = nullptr) {
+    LMH_STAMP(0);
     model_phases(cx, w, K);
+    LMH_STAMP(5);
     mpc_pd_phase(cx, w, K, P, plan_id);
+    LMH_STAMP(6);
     qp_stage(cx, w, K, dump);
+    LMH_STAMP(10);
     output_phase(cx, w);
+    LMH_STAMP(11);
     if (dump) dump_stage(cx, w, dump);
     LMH_FOR(i, NQ) w.vh[i] = w.v[i];     // Robot::updateVelocityState (Robot.cpp:271-274)
     cx.sync();
@@ -2052,6 +2090,7 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
                       int plan_id, LmhStepLog* log, StatsAcc* st) {
     const double dt = K.dt;
     const double half = 0.5 * dt;
+    LMH_STAMP(12);
     cx.handover(1);                                 // helper warps learn here whether the environment is still alive
     if (w.dead != 0) {
         // a fallen environment evaluates nothing; it only keeps its appointments with the warps it shares a block with,
@@ -2150,6 +2189,11 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
         LMH_FOR(i, 3) { log->com_k4[i] = w.com[i]; log->rfoot[i] = w.ps[0][i]; log->lfoot[i] = w.ps[1][i]; }
         LMH_FOR(i, 1) { log->qp_iters = w.acc_iters; log->qp_fail = w.acc_fails; }
     }
+#if defined(LMH_TIMELINE) && defined(__CUDA_ARCH__)
+    LMH_STAMP(13);
+    cx.sync();
+    if (log) { LMH_FOR(i, 16) log->tau_k1[i] = w.stamp[i]; }
+#endif
     cx.sync();                        // nobody reads kacc / w.dead of this step any more
     if (!healthy) { LMH_FOR(i, 1) w.dead = 1; }
     cx.sync();

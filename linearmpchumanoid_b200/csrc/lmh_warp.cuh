@@ -184,12 +184,14 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
 #pragma unroll
         for (int d = 0; d < MAXDEPTH; ++d) {
             if (d >= len) break;
+            const double* L = Xl + 12 * (first + d);
+            double* O = Tw + 12 * (first + d);
 #else
 #pragma unroll 1
         for (int d = 0; d < len; ++d) {
-#endif
             const double* L = Xl + 12 * (first + d);
             double* O = Tw + 12 * (first + d);
+#endif
             const double n0 = R0 * L[0] + R1 * L[3] + R2 * L[6];
             const double n1 = R0 * L[1] + R1 * L[4] + R2 * L[7];
             const double n2 = R0 * L[2] + R1 * L[5] + R2 * L[8];
@@ -204,12 +206,13 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
         double Ti[12];
         ld12v(Tw + 12 * lane, Ti);
         double* O = Xl + 12 * lane;
-        if (lane == 0) {
-#pragma unroll
-            for (int e = 0; e < 12; ++e) O[e] = Ti[e];
-        } else {
+        {
+            // the torso (lane 0) keeps its world transform: an identity parent gives exactly that (1 x + 0 y + 0 z = x),
+            // without a divergent special case
             double P[12];
-            ld12v(Tw + 12 * frame_parent(lane), P);
+            ld12v(Tw + 12 * (lane == 0 ? 0 : frame_parent(lane)), P);
+#pragma unroll
+            for (int e = 0; e < 12; ++e) P[e] = lane == 0 ? ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0) : P[e];
 #pragma unroll
             for (int r3 = 0; r3 < 3; ++r3) {
 #pragma unroll
@@ -570,6 +573,7 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
     const int yr = lane - ND1;                       // right-hand-side row of this lane (0..9) if >= 0
     const bool yrow = yr >= 0 && yr < NYR;
     const bool isbase = lane >= 12 && lane < ND1;
+    double* const dump = w.red + lane;
 #pragma unroll
     for (int j = 0; j < ND1; ++j) h[j] = 0.0;
 #if LMH_JTJ_DMMA
@@ -713,12 +717,16 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
         const double lika = lane == k ? piva * rsa : sa * rsa;
         const double likb = lane == 6 + k ? pivb * rsb : sb * rsb;
         h[k] = lika; h[6 + k] = likb;
-        if (mrow) {
-            if (lane > k) L1[LD1 * lane + k] = lika;
-            if (lane > 6 + k) L1[LD1 * lane + 6 + k] = likb;
+        {
+            // branch-free stores: a lane with nothing to store writes to its own dump word (w.red is free here)
+            double* pa = (mrow && lane > k) ? L1 + LD1 * lane + k : dump;
+            double* pb = (mrow && lane > 6 + k) ? L1 + LD1 * lane + 6 + k : dump;
+            *pa = lika; *pb = likb;
+            const bool da = lane == k, db = lane == 6 + k;
+            double* pd = da ? w.ladiag + k : db ? w.ladiag + 6 + k : dump;
+            double* pi = da ? w.ladinv + k : db ? w.ladinv + 6 + k : dump;
+            *pd = da ? lika : likb; *pi = da ? rsa : rsb;
         }
-        if (lane == k) { w.ladiag[k] = lika; w.ladinv[k] = rsa; }
-        if (lane == 6 + k) { w.ladiag[6 + k] = likb; w.ladinv[6 + k] = rsb; }
         __syncwarp();
     }
 #if LMH_FACTOR_DMMA
@@ -770,8 +778,14 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
         const double rs = lmh_rsqrt(piv);
         const double lik = lane == k ? piv * rs : s * rs;
         h[k] = lik;
-        if (lane > k && mrow) L1[LD1 * lane + k] = lik;
-        if (lane == k) { w.ladiag[k] = lik; w.ladinv[k] = rs; }
+        {
+            double* pl = (lane > k && mrow) ? L1 + LD1 * lane + k : dump;
+            *pl = lik;
+            const bool dk = lane == k;
+            double* pd = dk ? w.ladiag + k : dump;
+            double* pi = dk ? w.ladinv + k : dump;
+            *pd = lik; *pi = rs;
+        }
         __syncwarp();
     }
     if (yrow) {
@@ -792,17 +806,17 @@ __device__ void qp_backsolve_warp(EnvWS& w, int lane) {
         if (lane == k) ai = xk;
         else if (lane < k) ai -= L1[LD1 * k + lane] * xk;
     }
+    const bool legb = lane >= 6;
 #pragma unroll
     for (int k = 5; k >= 0; --k) {                   // the legs do not see each other: pivots 6 + k and k together
+        // branch-free (selects and an always-valid address): a divergent branch per step costs more than the step
         const double t = ai * invd;
         const double xb = __shfl_sync(0xffffffffu, t, 6 + k), xa = __shfl_sync(0xffffffffu, t, k);
-        if (lane >= 6) {
-            if (lane == 6 + k) ai = xb;
-            else if (lane < 6 + k) ai -= L1[LD1 * (6 + k) + lane] * xb;
-        } else {
-            if (lane == k) ai = xa;
-            else if (lane < k) ai -= L1[LD1 * k + lane] * xa;
-        }
+        const int piv = legb ? 6 + k : k;
+        const double x = legb ? xb : xa;
+        const double l = L1[LD1 * piv + (lane < piv ? lane : piv)];
+        const double upd = ai - l * x;
+        ai = lane == piv ? x : (lane < piv ? upd : ai);
     }
     __syncwarp();
     if (lane < ND1) w.a[qp_orig(lane)] = ai;
