@@ -93,7 +93,7 @@ LMH_HD int frame_joint(int i) {
     if (i == 0 || i == 7 || i == 14) return -1;
     return i < 7 ? i - 1 : i < 14 ? i - 2 : i - 3;
 }
-LMH_HD int frame_parent(int i) { return (i == 1 || i == 8 || i == 15 || i == 20 || i == 25) ? 0 : i - 1; }
+LMH_HD int frame_parent(int i) { return ((0x2108102u >> i) & 1u) ? 0 : i - 1; }     // frames 1, 8, 15, 20, 25 hang off the torso (bit mask: no branches)
 LMH_HD int joint_chain(int a) { return a < 6 ? 0 : a < 12 ? 1 : a < 17 ? 2 : a < 22 ? 3 : 4; }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,7 +370,10 @@ LMH_HD double rot_row(const double* R, int k, const double* x) { return R[3 * k]
 // y = R' x, one component
 LMH_HD double rotT_row(const double* R, int k, const double* x) { return R[k] * x[0] + R[3 + k] * x[1] + R[6 + k] * x[2]; }
 LMH_HD double cross_k(const double* a, const double* b, int k) {
-    return k == 0 ? a[1] * b[2] - a[2] * b[1] : k == 1 ? a[2] * b[0] - a[0] * b[2] : a[0] * b[1] - a[1] * b[0];
+    // all three components, then a select: the lazy form compiles to a branch around each arm's loads
+    const double a0 = a[0], a1 = a[1], a2 = a[2], b0 = b[0], b1 = b[1], b2 = b[2];
+    const double c0 = a1 * b2 - a2 * b1, c1 = a2 * b0 - a0 * b2, c2 = a0 * b1 - a1 * b0;
+    return k == 0 ? c0 : k == 1 ? c1 : c2;
 }
 // Motion transform of the reference, X = [[E,0],[-E p^,E]] with E = R', applied to [w; u] (generalizedFunctions.cpp:11-19)
 LMH_HD double xmotion_k(const double* Rp, const double* m, int k) {
@@ -883,9 +886,10 @@ LMH_HDN int mpc_window_sums(const Cx& cx, EnvWS& w, const Consts& K, const Plan&
         // the sixteen partial sums of an axis take the same number of turns (a short one adds 0 x z[0]): no divergent exit
         for (int i0 = 0; i0 < n1; i0 += 16) {
             const int i = i0 + part;
-            const bool on = i < n1;
-            const double r = on ? mr[on ? i : 0] : 0.0;
-            s += r * z[on ? i : 0];
+            const int ii = i < n1 ? i : n1 - 1;
+            double r = mr[ii];
+            r = i < n1 ? r : 0.0;
+            s += r * z[ii];
         }
         w.red[it] = s;
     }
@@ -1054,7 +1058,8 @@ LMH_HDN void assemble_ga_phase(const Cx& cx, EnvWS& w, const Consts& K) {
                 sj += jv * (w.Jpqp[6 * f + k] - w.footAccRef[6 * f + k]);
             }
         }
-        double wj = i < 3 ? K.wBasePos : i < 6 ? K.wBaseAng : K.wJoints;
+        const double wbp = K.wBasePos, wba = K.wBaseAng, wjn = K.wJoints;
+        const double wj = i < 3 ? wbp : i < 6 ? wba : wjn;
         w.ga[i] = s - wj * w.qppRef[i] + K.wFoot * sj;
     }
     cx.sync();
@@ -1768,7 +1773,10 @@ LMH_HDN void qp_phase(const Cx& cx, EnvWS& w, const Consts& K, bool factor_done)
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(ua), "+d"(ub) : "d"(di), "d"(jb[f][kt]));
                 }
                 const bool on = (contact >> f) & 1;
-                if (inr && inc) { U[36 * f + 6 * fr + c0] = on ? ua : 0.0; U[36 * f + 6 * fr + c0 + 1] = on ? ub : 0.0; }
+                {
+                    double* pu = (inr && inc) ? U + 36 * f + 6 * fr + c0 : w.red + 2 * (lane & 15);     // (dump: w.red is free here)
+                    pu[0] = on ? ua : 0.0; pu[1] = on ? ub : 0.0;
+                }
             }
             __syncwarp();
             LMH_UNROLL
@@ -2135,7 +2143,8 @@ LMH_HDN void rk4_step(const Cx& cx, EnvWS& w, double* x, double* kacc, double& t
             if (Cx::NT == 32) {
                 const int i = cx.tid;
                 // NaN-propagating maxima (fmax would drop a NaN torque): a non-finite torque must fail the health test
-                const double ti = i < NJ ? fabs(w.tau[i]) : 0.0, ai = i < NQ ? fabs(w.xdot[NQ + i]) : 0.0;
+                const double tv = fabs(w.tau[i < NJ ? i : 0]), av = fabs(w.xdot[NQ + (i < NQ ? i : 0)]);
+                const double ti = i < NJ ? tv : 0.0, ai = i < NQ ? av : 0.0;
                 const double tm = warp_max(ti == ti ? ti : 1e300), am = warp_max(ai == ai ? ai : 1e300);
                 if (i == 0) { w.acc_tau = tm; w.acc_qpp = am; }
             } else

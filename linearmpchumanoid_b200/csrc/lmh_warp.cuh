@@ -700,7 +700,8 @@ __device__ void qp_factor_warp(EnvWS& w, const Consts& K, int lane) {
 #endif
     if (mrow) {
         const int o = qp_orig(lane);
-        const double wj = o < 3 ? K.wBasePos : o < 6 ? K.wBaseAng : K.wJoints;
+        const double wbp = K.wBasePos, wba = K.wBaseAng, wjn = K.wJoints;
+        const double wj = o < 3 ? wbp : o < 6 ? wba : wjn;
 #pragma unroll
         for (int j = 0; j < ND1; ++j) h[j] += dsel(j == lane, wj, 0.0);
     }
