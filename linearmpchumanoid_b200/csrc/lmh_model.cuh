@@ -178,6 +178,7 @@ struct EnvWS {
     double acc_tau, acc_qpp;       // step in flight: max |tau|, max |qpp| of its first stage
     StatsAcc stats;                // running statistics (rollout kernels)
     int32_t acc_iters, acc_fails, acc_nfall, acc_pad;
+    alignas(16) double dump[4];    // where a lane with nothing to store writes (branch-free conditional stores); never read
 #if defined(LMH_TIMELINE)
     double stamp[16];              // debug build: clock64 at the phase boundaries of the last stage evaluated
 #endif

@@ -185,19 +185,21 @@ __device__ void fk_chain_warp(EnvWS& w, const Consts& K, int lane) {
         for (int d = 0; d < MAXDEPTH; ++d) {
             if (d >= len) break;
             const double* L = Xl + 12 * (first + d);
-            double* O = Tw + 12 * (first + d);
+            double* O3 = Tw + 12 * (first + d) + 3 * r3;
+            double* O9 = Tw + 12 * (first + d) + 9 + r3;
 #else
 #pragma unroll 1
         for (int d = 0; d < len; ++d) {
             const double* L = Xl + 12 * (first + d);
-            double* O = Tw + 12 * (first + d);
+            double* O3 = Tw + 12 * (first + d) + 3 * r3;
+            double* O9 = Tw + 12 * (first + d) + 9 + r3;
 #endif
             const double n0 = R0 * L[0] + R1 * L[3] + R2 * L[6];
             const double n1 = R0 * L[1] + R1 * L[4] + R2 * L[7];
             const double n2 = R0 * L[2] + R1 * L[5] + R2 * L[8];
             pp = R0 * L[9] + R1 * L[10] + R2 * L[11] + pp;
             R0 = n0; R1 = n1; R2 = n2;
-            O[3 * r3] = R0; O[3 * r3 + 1] = R1; O[3 * r3 + 2] = R2; O[9 + r3] = pp;
+            O3[0] = R0; O3[1] = R1; O3[2] = R2; *O9 = pp;
         }
     }
     __syncwarp();
@@ -300,10 +302,10 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         const double colv = dsel(lin, dsel(r == 3, nv[4], nv[3]), dsel(r == 0, nv[1], nv[0]));
         xa += (csgn * colv) * qd;
         const double hb = Irow[0] * nv[0] + Irow[1] * nv[1] + Irow[2] * nv[2] + Irow[3] * nv[3] + Irow[4] * nv[4] + Irow[5] * nv[5];
-        if (act) {
-            S.hbuf[c8 + r] = hb;
-            S.abuf[cur ^ 1][c8 + r] = xa;
-            if (d == 7) S.accs[6 * L.c + r] = xa;    // sole frames (legs only): spatial acceleration for Jdot*qdot
+        {   // branch-free conditional stores (a lane with nothing to store writes to the dump word)
+            *(act ? S.hbuf + c8 + r : w.dump) = hb;
+            *(act ? S.abuf[cur ^ 1] + c8 + r : w.dump) = xa;
+            *((act && d == 7) ? S.accs + 6 * L.c + r : w.dump) = xa;    // sole frames (legs only): spatial acceleration for Jdot*qdot
         }
         __syncwarp();
         {
@@ -336,8 +338,10 @@ __device__ void rnea_warp(EnvWS& w, const Consts& K, const double* Isp, const La
         const double rf = g0 * f[3] + g1 * f[4] + g2 * f[5];
         const double rf1 = __shfl_sync(0xffffffffu, rf, src1), rf2 = __shfl_sync(0xffffffffu, rf, src2);
         const double o = dsel(lin, rf, g0 * f[0] + g1 * f[1] + g2 * f[2] + (X[9 + k1] * rf2 - X[9 + k2] * rf1));
-        if (on) {
-            if (d > 1) S.frc[8 * (i - 1) + r] += o; else S.contrib[c8 + r] = o;
+        {
+            double* pf = (on && d > 1) ? S.frc + 8 * (i - 1) + r : w.dump + 1;
+            *pf = *pf + o;
+            *((on && d == 1) ? S.contrib + c8 + r : w.dump) = o;
         }
         __syncwarp();
     }
