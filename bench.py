@@ -49,11 +49,11 @@ STATE_BYTES_PER_ENV = (60 + 30 + 1) * 8 * 2 + 48 + 24   # state read+write, stat
 # dram__bytes_read.sum + dram__bytes_write.sum of rollout_kernel_multi from the committed ncu --set full captures (the
 # traffic of a launch does not depend on the number of steps it fuses: the state stays on chip).  Walking reads each
 # environment's own plan (ZMP reference + per-phase foot polynomials) as well.
-NCU_DRAM_BYTES_PER_LAUNCH = {"push": 3570688 + 0, "walk": 68395520 + 2939904, "sweep": None}
+NCU_DRAM_BYTES_PER_LAUNCH = {"push": 3572224 + 0, "walk": 68396544 + 2678272, "sweep": None}
 NCU_TRAFFIC_SOURCE = {"push": "profiles/r02_rollout_push.txt: dram read 3.57 MB + write 0 for a 10-step launch of 4096 envs "
                               "(algorithmic: 6.3 MB of state and statistics per launch, independent of the step count; the "
                               "written state was still in the 126 MB L2 when the kernel ended)",
-                      "walk": "profiles/r02_rollout_walk.txt: dram read 68.4 MB + write 2.9 MB for a 10-step launch of 16384 envs "
+                      "walk": "profiles/r02_rollout_walk.txt: dram read 68.4 MB + write 2.7 MB for a 10-step launch of 16384 envs "
                               "(algorithmic: 25 MB of state and statistics + 16384 plans x 9 KB = 147 MB if every plan were read whole; "
                               "a 10-step launch touches only the current ZMP window and phase)",
                       "sweep": "no capture of the 32768-environment sweep launch (same kernel and plan layout as the walking workload)"}

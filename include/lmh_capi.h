@@ -49,7 +49,7 @@ typedef struct {
                               0 = as many as the shared memory holds (the default: the throughput kernel, results
                               independent of batch size and sharding bit for bit), 1..that many = fewer;
                               -1 = LATENCY MODE for a handful of environments: one environment per block plus two helper
-                              warps (RNEA, CRBA and the sole Jacobians + MPC / PD references side by side): 55 instead of 71 us per RK4 step
+                              warps (RNEA, CRBA and the sole Jacobians + MPC / PD references side by side): 46 instead of 62 us per RK4 step
                               at one environment; agrees with the default to rounding, not bit for bit */
     int32_t placement;     /* 0 = lmh_set_pushes places environments that are pushed at the same step in the same
                               block (default; results do not depend on it), 1 = keep the index order */

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(32 * kMaxEpb, 1) rollout_kernel_multi(Params p
 // Latency mode (LmhConfig.envs_per_block = -1, meant for a handful of environments): one environment per block of three
 // warps.  Warp 0 is the environment's warp and runs the whole step; while it runs the RNEA, warp 1 computes the CRBA and
 // warp 2 the sole Jacobians and then what of the MPC / PD phase needs no dynamics: ZMP window sums, joint PD, foot references
-// (the three only read the transforms; their outputs and scratch are disjoint): 55 us instead of 71 us per RK4 step of a
+// (the three only read the transforms; their outputs and scratch are disjoint): 46 us instead of 62 us per RK4 step of a
 // single environment.  Every phase is the same source on the same data, but this is another
 // kernel: the compiler contracts a few sums of products differently, so results agree with the throughput kernel to
 // rounding (1e-12 after 50 pushed steps), not bit for bit -- which is why it is opt-in and the default path is one kernel
